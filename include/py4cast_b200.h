@@ -1,0 +1,273 @@
+/*
+ * py4cast_b200 — C ABI of the B200 (sm_100a) kernels behind py4cast's
+ * autoregressive-training hot path.
+ *
+ * Drop-in boundary: every entry point takes plain device pointers, sizes and a
+ * cudaStream_t (as void*); no torch types.  The reference is pure Python on
+ * PyTorch, so each entry point replaces a *group of ATen calls* made by the
+ * reference (file:line cited per function, relative to the reference tree) and
+ * is bound from Python with ctypes (py4cast_b200/_lib.py).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise;
+ *   - `dtype`: P4C_F32 (float) or P4C_BF16 (__nv_bfloat16) = storage type of
+ *     activation tensors; all arithmetic is fp32 (accumulation included);
+ *   - return value: 0 on success, negative P4C_E* on error; the message of the
+ *     last error of the calling thread is returned by p4c_last_error();
+ *   - no entry point synchronises the stream or allocates memory; every one
+ *     is CUDA-graph capturable; workspaces are caller-provided;
+ *   - no atomics on floating-point data anywhere: results are bit-reproducible
+ *     run to run for a fixed launch configuration.
+ */
+#ifndef PY4CAST_B200_H
+#define PY4CAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P4C_F32 0
+#define P4C_BF16 1
+
+#define P4C_OK 0
+#define P4C_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define P4C_ECUDA (-2)    /* CUDA runtime error (launch failure, ...)     */
+#define P4C_ENOSPACE (-3) /* caller-provided workspace too small          */
+
+#define P4C_HIDDEN 64      /* hidden width of every fused MLP (hidden_dims) */
+#define P4C_MAX_SRC 3      /* input segments of a fused MLP                 */
+#define P4C_MAX_PREV 8     /* max input time steps of the AR concat         */
+
+const char* p4c_last_error(void);
+int p4c_version(void);
+/* number of kernels launched by this library since load / last reset (host counter) */
+int64_t p4c_launch_count(void);
+void p4c_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * CSR construction (bit-exact w.r.t. a stable sort by key).
+ * Replaces PyG's implicit COO handling inside mfai InteractionNet
+ * (scatter over `edge_index[1]`).
+ *   keys    [E]  int64, values in [0, num_keys)
+ *   rowptr  [num_keys+1] int32 out
+ *   perm    [E]  int32 out: edge ids grouped by key, ascending edge id inside a group
+ *   scratch [E + num_keys + 1] int32 workspace
+ * ---------------------------------------------------------------------- */
+int p4c_csr_build(const int64_t* keys, int64_t E, int32_t num_keys, int32_t* rowptr,
+                  int32_t* perm, int32_t* scratch, void* stream);
+
+/* int64 -> int32 narrowing copy of an index vector (edge_index rows). */
+int p4c_index_to_i32(const int64_t* src, int32_t* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Deterministic segment sum:  out[b, s, :] (+)= scale_s * sum_{j in [rowptr[s], rowptr[s+1])} src[b, perm[j], :]
+ * (perm == NULL  =>  rows of a segment are contiguous: src[b, j, :]).
+ * Replaces scatter_add / index_add_ of InteractionNet.aggregate (K3) and the
+ * transposed scatters of its backward.  Row width is P4C_HIDDEN.
+ *   mean != 0  => scale_s = 1 / max(1, segment length)  (PyG "mean" aggregation)
+ *   accumulate != 0 => out += result
+ * ---------------------------------------------------------------------- */
+int p4c_segment_sum(const void* src, int64_t src_batch_stride, const int32_t* rowptr,
+                    const int32_t* perm, int32_t num_seg, int32_t batch, void* out,
+                    int64_t out_batch_stride, int mean, int accumulate, int dtype,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused 2-layer MLP:  y = [LayerNorm]( W2 * SiLU(W1 * x + b1) + b2 ) [+ residual]
+ * with x = concat of up to 3 (optionally gathered) row segments.
+ * Replaces, per call, the ATen chain index_select x2 + cat + Linear + SiLU +
+ * Linear + LayerNorm (+ add) of mfai make_mlp / InteractionNet (K1,K2,K4,K5,K6).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;      /* rows of `width` contiguous elements, row stride `ld` elements */
+  const int32_t* index; /* optional gather index [rows] into this source (NULL = identity) */
+  int64_t batch_stride; /* elements between samples (0 = shared by all samples)  */
+  int32_t ld;
+  int32_t width;
+} p4c_src_t;
+
+typedef struct {
+  int32_t rows;  /* rows per sample (E or N) */
+  int32_t batch; /* samples                  */
+  int32_t nsrc;  /* 1..3; if nsrc > 1 every width must be P4C_HIDDEN */
+  int32_t k1;    /* sum of widths (input features of layer 1)        */
+  int32_t out_features; /* <= 64; must be 64 when layer_norm          */
+  int32_t layer_norm;
+  int32_t dtype; /* storage type of sources, outputs, saved activations */
+  int32_t full_rows; /* rows per sample of the output-like arrays (out, out2, residual, saved
+                        activations, dy_b, dh1, dx): 0 = `rows`; > rows when this call covers a
+                        row sub-range of bigger tensors (pointers pre-offset by the caller) */
+  p4c_src_t src[P4C_MAX_SRC];
+  const float* w1; /* [64][k1]  (nn.Linear layout: out, in) */
+  const float* b1; /* [64]                                  */
+  const float* w2; /* [out_features][64]                    */
+  const float* b2; /* [out_features]                        */
+  const float* gamma; /* [64] or NULL */
+  const float* beta;  /* [64] or NULL */
+  float ln_eps;
+} p4c_mlp_t;
+
+/*   residual  : optional [batch][rows][out_features] added to the output (K4 "rec + aggr_mlp(..)")
+ *   out       : [batch][rows][out_features]
+ *   out2      : optional, = src[0] row (identity index) + y   (K5 edge update "edge + msg")
+ *   save_h1   : optional [batch][rows][64] pre-activation of layer 1 (for backward)
+ *   save_stats: optional [batch][rows][2] float (mean, rstd of the LayerNorm input)
+ */
+int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,
+                    void* save_h1, float* save_stats, void* stream);
+
+/* Backward.
+ *   dy_a (+ dy_b): gradient w.r.t. y; dy_a may be gathered through dy_a_index
+ *                  (rows -> row of dy_a, e.g. d_aggr[receiver[e]]) and scaled per
+ *                  row by dy_a_scale[index] (mean aggregation); dy_b optional, identity rows.
+ *   dh1_out      : optional [batch][rows][64] gradient w.r.t. layer-1 pre-activation
+ *                  (consumed by p4c_segment_sum + p4c_rows_matmul for gathered sources)
+ *   dx[i]        : optional gradient w.r.t. source i (identity-indexed sources only),
+ *                  [batch][rows][width_i] with row stride dx_ld[i]; dx_accumulate[i] != 0 => +=
+ *   wgrad_partials: workspace, p4c_mlp_wgrad_partial_floats(m) floats; reduced (in a fixed
+ *                  order) into the g_* buffers ( += ) by the same call.
+ */
+typedef struct {
+  const void* dy_a;
+  const int32_t* dy_a_index;
+  const float* dy_a_scale;
+  int64_t dy_a_batch_stride;
+  const void* dy_b;
+  const void* h1;        /* saved by forward */
+  const float* stats;    /* saved by forward (layer_norm only) */
+  void* dh1_out;
+  void* dx[P4C_MAX_SRC];
+  int32_t dx_ld[P4C_MAX_SRC];
+  int32_t dx_accumulate[P4C_MAX_SRC];
+  int32_t dx0_add_dy; /* 1: dx[0] += dy_b ; 2: dx[0] += dy_a + dy_b (src[0] is also the residual) */
+  float* g_w1; float* g_b1; float* g_w2; float* g_b2; float* g_gamma; float* g_beta;
+  float* wgrad_partials;
+  int64_t wgrad_partials_floats;
+} p4c_mlp_bwd_t;
+
+int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m);
+int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream);
+
+/* out[b, r, :] (+)= in[b, r, :] (64 wide) x W[:, col0 : col0+64]  with W = w1 [64][k1]
+ * i.e. the input-gradient of one 64-wide input segment from (segment-summed) dh1.
+ * Used for the sender / receiver gradients of the edge MLP (linearity of dX = dh1 W1). */
+int p4c_rows_matmul(const void* in, int64_t in_batch_stride, const float* w, int32_t k1,
+                    int32_t col0, int32_t rows, int32_t batch, void* out,
+                    int64_t out_batch_stride, int accumulate, int dtype, void* stream);
+
+/* sum over the batch dimension: out[r, :] (+)= sum_b in[b, r, :]   (width elements per row) */
+int p4c_batch_sum(const void* in, int64_t batch_stride, int32_t batch, int64_t n, void* out,
+                  int accumulate, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AR step (reference py4cast/lightning.py:565-662).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;
+  int32_t nodes;        /* N (grid points; H*W for conv layouts) */
+  int32_t f_state;      /* F   */
+  int32_t f_static;     /* F_s */
+  int32_t f_forcing;    /* F_f */
+  int32_t num_prev;     /* T_in */
+  const float* prev[P4C_MAX_PREV];      /* prev[t]: [batch][nodes][F], oldest first  */
+  int64_t prev_batch_stride[P4C_MAX_PREV];
+  const float* stat;     /* [batch?][nodes][F_s] */
+  int64_t stat_batch_stride; /* 0 if shared */
+  const float* forcing;  /* [batch][nodes][F_f] for the step the x is built for */
+  int64_t forcing_batch_stride;
+} p4c_ar_x_t;
+
+/* x[b,n,:] = cat(prev[0..T_in-1], static, forcing)      (lightning.py:711-767 `_next_x`)
+ * x: [batch][nodes][T_in*F + F_s + F_f] of `x_dtype`. */
+int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream);
+
+/* new_state = border*truth + interior*(prev_last + y*std + mean)   (lightning.py:598-633)
+ *   scale_y == 0      => predicted = prev_last + y                  (diff_ar, :623)
+ *   truth/border NULL => new_state = predicted                      (inference or diff_ar)
+ * new_state is written with batch stride new_state_batch_stride (a slot of the (B,T,N,F)
+ * prediction slab, replacing torch.stack at :660).  If `next` != NULL the x of the NEXT
+ * model call is produced in the same pass: next->prev[T_in-1] is ignored and replaced by
+ * new_state.                                                                             */
+int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev_last,
+                        int64_t prev_last_batch_stride, const float* truth,
+                        int64_t truth_batch_stride, const float* border /*[nodes]*/,
+                        const float* diff_std /*[F] or NULL*/, const float* diff_mean,
+                        int32_t batch, int32_t nodes, int32_t f_state, float* new_state,
+                        int64_t new_state_batch_stride, const p4c_ar_x_t* next, void* x_next,
+                        int x_dtype, void* stream);
+
+/* Backward of p4c_ar_step_forward, for the autograd node
+ *     (y, prev[0..T_in-1]) -> (new_state, x_next).
+ *   g_new   : gradient w.r.t. new_state from its other consumers ([batch][nodes][F], may be NULL)
+ *   g_xnext : gradient w.r.t. x_next ([batch][nodes][f_in] of x_dtype, may be NULL)
+ *   G = g_new + g_xnext[slot T_in-1];  dy = G*interior*(std);
+ *   d_prev[T_in-1] = G*interior + g_xnext[slot T_in-2]   (prev_last is also copied into x_next)
+ *   d_prev[t]      = g_xnext[slot t-1]   for 1 <= t <= T_in-2;   d_prev[0] unused (T_in >= 2).
+ *   d_prev: HOST array of T_in device pointers (NULL entries are skipped); all outputs are
+ *   written, not accumulated. */
+int p4c_ar_step_backward(const float* g_new, int64_t g_new_batch_stride, const void* g_xnext,
+                         int x_dtype, const float* border, const float* diff_std,
+                         int32_t batch, int32_t nodes, int32_t f_state, int32_t num_prev,
+                         int32_t f_in, void* dy, int y_dtype, float* const* d_prev,
+                         void* stream);
+
+/* ------------------------------------------------------------------------
+ * Losses (reference py4cast/losses.py:103-210).
+ *   kind: 0 = MSELoss, 1 = L1Loss
+ *   form: 0 = WeightedLoss        -> out [BT]      (losses.py:130-169)
+ *         1 = ScaledLoss          -> out [BT][F]   (losses.py:186-210, sqrt iff MSE)
+ *         2 = WeightedLoss, reduce_spatial_dim=False -> out [BT][N]  (losses.py:152-154)
+ *   pred/target: [BT][N][F] fp32;  mask: same shape fp32 or NULL (= all ones, lightning.py:797)
+ *   interior: [N] fp32 (any per-pixel weight);  w: [F]
+ *   denom: num_interior - #{pixels masked in every sample/step/feature} — computed by
+ *          p4c_loss_denominator into a device float (losses.py:156,164-167).
+ *   partials: workspace of p4c_loss_partial_floats(...) floats.
+ * ---------------------------------------------------------------------- */
+int p4c_loss_denominator(const float* mask, int64_t bt, int32_t nodes, int32_t f,
+                         float num_interior, float* denom_out, int32_t* scratch /*[nodes]*/,
+                         void* stream);
+int64_t p4c_loss_partial_floats(int64_t bt, int32_t nodes, int32_t f, int form);
+int p4c_loss_forward(const float* pred, const float* target, const float* mask,
+                     const float* interior, const float* w, const float* denom, int64_t bt,
+                     int32_t nodes, int32_t f, int kind, int form, float* partials,
+                     float* out, void* stream);
+/* dpred = d(sum(gout * out))/dpred ; gout has the shape of `out`; `out` = forward result
+ * (needed for form 1 + MSE).  dtarget (optional) receives -dpred-equivalent gradient. */
+int p4c_loss_backward(const float* pred, const float* target, const float* mask,
+                      const float* interior, const float* w, const float* denom,
+                      const float* gout, const float* out, int64_t bt, int32_t nodes,
+                      int32_t f, int kind, int form, float* dpred, float* dtarget,
+                      void* stream);
+
+/* ------------------------------------------------------------------------
+ * Optimiser: AdamW on one flat fp32 buffer (reference lightning.py:442-467:
+ * torch.optim.AdamW + cosine-with-min-lr schedule with warm-up).
+ * `state` is a device struct advanced by p4c_adamw_advance (one tiny kernel, so the
+ * whole step is CUDA-graph replayable without host-side scalar updates).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int64_t step;        /* optimiser steps taken so far           */
+  float lr;            /* learning rate for the current step     */
+  float bias1;         /* 1 - beta1^step                         */
+  float bias2;         /* 1 - beta2^step                         */
+  float _pad;
+} p4c_adamw_state_t;
+
+int p4c_adamw_advance(p4c_adamw_state_t* state, float base_lr, float min_lr,
+                      int64_t warmup_steps, int64_t total_steps, float beta1, float beta2,
+                      void* stream);
+int p4c_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, const p4c_adamw_state_t* state, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_scale, void* stream);
+
+/* utility: y = x cast (fp32 <-> bf16), n elements */
+int p4c_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* utility: dst[i] = a[i] + b[i] (fp32), used for gradient fan-in without ATen */
+int p4c_add(const void* a, const void* b, void* dst, int64_t n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PY4CAST_B200_H */

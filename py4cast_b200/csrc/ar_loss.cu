@@ -1,0 +1,559 @@
+// AR-step state update / input concatenation, losses and the flat AdamW step.
+//
+// Streaming (HBM-bound) kernels: flat, fully coalesced indexing over the innermost
+// (node, feature) plane; reductions use fixed-order trees (no float atomics).
+//
+// Reference lines replaced (relative to the reference tree):
+//   p4c_ar_concat         py4cast/lightning.py:711-767  (_next_x: select x T_in + cat)
+//   p4c_ar_step_forward   py4cast/lightning.py:598-662  (clone, scaled/diff update, border blend,
+//                                                        prev-state roll, torch.stack slot)
+//   p4c_loss_*            py4cast/losses.py:130-169 (WeightedLoss), :186-210 (ScaledLoss)
+//   p4c_adamw_*           py4cast/lightning.py:442-467  (torch.optim.AdamW + cosine/min-lr schedule)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace p4c {
+
+struct ArX {
+  p4c_ar_x_t a;
+};
+
+template <typename TX>
+__device__ __forceinline__ float ar_x_value(const p4c_ar_x_t& a, int b, int n, int k,
+                                            bool* is_last_slot, int* f_out) {
+  const int F = a.f_state;
+  const int ks = a.num_prev * F;
+  *is_last_slot = false;
+  if (k < ks) {
+    const int t = k / F, f = k - t * F;
+    if (t == a.num_prev - 1) {
+      *is_last_slot = true;
+      *f_out = f;
+      return 0.f;
+    }
+    return a.prev[t][(long long)b * a.prev_batch_stride[t] + (long long)n * F + f];
+  }
+  k -= ks;
+  if (k < a.f_static) return a.stat[(long long)b * a.stat_batch_stride + (long long)n * a.f_static + k];
+  k -= a.f_static;
+  return a.forcing[(long long)b * a.forcing_batch_stride + (long long)n * a.f_forcing + k];
+}
+
+template <typename TX>
+__global__ void __launch_bounds__(256)
+ar_concat_kernel(const p4c_ar_x_t a, TX* __restrict__ x) {
+  const int F = a.f_state;
+  const int f_in = a.num_prev * F + a.f_static + a.f_forcing;
+  const long long per_b = (long long)a.nodes * f_in;
+  const long long total = per_b * a.batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long rem = i - (long long)b * per_b;
+    const int n = (int)(rem / f_in), k = (int)(rem - (long long)n * f_in);
+    bool last;
+    int f;
+    float v = ar_x_value<TX>(a, b, n, k, &last, &f);
+    if (last) {
+      const int t = a.num_prev - 1;
+      v = a.prev[t][(long long)b * a.prev_batch_stride[t] + (long long)n * F + f];
+    }
+    x[i] = from_f32<TX>(v);
+  }
+}
+
+struct ArStep {
+  const void* y;
+  const float* prev_last;
+  long long prev_last_bs;
+  const float* truth;
+  long long truth_bs;
+  const float* border;
+  const float* std_;
+  const float* mean_;
+  int batch, nodes, F;
+  float* new_state;
+  long long new_state_bs;
+};
+
+template <typename TY>
+__device__ __forceinline__ float ar_new_state(const ArStep& s, int b, int n, int f) {
+  const long long o = (long long)n * s.F + f;
+  const float yv = to_f32<TY>(reinterpret_cast<const TY*>(s.y)[(long long)b * s.nodes * s.F + o]);
+  const float pl = s.prev_last[(long long)b * s.prev_last_bs + o];
+  float pred = s.std_ ? pl + yv * s.std_[f] + s.mean_[f] : pl + yv;
+  if (s.border) {
+    const float bm = s.border[n];
+    // same expression as the reference: border*truth + interior*pred, interior = 1 - border
+    pred = bm * s.truth[(long long)b * s.truth_bs + o] + (1.0f - bm) * pred;
+  }
+  return pred;
+}
+
+// update only (last AR step: no next x)
+template <typename TY>
+__global__ void __launch_bounds__(256) ar_update_kernel(const ArStep s) {
+  const long long per_b = (long long)s.nodes * s.F;
+  const long long total = per_b * s.batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long rem = i - (long long)b * per_b;
+    const int n = (int)(rem / s.F), f = (int)(rem - (long long)n * s.F);
+    s.new_state[(long long)b * s.new_state_bs + rem] = ar_new_state<TY>(s, b, n, f);
+  }
+}
+
+// update + concat of the next model input in one pass over x_next
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256)
+ar_step_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x) {
+  const int F = a.f_state;
+  const int f_in = a.num_prev * F + a.f_static + a.f_forcing;
+  const long long per_b = (long long)a.nodes * f_in;
+  const long long total = per_b * a.batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long rem = i - (long long)b * per_b;
+    const int n = (int)(rem / f_in), k = (int)(rem - (long long)n * f_in);
+    bool last;
+    int f;
+    float v = ar_x_value<TX>(a, b, n, k, &last, &f);
+    if (last) {
+      v = ar_new_state<TY>(s, b, n, f);
+      s.new_state[(long long)b * s.new_state_bs + (long long)n * F + f] = v;
+    }
+    x[i] = from_f32<TX>(v);
+  }
+}
+
+struct ArBwd {
+  const float* g_new;
+  long long g_new_bs;
+  const void* g_x;
+  const float* border;
+  const float* std_;
+  int batch, nodes, F, num_prev, f_in;
+  void* dy;
+  float* d_prev[P4C_MAX_PREV];
+};
+
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256) ar_step_bwd_kernel(const ArBwd s) {
+  const long long per_b = (long long)s.nodes * s.F;
+  const long long total = per_b * s.batch;
+  const TX* gx = reinterpret_cast<const TX*>(s.g_x);
+  TY* dy = reinterpret_cast<TY*>(s.dy);
+  const int T = s.num_prev;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long rem = i - (long long)b * per_b;
+    const int n = (int)(rem / s.F), f = (int)(rem - (long long)n * s.F);
+    const long long xrow = ((long long)b * s.nodes + n) * s.f_in;
+    float G = s.g_new ? s.g_new[(long long)b * s.g_new_bs + rem] : 0.f;
+    if (gx) G += to_f32<TX>(gx[xrow + (long long)(T - 1) * s.F + f]);
+    const float interior = s.border ? 1.0f - s.border[n] : 1.0f;
+    const float gi = G * interior;
+    dy[i] = from_f32<TY>(s.std_ ? gi * s.std_[f] : gi);
+    // states copied into x_next slots 0..T-2 are the step inputs prev[1..T-1]
+    float dlast = gi;
+    if (gx && T >= 2) dlast += to_f32<TX>(gx[xrow + (long long)(T - 2) * s.F + f]);
+    if (s.d_prev[T - 1]) s.d_prev[T - 1][i] = dlast;
+    if (gx) {
+      for (int t = 1; t < T - 1; ++t)
+        if (s.d_prev[t]) s.d_prev[t][i] = to_f32<TX>(gx[xrow + (long long)(t - 1) * s.F + f]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ losses
+constexpr int LOSS_NT = 256;
+constexpr int LOSS_CHUNK_ITERS = 64;  // node-iterations per CTA
+
+__device__ __forceinline__ float loss_elem(float p, float t, float m, int kind) {
+  const float d = p * m - t * m;
+  return kind == 0 ? d * d : fabsf(d);
+}
+
+__host__ __device__ inline int loss_nodes_per_iter(int F) { return LOSS_NT / F; }
+__host__ __device__ inline int loss_chunk_nodes(int F) { return loss_nodes_per_iter(F) * LOSS_CHUNK_ITERS; }
+
+// partial[bt][chunk][F]  (per-feature interior-weighted sums, un-normalised)
+__global__ void __launch_bounds__(LOSS_NT)
+loss_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                    const float* __restrict__ mask, const float* __restrict__ interior, int nodes,
+                    int F, int kind, float* __restrict__ partials) {
+  __shared__ float red[LOSS_NT];
+  const int npi = loss_nodes_per_iter(F);
+  const int active = npi * F;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, nchunks = gridDim.x;
+  const long long bt = blockIdx.y;
+  const int n0 = chunk * loss_chunk_nodes(F);
+  const int n1 = min(nodes, n0 + loss_chunk_nodes(F));
+  float acc = 0.f;
+  if (tid < active) {
+    const int f = tid % F, no = tid / F;
+    const long long base = bt * (long long)nodes * F;
+    for (int n = n0 + no; n < n1; n += npi) {
+      const long long idx = base + (long long)n * F + f;
+      const float m = mask ? mask[idx] : 1.0f;
+      acc += interior[n] * loss_elem(pred[idx], target[idx], m, kind);
+    }
+  }
+  red[tid] = acc;
+  __syncthreads();
+  if (tid < F) {
+    float s = 0.f;
+    for (int j = 0; j < npi; ++j) s += red[tid + j * F];
+    partials[(bt * nchunks + chunk) * F + tid] = s;
+  }
+}
+
+// form 0: out[bt] = sum_f w_f * S_f / denom ; form 1: out[bt][f] = w_f * sqrt?(S_f/denom)
+__global__ void loss_finalize_kernel(const float* __restrict__ partials, int nchunks, int F,
+                                     const float* __restrict__ w, const float* __restrict__ denom,
+                                     int kind, int form, float* __restrict__ out) {
+  __shared__ float sf[LOSS_NT];
+  const long long bt = blockIdx.x;
+  const int tid = threadIdx.x;
+  float s = 0.f;
+  if (tid < F) {
+    for (int c = 0; c < nchunks; ++c) s += partials[(bt * nchunks + c) * F + tid];
+    s /= *denom;
+    if (form == 1) {
+      if (kind == 0) s = sqrtf(s);
+      out[bt * F + tid] = s * w[tid];
+    } else {
+      sf[tid] = s * w[tid];
+    }
+  }
+  if (form == 0) {
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int f = 0; f < F; ++f) t += sf[f];
+      out[bt] = t;
+    }
+  }
+}
+
+// form 2: out[bt][n] = sum_f w_f * l(p,t)
+__global__ void loss_map_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                const float* __restrict__ mask, const float* __restrict__ w,
+                                long long rows, int F, int kind, float* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int f = 0; f < F; ++f) {
+      const long long idx = r * F + f;
+      s += w[f] * loss_elem(pred[idx], target[idx], mask ? mask[idx] : 1.0f, kind);
+    }
+    out[r] = s;
+  }
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                const float* __restrict__ mask, const float* __restrict__ interior,
+                                const float* __restrict__ w, const float* __restrict__ denom,
+                                const float* __restrict__ gout, const float* __restrict__ out,
+                                long long bt_total, int nodes, int F, int kind, int form,
+                                float* __restrict__ dpred, float* __restrict__ dtarget) {
+  const long long per_bt = (long long)nodes * F;
+  const long long total = per_bt * bt_total;
+  const float inv_denom = 1.0f / *denom;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long bt = i / per_bt;
+    const long long rem = i - bt * per_bt;
+    const int n = (int)(rem / F), f = (int)(rem - (long long)n * F);
+    const float m = mask ? mask[i] : 1.0f;
+    const float d = pred[i] * m - target[i] * m;
+    float coef;
+    if (form == 0) {
+      coef = gout[bt] * w[f] * interior[n] * inv_denom;
+    } else if (form == 1) {
+      if (kind == 0) {
+        const float o = out[bt * F + f];  // = w_f * sqrt(S_f/denom)
+        coef = o > 0.f ? gout[bt * F + f] * w[f] * w[f] / o * interior[n] * inv_denom * 0.5f : 0.f;
+      } else {
+        coef = gout[bt * F + f] * w[f] * interior[n] * inv_denom;
+      }
+    } else {
+      coef = gout[bt * (long long)nodes + n] * w[f];
+    }
+    const float dl = kind == 0 ? 2.0f * d * m : (d > 0.f ? m : (d < 0.f ? -m : 0.f));
+    const float gval = coef * dl;
+    dpred[i] = gval;
+    if (dtarget) dtarget[i] = -gval;
+  }
+}
+
+// pixels whose mask is zero for every (sample, step, feature)
+__global__ void loss_never_kernel(const float* __restrict__ mask, long long bt, int nodes, int F,
+                                  int* __restrict__ count) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nodes; n += gridDim.x * blockDim.x) {
+    bool any = false;
+    for (long long q = 0; q < bt && !any; ++q)
+      for (int f = 0; f < F; ++f)
+        if (mask[(q * nodes + n) * F + f] != 0.f) { any = true; break; }
+    if (!any) atomicAdd(count, 1);  // integer atomic: order-independent
+  }
+}
+__global__ void loss_denom_kernel(float num_interior, const int* __restrict__ count,
+                                  float* __restrict__ denom) {
+  *denom = num_interior - (count ? (float)*count : 0.f);
+}
+
+// ------------------------------------------------------------------------------- AdamW
+__global__ void adamw_advance_kernel(p4c_adamw_state_t* st, float base_lr, float min_lr,
+                                     long long warmup, long long total_steps, float beta1,
+                                     float beta2) {
+  const long long cur = st->step;  // scheduler step index for this optimiser step
+  double lam;
+  if (cur < warmup) {
+    lam = (double)cur / (double)(warmup > 1 ? warmup : 1);
+  } else {
+    const long long span = total_steps - warmup;
+    const double progress = (double)(cur - warmup) / (double)(span > 1 ? span : 1);
+    double factor = 0.5 * (1.0 + cos(3.14159265358979323846 * progress));
+    const double rate = (double)min_lr / (double)base_lr;
+    factor = factor * (1.0 - rate) + rate;
+    lam = factor > 0.0 ? factor : 0.0;
+  }
+  const long long t = cur + 1;
+  st->step = t;
+  st->lr = (float)((double)base_lr * lam);
+  st->bias1 = (float)(1.0 - pow((double)beta1, (double)t));
+  st->bias2 = (float)(1.0 - pow((double)beta2, (double)t));
+}
+
+__global__ void __launch_bounds__(256)
+adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                  float* __restrict__ v, long long n, const p4c_adamw_state_t* __restrict__ st,
+                  float beta1, float beta2, float eps, float wd, float grad_scale) {
+  const float lr = st->lr, bias1 = st->bias1, bias2 = st->bias2;
+  const float step_size = lr / bias1;
+  const float inv_sqrt_b2 = 1.0f / sqrtf(bias2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float den = sqrtf(vi) * inv_sqrt_b2 + eps;
+    pi -= step_size * (mi / den);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+static int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)kNumSMs * 16;
+  if (g < 1) g = 1;
+  return (int)(g < cap ? g : cap);
+}
+
+static int check_ar_x(const p4c_ar_x_t* a, bool last_may_be_null) {
+  P4C_REQUIRE(a != nullptr, "ar: null descriptor");
+  P4C_REQUIRE(a->batch > 0 && a->nodes > 0 && a->f_state > 0, "ar: empty problem");
+  P4C_REQUIRE(a->num_prev >= 1 && a->num_prev <= P4C_MAX_PREV, "ar: num_prev=%d not in [1,%d]",
+              a->num_prev, P4C_MAX_PREV);
+  for (int t = 0; t < a->num_prev; ++t)
+    P4C_REQUIRE(a->prev[t] != nullptr || (last_may_be_null && t == a->num_prev - 1),
+                "ar: prev[%d] is null", t);
+  P4C_REQUIRE(a->f_static == 0 || a->stat, "ar: static features missing");
+  P4C_REQUIRE(a->f_forcing == 0 || a->forcing, "ar: forcing missing");
+  return P4C_OK;
+}
+
+}  // namespace p4c
+
+using namespace p4c;
+
+extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream) {
+  int rc = check_ar_x(a, false);
+  if (rc) return rc;
+  P4C_REQUIRE(x != nullptr, "ar_concat: x is null");
+  const long long total =
+      (long long)a->batch * a->nodes * (a->num_prev * a->f_state + a->f_static + a->f_forcing);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == P4C_F32)
+    ar_concat_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(*a, (float*)x);
+  else if (x_dtype == P4C_BF16)
+    ar_concat_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(*a, (__nv_bfloat16*)x);
+  else
+    P4C_REQUIRE(false, "ar_concat: bad dtype %d", x_dtype);
+  P4C_CHECK_LAUNCH("ar_concat");
+  return P4C_OK;
+}
+
+extern "C" int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev_last,
+                                   int64_t prev_last_bs, const float* truth, int64_t truth_bs,
+                                   const float* border, const float* diff_std,
+                                   const float* diff_mean, int32_t batch, int32_t nodes,
+                                   int32_t f_state, float* new_state, int64_t new_state_bs,
+                                   const p4c_ar_x_t* next, void* x_next, int x_dtype,
+                                   void* stream) {
+  P4C_REQUIRE(y && prev_last && new_state, "ar_step_forward: null pointer");
+  P4C_REQUIRE(batch > 0 && nodes > 0 && f_state > 0, "ar_step_forward: empty problem");
+  P4C_REQUIRE((border == nullptr) == (truth == nullptr), "ar_step_forward: border and truth go together");
+  P4C_REQUIRE((diff_std == nullptr) == (diff_mean == nullptr), "ar_step_forward: std and mean go together");
+  P4C_REQUIRE(y_dtype == P4C_F32 || y_dtype == P4C_BF16, "ar_step_forward: bad y dtype");
+  ArStep s{y, prev_last, prev_last_bs, truth, truth_bs, border, diff_std, diff_mean,
+           batch, nodes, f_state, new_state, new_state_bs};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!next) {
+    const long long total = (long long)batch * nodes * f_state;
+    if (y_dtype == P4C_F32) ar_update_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(s);
+    else ar_update_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(s);
+    P4C_CHECK_LAUNCH("ar_update");
+    return P4C_OK;
+  }
+  int rc = check_ar_x(next, true);
+  if (rc) return rc;
+  P4C_REQUIRE(x_next != nullptr, "ar_step_forward: x_next is null");
+  P4C_REQUIRE(next->batch == batch && next->nodes == nodes && next->f_state == f_state,
+              "ar_step_forward: next-x descriptor does not match the state shape");
+  P4C_REQUIRE(x_dtype == P4C_F32 || x_dtype == P4C_BF16, "ar_step_forward: bad x dtype");
+  const long long total =
+      (long long)batch * nodes * (next->num_prev * f_state + next->f_static + next->f_forcing);
+  const int grid = grid_for(total, 256);
+  if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
+    ar_step_kernel<float, float><<<grid, 256, 0, st>>>(s, *next, (float*)x_next);
+  else if (y_dtype == P4C_F32 && x_dtype == P4C_BF16)
+    ar_step_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(s, *next, (__nv_bfloat16*)x_next);
+  else if (y_dtype == P4C_BF16 && x_dtype == P4C_F32)
+    ar_step_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(s, *next, (float*)x_next);
+  else
+    ar_step_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(s, *next, (__nv_bfloat16*)x_next);
+  P4C_CHECK_LAUNCH("ar_step");
+  return P4C_OK;
+}
+
+extern "C" int p4c_ar_step_backward(const float* g_new, int64_t g_new_bs, const void* g_xnext,
+                                    int x_dtype, const float* border, const float* diff_std,
+                                    int32_t batch, int32_t nodes, int32_t f_state,
+                                    int32_t num_prev, int32_t f_in, void* dy, int y_dtype,
+                                    float* const* d_prev, void* stream) {
+  P4C_REQUIRE(dy != nullptr, "ar_step_backward: dy is null");
+  P4C_REQUIRE(g_new || g_xnext, "ar_step_backward: no incoming gradient");
+  P4C_REQUIRE(batch > 0 && nodes > 0 && f_state > 0, "ar_step_backward: empty problem");
+  P4C_REQUIRE(num_prev >= 1 && num_prev <= P4C_MAX_PREV, "ar_step_backward: bad num_prev %d", num_prev);
+  P4C_REQUIRE(!g_xnext || f_in >= num_prev * f_state, "ar_step_backward: f_in too small");
+  ArBwd s{};
+  s.g_new = g_new; s.g_new_bs = g_new_bs; s.g_x = g_xnext; s.border = border; s.std_ = diff_std;
+  s.batch = batch; s.nodes = nodes; s.F = f_state; s.num_prev = num_prev; s.f_in = f_in; s.dy = dy;
+  for (int t = 0; t < P4C_MAX_PREV; ++t) s.d_prev[t] = (d_prev && t < num_prev) ? d_prev[t] : nullptr;
+  const long long total = (long long)batch * nodes * f_state;
+  const int grid = grid_for(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool xb = g_xnext && x_dtype == P4C_BF16;
+  if (y_dtype == P4C_F32 && !xb) ar_step_bwd_kernel<float, float><<<grid, 256, 0, st>>>(s);
+  else if (y_dtype == P4C_F32 && xb) ar_step_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(s);
+  else if (y_dtype == P4C_BF16 && !xb) ar_step_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(s);
+  else if (y_dtype == P4C_BF16 && xb) ar_step_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(s);
+  else P4C_REQUIRE(false, "ar_step_backward: bad dtype");
+  P4C_CHECK_LAUNCH("ar_step_bwd");
+  return P4C_OK;
+}
+
+extern "C" int p4c_loss_denominator(const float* mask, int64_t bt, int32_t nodes, int32_t f,
+                                    float num_interior, float* denom_out, int32_t* scratch,
+                                    void* stream) {
+  P4C_REQUIRE(denom_out != nullptr, "loss_denominator: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask) {
+    P4C_REQUIRE(scratch != nullptr && bt > 0 && nodes > 0 && f > 0, "loss_denominator: bad arguments");
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int), st);
+    if (e != cudaSuccess) {
+      set_error("loss_denominator: memset failed: %s", cudaGetErrorString(e));
+      return P4C_ECUDA;
+    }
+    loss_never_kernel<<<grid_for(nodes, 128), 128, 0, st>>>(mask, bt, nodes, f, scratch);
+    P4C_CHECK_LAUNCH("loss_never");
+  }
+  loss_denom_kernel<<<1, 1, 0, st>>>(num_interior, mask ? scratch : nullptr, denom_out);
+  P4C_CHECK_LAUNCH("loss_denom");
+  return P4C_OK;
+}
+
+static int loss_nchunks(int nodes, int F) {
+  const int cn = loss_chunk_nodes(F);
+  return (nodes + cn - 1) / cn;
+}
+
+extern "C" int64_t p4c_loss_partial_floats(int64_t bt, int32_t nodes, int32_t f, int form) {
+  if (form == 2 || f <= 0 || f > LOSS_NT) return 0;
+  return bt * (int64_t)loss_nchunks(nodes, f) * f;
+}
+
+extern "C" int p4c_loss_forward(const float* pred, const float* target, const float* mask,
+                                const float* interior, const float* w, const float* denom,
+                                int64_t bt, int32_t nodes, int32_t f, int kind, int form,
+                                float* partials, float* out, void* stream) {
+  P4C_REQUIRE(pred && target && w && out, "loss_forward: null pointer");
+  P4C_REQUIRE(bt > 0 && nodes > 0 && f > 0 && f <= LOSS_NT, "loss_forward: bad sizes (f must be <= 256)");
+  P4C_REQUIRE(kind == 0 || kind == 1, "loss_forward: kind must be 0 (MSE) or 1 (L1)");
+  P4C_REQUIRE(form >= 0 && form <= 2, "loss_forward: bad form %d", form);
+  P4C_REQUIRE(bt <= 65535, "loss_forward: batch*steps=%lld exceeds 65535", (long long)bt);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (form == 2) {
+    const long long rows = bt * nodes;
+    loss_map_kernel<<<grid_for(rows, 256), 256, 0, st>>>(pred, target, mask, w, rows, f, kind, out);
+    P4C_CHECK_LAUNCH("loss_map");
+    return P4C_OK;
+  }
+  P4C_REQUIRE(interior && denom && partials, "loss_forward: interior / denom / partials missing");
+  const int nchunks = loss_nchunks(nodes, f);
+  dim3 grid(nchunks, (unsigned)bt);
+  loss_partial_kernel<<<grid, LOSS_NT, 0, st>>>(pred, target, mask, interior, nodes, f, kind, partials);
+  P4C_CHECK_LAUNCH("loss_partial");
+  loss_finalize_kernel<<<(unsigned)bt, LOSS_NT, 0, st>>>(partials, nchunks, f, w, denom, kind, form, out);
+  P4C_CHECK_LAUNCH("loss_finalize");
+  return P4C_OK;
+}
+
+extern "C" int p4c_loss_backward(const float* pred, const float* target, const float* mask,
+                                 const float* interior, const float* w, const float* denom,
+                                 const float* gout, const float* out, int64_t bt, int32_t nodes,
+                                 int32_t f, int kind, int form, float* dpred, float* dtarget,
+                                 void* stream) {
+  P4C_REQUIRE(pred && target && w && gout && dpred, "loss_backward: null pointer");
+  P4C_REQUIRE(bt > 0 && nodes > 0 && f > 0, "loss_backward: bad sizes");
+  P4C_REQUIRE(form == 2 || (interior && denom), "loss_backward: interior / denom missing");
+  P4C_REQUIRE(!(form == 1 && kind == 0) || out, "loss_backward: forward output needed for ScaledLoss(MSE)");
+  const long long total = bt * (long long)nodes * f;
+  const float* dn = denom;
+  P4C_REQUIRE(dn != nullptr || form == 2, "loss_backward: denom missing");
+  if (!dn) dn = w;  // form 2 never uses inv_denom's value; any valid address
+  loss_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      pred, target, mask, interior, w, dn, gout, out, bt, nodes, f, kind, form, dpred, dtarget);
+  P4C_CHECK_LAUNCH("loss_bwd");
+  return P4C_OK;
+}
+
+extern "C" int p4c_adamw_advance(p4c_adamw_state_t* state, float base_lr, float min_lr,
+                                 int64_t warmup_steps, int64_t total_steps, float beta1,
+                                 float beta2, void* stream) {
+  P4C_REQUIRE(state != nullptr && base_lr > 0.f, "adamw_advance: bad arguments");
+  adamw_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, base_lr, min_lr, warmup_steps,
+                                                          total_steps, beta1, beta2);
+  P4C_CHECK_LAUNCH("adamw_advance");
+  return P4C_OK;
+}
+
+extern "C" int p4c_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                              int64_t n, const p4c_adamw_state_t* state, float beta1, float beta2,
+                              float eps, float weight_decay, float grad_scale, void* stream) {
+  P4C_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, "adamw_step: bad arguments");
+  adamw_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, weight_decay, grad_scale);
+  P4C_CHECK_LAUNCH("adamw_step");
+  return P4C_OK;
+}
