@@ -125,23 +125,37 @@ class DataParallelTrainer:
         self._static_batch: Optional[ItemBatch] = None
         self._static_loss: Optional[torch.Tensor] = None
 
-    # one optimiser step on `batch` (this rank's shard)
-    def _step_impl(self, batch: ItemBatch) -> torch.Tensor:
-        self.flat.zero_grad()
-        loss = self.lm.training_step(batch, 1)
-        loss.backward()
+    def sync_gradients(self) -> float:
+        """ONE all-reduce (sum) of the flat gradient buffer; returns the scale that turns the sum
+        into DDP's mean over ranks (applied inside the AdamW kernel, not as an extra pass)."""
         if self.world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
-        self.opt.step(grad_scale=1.0 / self.world)  # DDP averages gradients over ranks
+        return 1.0 / self.world
+
+    def _forward_backward(self, batch: ItemBatch) -> torch.Tensor:
+        self.flat.zero_grad()
+        loss = self.lm.training_step(batch, 1)
+        self.lm.training_step_losses.clear()
+        loss.backward()
         return loss.detach()
+
+    # one optimiser step on `batch` (this rank's shard)
+    def _step_impl(self, batch: ItemBatch) -> torch.Tensor:
+        loss = self._forward_backward(batch)
+        self.opt.step(grad_scale=self.sync_gradients())
+        return loss
 
     def train_step(self, batch: ItemBatch) -> torch.Tensor:
         return self._step_impl(_fresh(batch))
 
     # ----------------------------------------------------------------- CUDA graph
-    def capture(self, example: ItemBatch, warmup: int = 2) -> None:
-        """Records one full optimiser step.  `example` fixes the shapes; later batches are
-        copied into the captured input buffers by `replay`."""
+    def capture(self, example: ItemBatch, warmup: int = 1) -> None:
+        """Records zero-grad + forward + loss + backward of one step into a CUDA graph (the
+        gradient all-reduce and the 2-kernel AdamW step stay eager, after the replay).
+        `example` fixes the shapes; `warmup` full steps are run on it first (lazy set-up work —
+        CSR construction, shared-memory opt-in, casts — must not happen under capture)."""
+        if warmup < 1:
+            raise ValueError("at least one warm-up step is needed before capture")
         self._static_batch = _clone_batch(example)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -152,7 +166,7 @@ class DataParallelTrainer:
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._static_loss = self._step_impl(_fresh(self._static_batch))
+            self._static_loss = self._forward_backward(_fresh(self._static_batch))
 
     def load_inputs(self, batch: ItemBatch) -> None:
         """Copies a (host or device) batch into the captured input buffers (H2D when pinned)."""
@@ -162,12 +176,31 @@ class DataParallelTrainer:
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def replay(self, batch: Optional[ItemBatch] = None) -> torch.Tensor:
+        """One optimiser step: graph replay (fwd+bwd) + all-reduce + AdamW."""
         if self._graph is None:
             raise RuntimeError("call capture() first")
         if batch is not None:
             self.load_inputs(batch)
         self._graph.replay()
+        self.opt.step(grad_scale=self.sync_gradients())
         return self._static_loss
+
+
+def shard_indices(num_samples: int, rank: int, world: int) -> list:
+    """Sample i goes to rank i mod world (torch DistributedSampler without shuffling/padding)."""
+    return list(range(rank, num_samples, world))
+
+
+def cosine_min_lr_lambda(step: int, warmup_steps: int, total_steps: int, min_lr_rate: float) -> float:
+    """Host restatement of the schedule p4c_adamw_advance evaluates on the device
+    (transformers.get_cosine_with_min_lr_schedule_with_warmup, num_cycles = 0.5)."""
+    import math
+
+    if step < warmup_steps:
+        return float(step) / float(max(1, warmup_steps))
+    progress = float(step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+    factor = 0.5 * (1.0 + math.cos(math.pi * progress))
+    return max(0.0, factor * (1 - min_lr_rate) + min_lr_rate)
 
 
 def _fresh(batch: ItemBatch) -> ItemBatch:

@@ -18,9 +18,13 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).norm() / den).item()
 
 
+REPORT = []  # (test id, what, error, tolerance) — dumped by conftest at session end
+
+
 def assert_close(a, b, tol, what=""):
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     e = rel_err(a, b)
+    REPORT.append((os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], what, e, tol))
     assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
     return e
 
