@@ -64,13 +64,23 @@ class InteractionNet(nn.Module):
         edge_chunk_sizes: Optional[Sequence[int]] = None,
         aggr_chunk_sizes: Optional[Sequence[int]] = None,
         aggr: str = "sum",
+        num_rec: Optional[int] = None,
     ):
         super().__init__()
         assert aggr in ("sum", "mean")
         hidden_dim = hidden_dim or input_dim
         ei = edge_index.clone()
-        ei = ei - ei.min(dim=1, keepdim=True)[0]  # 0-based both rows
-        self.num_rec = int(ei[1].max()) + 1
+        if num_rec is None:
+            # upstream behaviour (A.2): re-base each row by its minimum, receivers counted from
+            # the largest receiver id.  NOTE: this silently shifts sender ids when the
+            # lowest-numbered sender has no edge — e.g. g2m, where the grid corner nodes lie at
+            # dm/sqrt(2) > 0.67 dm from the nearest mesh node and send nothing.  The models below
+            # therefore pass exact 0-based ids + num_rec (the intended semantics; mfai parity is
+            # unpinned either way, see the header).
+            ei = ei - ei.min(dim=1, keepdim=True)[0]
+            self.num_rec = int(ei[1].max()) + 1
+        else:
+            self.num_rec = int(num_rec)
         ei[0] = ei[0] + self.num_rec  # senders after receivers in cat(rec, send)
         self.register_buffer("edge_index", ei, persistent=False)
         edge_recipe = [3 * input_dim] + [hidden_dim] * (hidden_layers + 1)
@@ -126,11 +136,13 @@ class _BaseGraph(nn.Module):
         self.g2m_embedder = make_mlp([3] + end)
         self.m2g_embedder = make_mlp([3] + end)
         self.g2m_gnn = InteractionNet(
-            _global_ids(graph.g2m), d, hidden_layers=hidden_layers, update_edges=False
+            graph.g2m.edge_index, d, hidden_layers=hidden_layers, update_edges=False,
+            num_rec=graph.g2m.num_rec,
         )
         self.encoding_grid_mlp = make_mlp([d] + end)
         self.m2g_gnn = InteractionNet(
-            _global_ids(graph.m2g), d, hidden_layers=hidden_layers, update_edges=False
+            graph.m2g.edge_index, d, hidden_layers=hidden_layers, update_edges=False,
+            num_rec=graph.m2g.num_rec,
         )
         self.output_map = make_mlp(end + [out_channels], layer_norm=False)
 
@@ -145,12 +157,6 @@ class _BaseGraph(nn.Module):
         mesh_rep = self.process_step(mesh_rep)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, _expand(m2g_emb, B))
         return self.output_map(grid_rep)
-
-
-def _global_ids(edge_set, send_offset=None):
-    """Emit neural-lam style ids (receivers and senders in disjoint ranges are
-    not required: InteractionNet re-bases each row by its own minimum)."""
-    return edge_set.edge_index
 
 
 class GraphLAM(_BaseGraph):
@@ -172,7 +178,8 @@ class GraphLAM(_BaseGraph):
         self.processor = nn.ModuleList(
             [
                 InteractionNet(
-                    graph.m2m[0].edge_index, d, hidden_layers=hidden_layers, aggr=mesh_aggr
+                    graph.m2m[0].edge_index, d, hidden_layers=hidden_layers, aggr=mesh_aggr,
+                    num_rec=graph.m2m[0].num_rec,
                 )
                 for _ in range(processor_layers)
             ]
@@ -210,11 +217,11 @@ class _BaseHiGraph(_BaseGraph):
         self.mesh_up_embedders = nn.ModuleList([make_mlp([3] + self.end) for _ in range(L - 1)])
         self.mesh_down_embedders = nn.ModuleList([make_mlp([3] + self.end) for _ in range(L - 1)])
         self.mesh_init_gnns = nn.ModuleList(
-            [InteractionNet(e.edge_index, d, hidden_layers=hl) for e in graph.mesh_up]
+            [InteractionNet(e.edge_index, d, hidden_layers=hl, num_rec=e.num_rec) for e in graph.mesh_up]
         )
         self.mesh_read_gnns = nn.ModuleList(
             [
-                InteractionNet(e.edge_index, d, hidden_layers=hl, update_edges=False)
+                InteractionNet(e.edge_index, d, hidden_layers=hl, update_edges=False, num_rec=e.num_rec)
                 for e in graph.mesh_down
             ]
         )
@@ -261,7 +268,7 @@ class HiLAM(_BaseHiGraph):
 
         def nets(edge_sets):
             return nn.ModuleList(
-                [InteractionNet(e.edge_index, d, hidden_layers=hl) for e in edge_sets]
+                [InteractionNet(e.edge_index, d, hidden_layers=hl, num_rec=e.num_rec) for e in edge_sets]
             )
 
         self.mesh_down_gnns = nn.ModuleList([nets(graph.mesh_down) for _ in range(processor_layers)])
@@ -315,7 +322,7 @@ class HiLAMParallel(_BaseHiGraph):
                 InteractionNet(
                     total, d, hidden_layers=hl,
                     edge_chunk_sizes=self.edge_split_sections,
-                    aggr_chunk_sizes=self.level_mesh_sizes,
+                    aggr_chunk_sizes=self.level_mesh_sizes, num_rec=offs[-1],
                 )
                 for _ in range(processor_layers)
             ]

@@ -33,7 +33,7 @@ def pytest_sessionfinish(session, exitstatus):
         import torch
 
         tag = "gpu" if torch.cuda.is_available() else "cpu"
-        with open(os.path.join(out, f"parity_report_{tag}.txt"), "w") as f:
+        with open(os.path.join(out, f"parity_report_{tag}.txt"), "a") as f:
             for test, what, err, tol in helpers.REPORT:
                 f.write(f"{err:.3e}\t{tol:.1e}\t{'OK' if err <= tol else 'FAIL'}\t{test}\t{what}\n")
     except Exception as e:  # never mask the test result
