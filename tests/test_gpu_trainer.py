@@ -112,11 +112,13 @@ def test_full_training_steps_vs_oracle_pipeline(cuda, tmp_path, name, strategy):
         if step == 0:
             flat_r = torch.cat([p.grad.flatten() for p in ref.parameters()])
             flat_g = torch.cat([p.grad.flatten().cpu() for p in lm.model.parameters()])
-            assert_close(flat_g, flat_r, 5 * FP32_TOL, f"{name} rollout gradient")
+            assert_close(flat_g, flat_r, FP32_TOL, f"{name} rollout gradient")
         topt.step()
         assert_close(loss.cpu(), rl.detach(), FP32_TOL, f"{name} step {step} loss")
     for (n, p), (_, q) in zip(lm.model.named_parameters(), ref.named_parameters()):
-        assert_close(p.detach().cpu(), q.detach(), 1e-4, f"{name} weights after 2 steps: {n}")
+        # Adam's m/sqrt(v) normalisation amplifies gradient rounding where g ~ 0 (LayerNorm biases
+        # start at 0): weights are compared at 1e-3, gradients and losses above at 1e-5.
+        assert_close(p.detach().cpu(), q.detach(), 1e-3, f"{name} weights after 2 steps: {n}")
 
 
 def test_cuda_graph_replay_equals_eager(cuda, tmp_path):
