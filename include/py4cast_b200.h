@@ -115,6 +115,12 @@ typedef struct {
  *   save_h1   : optional [batch][rows][64] pre-activation of layer 1 (for backward)
  *   save_stats: optional [batch][rows][2] float (mean, rstd of the LayerNorm input)
  */
+/* Engine selection for the fused MLP: 1 (default) = tcgen05 tensor cores wherever the shape
+ * allows (bf16 storage, 64-wide sources), 0 = CUDA-core fp32 FFMA everywhere.  The environment
+ * variable P4C_ENGINE=simt sets the initial value to 0. */
+void p4c_set_engine(int tensor_cores);
+int p4c_get_engine(void);
+
 int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,
                     void* save_h1, float* save_stats, void* stream);
 

@@ -114,6 +114,8 @@ SYMBOLS = {
     "p4c_csr_build": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "p4c_index_to_i32": (_int, [_vp, _vp, _i64, _vp]),
     "p4c_segment_sum": (_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _int, _int, _int, _vp]),
+    "p4c_set_engine": (None, [_int]),
+    "p4c_get_engine": (_int, []),
     "p4c_mlp_forward": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "p4c_mlp_wgrad_partial_floats": (_i64, [C.POINTER(Mlp)]),
     "p4c_mlp_backward": (_int, [C.POINTER(Mlp), C.POINTER(MlpBwd), _vp]),

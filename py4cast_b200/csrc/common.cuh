@@ -30,6 +30,14 @@ void count_launch(int n = 1);
     ::p4c::count_launch();                                                           \
   } while (0)
 
+// tensor-core engine (mlp2_tc.cu)
+bool tc_forward_supported(const p4c_mlp_t* m);
+int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
+                           float* save_stats, cudaStream_t st);
+// P4C_ENGINE=simt forces the CUDA-core engine for every call (A/B testing); default: tensor cores
+// wherever the shape allows (bf16 storage, 64-wide sources)
+bool tc_engine_enabled();
+
 constexpr int kNumSMs = 148;  // B200
 constexpr int HIDDEN_W = P4C_HIDDEN;
 

@@ -12,6 +12,8 @@
 //   thread (tx = tid&15, ty = tid>>4) owns rows {ty + 16 i, i<8} x cols {4 tx .. 4 tx+3}.
 //   Layer-1 input is streamed through shared memory in K-chunks of 32 columns
 //   (register-prefetched, so global loads of chunk c+1 overlap the FFMAs of chunk c).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace p4c {
@@ -735,6 +737,15 @@ static int validate(const p4c_mlp_t* m) {
 
 static bool is_vec(const p4c_mlp_t* m) { return m->src[0].width == HID; }
 
+static int g_tc_enabled = -1;
+bool tc_engine_enabled() {
+  if (g_tc_enabled < 0) {
+    const char* e = getenv("P4C_ENGINE");
+    g_tc_enabled = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+  }
+  return g_tc_enabled == 1;
+}
+
 // Opt in to > 48 KB of dynamic shared memory, once per kernel instantiation (the attribute is
 // sticky), so that nothing but launches happens while a CUDA graph is being captured.
 template <auto kKernel>
@@ -754,6 +765,9 @@ static int set_smem(size_t bytes, const char* name) {
 
 using namespace p4c;
 
+extern "C" void p4c_set_engine(int tensor_cores) { g_tc_enabled = tensor_cores ? 1 : 0; }
+extern "C" int p4c_get_engine(void) { return tc_engine_enabled() ? 1 : 0; }
+
 extern "C" int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,
                                void* save_h1, float* save_stats, void* stream) {
   int rc = validate(m);
@@ -761,11 +775,13 @@ extern "C" int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* o
   P4C_REQUIRE(out != nullptr, "mlp_forward: out is null");
   P4C_REQUIRE(!out2 || (m->out_features == HID && m->src[0].width == HID && m->src[0].index == nullptr),
               "mlp_forward: out2 needs a 64-wide identity-indexed src[0]");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_engine_enabled() && tc_forward_supported(m))
+    return launch_mlp2_tc_forward(m, residual, out, out2, save_h1, save_stats, st);
   const long long total = (long long)m->rows * m->batch;
   const long long ntiles = (total + TM - 1) / TM;
   const int grid = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
   const size_t smem = sizeof(FwdSmem);
-  cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(T, VEC)                                                                   \
   do {                                                                                       \
     rc = set_smem<mlp2_fwd_kernel<T, VEC>>(smem, "mlp_forward");                             \

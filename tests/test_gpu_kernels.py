@@ -273,3 +273,47 @@ def test_interaction_net_chunked_weights(ops, cuda):
     assert_close(eg.grad.cpu(), er.grad, FP32_TOL)
     for (nm, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         assert_close(p.grad.cpu(), q.grad, FP32_TOL, nm)
+
+
+# ------------------------------------------------------- tensor-core engine vs CUDA-core engine
+@pytest.mark.parametrize("nsrc,out,ln,rows,batch", [
+    (1, 64, True, 1000, 2), (2, 64, True, 300, 1), (3, 64, True, 4097, 1), (1, 21, False, 513, 3),
+    (1, 64, True, 40000, 1),  # > 2 x 148 tiles: persistent loop + prefetch path
+])
+def test_tcgen05_engine_matches_simt_engine(ops, cuda, nsrc, out, ln, rows, batch):
+    """Same call through both engines (bf16 storage): forward outputs and saved activations."""
+    import ctypes as C
+
+    from py4cast_b200 import _lib
+    from py4cast_b200._lib import Mlp, check, ptr, stream
+
+    lib = _lib.load()
+    ref = _ref_mlp(64 * nsrc, out, ln, seed=nsrc)
+    ws = [w.detach() if w is not None else None for w in _weights(ref, ln, cuda)]
+    g = torch.Generator().manual_seed(rows)
+    srcs = [torch.randn(batch, rows, 64, generator=g).to(cuda).bfloat16() for _ in range(nsrc)]
+    resid = torch.randn(batch, rows, out, generator=g).to(cuda).bfloat16()
+    res = {}
+    for engine in (0, 1):
+        lib.p4c_set_engine(engine)
+        o = torch.zeros(batch, rows, out, device=cuda, dtype=torch.bfloat16)
+        o2 = torch.zeros(batch, rows, 64, device=cuda, dtype=torch.bfloat16) if out == 64 else None
+        h1 = torch.zeros(batch, rows, 64, device=cuda, dtype=torch.bfloat16)
+        st = torch.zeros(batch, rows, 2, device=cuda)
+        desc = Mlp()
+        ops._fill_mlp(desc, rows, batch, 0, [ops._SrcSpec(s) for s in srcs], ws, out, torch.bfloat16)
+        check(lib.p4c_mlp_forward(C.byref(desc), ptr(resid), ptr(o), ptr(o2), ptr(h1), ptr(st) if ln else None,
+                                  stream()), "fwd")
+        torch.cuda.synchronize()
+        res[engine] = (o.float(), o2.float() if o2 is not None else None, h1.float(), st)
+    lib.p4c_set_engine(1)
+    # fp32 reference on the same bf16 inputs
+    x = torch.cat([s.float() for s in srcs], -1).cpu()
+    want = ref(x) + resid.float().cpu()
+    assert_close(res[1][0].cpu(), want, BF16_TOL, "tc out vs fp32 reference")
+    assert_close(res[1][0], res[0][0], BF16_TOL, "tc out vs simt out")
+    assert_close(res[1][2], res[0][2], BF16_TOL, "tc h1 vs simt h1")
+    if out == 64:
+        assert_close(res[1][1], res[0][1], BF16_TOL, "tc out2 vs simt out2")
+    if ln:
+        assert_close(res[1][3], res[0][3], BF16_TOL, "tc LN stats vs simt")
