@@ -34,6 +34,9 @@ void count_launch(int n = 1);
 bool tc_forward_supported(const p4c_mlp_t* m);
 int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
                            float* save_stats, cudaStream_t st);
+bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g);
+int tc_backward_grid(const p4c_mlp_t* m);
+int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st);
 // P4C_ENGINE=simt forces the CUDA-core engine for every call (A/B testing); default: tensor cores
 // wherever the shape allows (bf16 storage, 64-wide sources)
 bool tc_engine_enabled();

@@ -807,7 +807,8 @@ static int bwd_grid(const p4c_mlp_t* m) {
 
 extern "C" int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m) {
   if (!m || m->rows <= 0 || m->batch <= 0) return 0;
-  return (int64_t)bwd_grid(m) * partial_floats(m->k1);
+  const int g_simt = bwd_grid(m), g_tc = tc_backward_grid(m);  // either engine may serve the call
+  return (int64_t)(g_simt > g_tc ? g_simt : g_tc) * partial_floats(m->k1);
 }
 
 extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream) {
@@ -821,11 +822,17 @@ extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void
   for (int s = 0; s < m->nsrc; ++s)
     P4C_REQUIRE(!g->dx[s] || m->src[s].index == nullptr,
                 "mlp_backward: dx[%d] requested for a gathered source (use dh1 + segment_sum)", s);
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid;
+  if (tc_engine_enabled() && tc_backward_supported(m, g)) {
+    grid = tc_backward_grid(m);
+    rc = launch_mlp2_tc_backward(m, g, st);
+    if (rc) return rc;
+  } else {
   const int k1pad = (m->k1 + KC - 1) / KC * KC;
   const size_t smem = sizeof(BwdSmemFixed) + (size_t)k1pad * HID * sizeof(float);
   P4C_REQUIRE(smem <= 227 * 1024, "mlp_backward: k1=%d needs %zu B of shared memory", m->k1, smem);
-  const int grid = bwd_grid(m);
-  cudaStream_t st = (cudaStream_t)stream;
+  grid = bwd_grid(m);
 #define LAUNCH_BWD(T, VEC)                                               \
   do {                                                                   \
     rc = set_smem<mlp2_bwd_kernel<T, VEC>>(smem, "mlp_backward");        \
@@ -839,6 +846,7 @@ extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void
   }
 #undef LAUNCH_BWD
   P4C_CHECK_LAUNCH("mlp_backward");
+  }
   const long long total = (long long)m->k1 * HID + (long long)m->out_features * HID + 4 * HID;
   const int rgrid = (int)((total + 255) / 256);
   mlp2_wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(g->wgrad_partials, grid, m->k1, m->out_features,

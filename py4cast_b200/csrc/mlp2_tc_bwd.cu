@@ -1,0 +1,572 @@
+// Tensor-core engine of the fused 2-layer MLP — BACKWARD (bf16 storage, 64-wide sources).
+//
+// Per 128-row tile (thread i owns row i), five groups of tcgen05 MMAs with fp32 accumulators in
+// TMEM (256 columns per CTA: 192 persistent weight-gradient columns + one 64-column scratch):
+//   G1  h2   = a1 · W2^T                      (recomputed; LayerNorm input)      -> scratch
+//   G2  da1  = dh2 · W2                                                           -> scratch
+//   G3  dW2 += a1^T · dh2        (A, B MN-major: the [row][col] tiles read "transposed")
+//   G4  dW1 += X^T · dh1         (two M=128 accumulators: sources 0-1, source 2)
+//   G5  dX_s = dh1 · W1[:, s]    (per identity-indexed source)                    -> scratch
+// The weight-gradient accumulators stay in TMEM over all tiles of the CTA and are written once,
+// as per-CTA partials that mlp2_wgrad_reduce_kernel sums in a fixed order (no float atomics).
+// An MN-major M=128 operand spans two consecutive 16 KB smem blocks; when only 64 rows of the
+// product are wanted (source 2, a1) the second block is whatever tile follows in shared memory
+// and the corresponding 64 TMEM lanes are simply never read.
+// Bias / LayerNorm-affine gradients are column sums over rows = over threads: a 31-shuffle
+// "transpose-reduce" butterfly per 32 columns, in a fixed order.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace p4c {
+namespace tc {
+
+constexpr int TM = 128;
+constexpr int NTHREADS = 128;
+constexpr int HID = P4C_HIDDEN;
+constexpr int BLK = TM * 128;    // 16 KB: one 128x64 bf16 tile
+constexpr int WBLK = HID * 128;  // 8 KB: one 64x64 bf16 tile
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t COL_DW1A = 0, COL_DW1B = 64, COL_DW2 = 128, COL_SCRATCH = 192;
+
+// small control block placed after the tiles (kept tiny: two CTAs must fit in one SM)
+struct BwdCtl {
+  float b2[HID], gamma[HID];
+  uint32_t row_off[2][P4C_MAX_SRC][TM];  // source row offset in units of 8 elements; ~0u = invalid row
+  int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid row
+  uint64_t mbar[4];
+  uint32_t tmem_base;
+};
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+
+// column sums over the 32 lanes of a warp: lane l ends with sum_lanes v[l] (fixed order)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+__device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, long long tile_row0, long long total_rows,
+                                             uint32_t (*row_off)[TM], int32_t* orow, int tid) {
+  const long long g = tile_row0 + tid;
+  long long o = -1, b = 0;
+  int rr = 0;
+  if (g < total_rows) {
+    b = g / m.rows;
+    rr = static_cast<int>(g - b * m.rows);
+    o = b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr;
+  }
+  orow[tid] = static_cast<int32_t>(o);
+  for (int s = 0; s < m.nsrc; ++s) {
+    uint32_t off = kNoRow;
+    if (o >= 0) {
+      const long long idx = m.src[s].index ? static_cast<long long>(m.src[s].index[rr]) : static_cast<long long>(rr);
+      off = static_cast<uint32_t>((b * m.src[s].batch_stride + idx * m.src[s].ld) >> 3);
+    }
+    row_off[s][tid] = off;
+  }
+}
+
+__device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const uint32_t (*row_off)[TM], uint8_t* xbase,
+                                           int tid) {
+  for (int s = 0; s < m.nsrc; ++s) {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[s].ptr);
+    const uint32_t xs = smem_u32(xbase + s * BLK);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * NTHREADS + tid;
+      const int r = idx >> 3, j = idx & 7;
+      const uint32_t off = row_off[s][r];
+      const __nv_bfloat16* src = off != kNoRow ? base + (static_cast<long long>(off) << 3) + j * 8 : base;
+      cp_async16(xs + sw128_offset(r, j), src, off != kNoRow ? 16u : 0u);
+    }
+  }
+}
+
+// shared-memory map (all tiles 1024-byte aligned):
+//   [X0 .. X(nsrc-1)] [A1] [DH] [W2] [W2T] [W1T x ndx] [BwdCtl]
+__host__ __device__ inline size_t bwd_smem_bytes(int nsrc, int ndx) {
+  return static_cast<size_t>(nsrc + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + sizeof(BwdCtl);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src0, int dx_src1) {
+  extern __shared__ unsigned char smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nsrc = m.nsrc;
+  uint8_t* Xs = base;
+  uint8_t* A1 = base + nsrc * BLK;
+  uint8_t* DH = A1 + BLK;
+  uint8_t* W2s = DH + BLK;
+  uint8_t* W2T = W2s + WBLK;
+  uint8_t* W1T = W2T + WBLK;
+  BwdCtl& C = *reinterpret_cast<BwdCtl*>(W1T + ndx * WBLK);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long total_rows = static_cast<long long>(m.rows) * m.batch;
+  const long long ntiles = (total_rows + TM - 1) / TM;
+  const int OUT = m.out_features;
+  const bool ln = m.layer_norm != 0;
+  const int dxs[2] = {dx_src0, dx_src1};
+
+  // ---- one-time set-up
+  for (int i = tid; i < HID * HID; i += NTHREADS) {
+    const int c = i >> 6, k = i & 63;
+    const __nv_bfloat16 w = __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
+    *reinterpret_cast<__nv_bfloat16*>(W2s + sw128_offset(c, k >> 3) + (k & 7) * 2) = w;  // [n=c][K=k]
+    *reinterpret_cast<__nv_bfloat16*>(W2T + sw128_offset(k, c >> 3) + (c & 7) * 2) = w;  // [n=k][K=c]
+  }
+  for (int d = 0; d < ndx; ++d) {
+    const int s = dxs[d];
+    for (int i = tid; i < HID * HID; i += NTHREADS) {
+      const int c = i >> 6, k = i & 63;  // W1T_s[n=k][K=c] = w1[c][64 s + k]
+      *reinterpret_cast<__nv_bfloat16*>(W1T + d * WBLK + sw128_offset(k, c >> 3) + (c & 7) * 2) =
+          __float2bfloat16_rn(m.w1[static_cast<long long>(c) * m.k1 + s * HID + k]);
+    }
+  }
+  if (tid < HID) {
+    C.b2[tid] = tid < OUT ? m.b2[tid] : 0.f;
+    C.gamma[tid] = m.gamma ? m.gamma[tid] : 1.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&C.mbar[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&C.tmem_base, TMEM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = C.tmem_base;
+  const uint32_t tmem_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t IDESC_KK = make_idesc_bf16(TM, HID, 0, 0);  // A, B K-major
+  constexpr uint32_t IDESC_MM = make_idesc_bf16(TM, HID, 1, 1);  // A, B MN-major (transposed reads)
+
+  const __nv_bfloat16* h1p = reinterpret_cast<const __nv_bfloat16*>(g.h1);
+  const __nv_bfloat16* dya = reinterpret_cast<const __nv_bfloat16*>(g.dy_a);
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(g.dy_b);
+  __nv_bfloat16* dh1_out = reinterpret_cast<__nv_bfloat16*>(g.dh1_out);
+
+  // per-thread column-sum accumulators: [vector: db1, db2, dgamma, dbeta][half]
+  float vacc[4][2];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) vacc[v][0] = vacc[v][1] = 0.f;
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) {
+    bwd_row_info(m, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);
+    __syncthreads();
+    bwd_gather(m, C.row_off[0], Xs, tid);
+  }
+  cp_async_commit();
+
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int p = it & 1;
+    const uint32_t parity = static_cast<uint32_t>(it & 1);
+    const uint32_t acc = it ? 1u : 0u;  // weight-gradient accumulators: overwrite on the first tile
+    const long long orow = C.orow[p][tid];  // -1 = row beyond the problem
+    const long long grow = tile * TM + tid;  // global row (for dy_a indexing)
+
+    // ---- a. h1 row -> registers (packed bf16), a1 = SiLU(h1) -> A1 tile
+    uint4 h1r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h1r[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(h1p + orow * HID + j * 8) : make_uint4(0, 0, 0, 0);
+      float h[8];
+      unpack8(h1r[j], h);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = silu(h[q]);
+      *reinterpret_cast<uint4*>(A1 + sw128_offset(tid, j)) = pack8(h);
+    }
+    // dy row -> packed bf16 registers (dy_a gathered and scaled, + dy_b)
+    uint4 dyr[8];
+    {
+      long long ia = -1, bb = 0;
+      float sc = 1.f;
+      if (orow >= 0) {
+        bb = grow / m.rows;
+        const int rr = static_cast<int>(grow - bb * m.rows);
+        ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
+        if (g.dy_a_scale) sc = g.dy_a_scale[ia];
+      }
+      if (OUT == HID) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (orow >= 0) {
+            unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + j * 8), d);
+            if (g.dy_a_scale) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d[q] *= sc;
+            }
+            if (dyb) {
+              float e[8];
+              unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + j * 8), e);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d[q] += e[q];
+            }
+          }
+          dyr[j] = pack8(d);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = j * 8 + q;
+            float v = 0.f;
+            if (orow >= 0 && c < OUT) {
+              v = __bfloat162float(dya[bb * g.dy_a_batch_stride + ia * OUT + c]) * sc;
+              if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
+            }
+            d[q] = v;
+          }
+          dyr[j] = pack8(d);
+        }
+      }
+    }
+
+    float mean = 0.f, rstd = 0.f;
+    if (ln) {
+      if (orow >= 0) {
+        mean = g.stats[2 * orow];
+        rstd = g.stats[2 * orow + 1];
+      }
+      // ---- b. G1: h2 = a1 W2^T -> scratch
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aa = smem_u32(A1), wa = smem_u32(W2s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(aa + j * 32, 16, 1024),
+                      make_desc_sw128(wa + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
+        mma_commit(&C.mbar[0]);
+      }
+      mbar_wait(&C.mbar[0], parity);
+      tc_fence_after();
+      // ---- c. LayerNorm backward, row-local; two passes over the TMEM row
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d[8];
+          unpack8(dyr[half * 4 + j], d);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = half * 32 + j * 8 + q;
+            const float xh = (v[j * 8 + q] + C.b2[c] - mean) * rstd;
+            const float dxh = d[q] * C.gamma[c];
+            s1 += dxh;
+            s2 += dxh * xh;
+          }
+        }
+      }
+      s1 *= (1.0f / HID);
+      s2 *= (1.0f / HID);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32], t0[32], t1[32];
+        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d[8], o[8];
+          unpack8(dyr[half * 4 + j], d);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = half * 32 + j * 8 + q;
+            const float xh = (v[j * 8 + q] + C.b2[c] - mean) * rstd;
+            const float dxh = d[q] * C.gamma[c];
+            t0[j * 8 + q] = d[q] * xh;  // dgamma contribution
+            t1[j * 8 + q] = d[q];       // dbeta contribution
+            o[q] = rstd * (dxh - s1 - xh * s2);
+          }
+          dyr[half * 4 + j] = pack8(o);  // dyr now holds dh2
+        }
+        vacc[2][half] += warp_colsum32(t0, lane);
+        vacc[3][half] += warp_colsum32(t1, lane);
+      }
+    }
+    // db2 column sums + dh2 -> DH tile
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unpack8(dyr[half * 4 + j], t + j * 8);
+        *reinterpret_cast<uint4*>(DH + sw128_offset(tid, half * 4 + j)) = dyr[half * 4 + j];
+      }
+      vacc[1][half] += warp_colsum32(t, lane);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- d. G2: da1 = dh2 W2 -> scratch ;  G3: dW2 += a1^T dh2
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t da = smem_u32(DH), wt = smem_u32(W2T), a1 = smem_u32(A1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+                    make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
+      if (g.g_w2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // K = 128 rows, 16 per MMA = 2 groups of 8 rows = 2048 bytes
+          mma_bf16_ss(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, BLK, 1024),
+                      make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
+      }
+      mma_commit(&C.mbar[1]);
+    }
+    mbar_wait(&C.mbar[1], parity);
+    tc_fence_after();
+
+    // ---- e. dh1 = da1 * SiLU'(h1): db1 sums, global store, DH tile (overwrites dh2)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h[8];
+        unpack8(h1r[half * 4 + j], h);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * silu_grad(h[q]) : 0.f;
+        const uint4 packed = pack8(v + j * 8);
+        *reinterpret_cast<uint4*>(DH + sw128_offset(tid, half * 4 + j)) = packed;
+        if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + (half * 4 + j) * 8) = packed;
+      }
+      vacc[0][half] += warp_colsum32(v, lane);
+    }
+    cp_async_wait<0>();  // X(tile) landed (issued one tile ago)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- f. G4: dW1 += X^T dh1 ; G5(0): dX = dh1 W1[:, s0]
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t da = smem_u32(DH), xa = smem_u32(Xs);
+      if (g.g_w1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          mma_bf16_ss(tmem + COL_DW1A, make_desc_sw128(xa + j * 2048, BLK, 1024),
+                      make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
+        if (nsrc == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            mma_bf16_ss(tmem + COL_DW1B, make_desc_sw128(xa + 2 * BLK + j * 2048, BLK, 1024),
+                        make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
+        }
+      }
+      if (ndx > 0) {
+        const uint32_t wt = smem_u32(W1T);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+                      make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
+      }
+      mma_commit(&C.mbar[2]);
+    }
+    // meanwhile: addressing of the next tile
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) bwd_row_info(m, next * TM, total_rows, C.row_off[p ^ 1], C.orow[p ^ 1], tid);
+    mbar_wait(&C.mbar[2], parity);
+    tc_fence_after();
+    __syncthreads();  // next row_off visible; X, A1 are free (DH still feeds a possible second dX)
+    if (next < ntiles) bwd_gather(m, C.row_off[p ^ 1], Xs, tid);
+    cp_async_commit();
+
+    // ---- g. dX stores (one or two identity-indexed sources)
+    for (int d = 0; d < ndx; ++d) {
+      if (d == 1) {
+        tc_fence_before();
+        __syncthreads();  // everyone has read the scratch of dX(0)
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t da = smem_u32(DH), wt = smem_u32(W1T + WBLK);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+                        make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
+          mma_commit(&C.mbar[3]);
+        }
+        mbar_wait(&C.mbar[3], parity);
+        tc_fence_after();
+      }
+      const int s = dxs[d];
+      __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(g.dx[s]);
+      const int ld = g.dx_ld[s];
+      const bool add_dy = (s == 0 && g.dx0_add_dy != 0);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
+        tmem_ld_wait();
+        if (orow < 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* o = v + j * 8;
+          const int c0 = (half * 4 + j) * 8;
+          __nv_bfloat16* dst = dxp + orow * ld + c0;
+          if (g.dx_accumulate[s]) {
+            float e[8];
+            unpack8(*reinterpret_cast<const uint4*>(dst), e);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] += e[q];
+          }
+          if (add_dy) {
+            // residual / edge-update pass-through: d src0 += dy (dy_b only when dx0_add_dy == 1)
+            float e[8];
+            if (g.dx0_add_dy == 2) {
+              const long long bb = grow / m.rows;
+              const int rr = static_cast<int>(grow - bb * m.rows);
+              const long long ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
+              unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + c0), e);
+              const float sc = g.dy_a_scale ? g.dy_a_scale[ia] : 1.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] += e[q] * sc;
+            }
+            if (dyb) {
+              unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] += e[q];
+            }
+          }
+          *reinterpret_cast<uint4*>(dst) = pack8(o);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // tile done: A1 / DH / scratch may be overwritten
+  }
+
+  // ---- per-CTA partials: weight gradients from TMEM, vector gradients from the warp sums
+  cp_async_wait<0>();
+  tc_fence_after();
+  const int k1pad = (m.k1 + 31) / 32 * 32;
+  const long long pf = static_cast<long long>(k1pad) * HID + HID * HID + 4 * HID;
+  float* part = g.wgrad_partials + static_cast<long long>(blockIdx.x) * pf;
+  {
+    float v[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // dW1[k = tid][c] for sources 0,1
+      tmem_ld32(tmem_row + COL_DW1A + half * 32, v);
+      tmem_ld_wait();
+      if (tid < m.k1) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) part[static_cast<long long>(tid) * HID + half * 32 + q] = v[q];
+      }
+      tmem_ld32(tmem_row + COL_DW1B + half * 32, v);
+      tmem_ld_wait();
+      if (nsrc == 3 && tid < HID) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) part[static_cast<long long>(2 * HID + tid) * HID + half * 32 + q] = v[q];
+      }
+      tmem_ld32(tmem_row + COL_DW2 + half * 32, v);
+      tmem_ld_wait();
+      if (tid < HID) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          part[static_cast<long long>(k1pad) * HID + static_cast<long long>(tid) * HID + half * 32 + q] = v[q];
+      }
+    }
+  }
+  // cross-warp sums in a fixed order; the A1 tile is free by now and serves as scratch
+  float (*red)[4][HID] = reinterpret_cast<float (*)[4][HID]>(A1);  // [warp][vector][column]
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    red[warp][v][lane] = vacc[v][0];
+    red[warp][v][32 + lane] = vacc[v][1];
+  }
+  __syncthreads();
+  if (tid < HID) {
+    float* pv = part + static_cast<long long>(k1pad) * HID + HID * HID;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) pv[v * HID + tid] = red[0][v][tid] + red[1][v][tid] + red[2][v][tid] + red[3][v][tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace tc
+
+bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g) {
+  if (!tc_forward_supported(m)) return false;
+  int ndx = 0;
+  for (int s = 0; s < m->nsrc; ++s) {
+    if (g->dx[s]) {
+      ++ndx;
+      if (g->dx_ld[s] % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dx[s]) % 16) != 0) return false;
+    }
+  }
+  if (ndx > 2) return false;
+  if (m->out_features == P4C_HIDDEN) {
+    if (g->dy_a_batch_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dy_a) % 16) != 0) return false;
+    if (g->dy_b && (reinterpret_cast<uintptr_t>(g->dy_b) % 16) != 0) return false;
+  }
+  if (g->dh1_out && (reinterpret_cast<uintptr_t>(g->dh1_out) % 16) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(g->h1) % 16) != 0) return false;
+  return true;
+}
+
+int tc_backward_grid(const p4c_mlp_t* m) {
+  const long long total = static_cast<long long>(m->rows) * m->batch;
+  const long long ntiles = (total + tc::TM - 1) / tc::TM;
+  return static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+}
+
+int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st) {
+  using namespace tc;
+  int dxs[2] = {-1, -1}, ndx = 0;
+  for (int s = 0; s < m->nsrc; ++s)
+    if (g->dx[s]) dxs[ndx++] = s;
+  const size_t smem = bwd_smem_bytes(m->nsrc, ndx) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp2_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("mlp_backward(tc): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return P4C_ECUDA;
+    }
+    configured = smem;
+  }
+  mlp2_tc_bwd_kernel<<<tc_backward_grid(m), NTHREADS, smem, st>>>(*m, *g, ndx, dxs[0], dxs[1]);
+  P4C_CHECK_LAUNCH("mlp_backward(tc)");
+  return P4C_OK;
+}
+
+}  // namespace p4c

@@ -21,7 +21,7 @@ from ._lib import HIDDEN, ArX, Mlp, MlpBwd, check, dtype_code, ptr, stream
 
 # ------------------------------------------------------------------ workspaces
 _WGRAD_WS: dict = {}
-_WGRAD_WS_FLOATS = 148 * (192 * 64 + 64 * 64 + 4 * 64)
+_WGRAD_WS_FLOATS = 2 * 148 * (192 * 64 + 64 * 64 + 4 * 64)
 
 
 def _wgrad_workspace(device: torch.device, floats: int) -> torch.Tensor:
