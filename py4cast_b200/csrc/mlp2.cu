@@ -653,9 +653,15 @@ __global__ void mlp2_wgrad_reduce_kernel(const float* __restrict__ partials, int
       dst = (base && (v != 1 || c < out_features)) ? base + c : nullptr;
     }
     if (!dst) continue;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partials[(long long)b * pf + src];
-    *dst += s;
+    // fixed-shape reduction tree: 8 interleaved partial sums (8 independent loads in flight)
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int b = 0;
+    for (; b + 8 <= nblocks; b += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += partials[(long long)(b + j) * pf + src];
+    }
+    for (int j = 0; b < nblocks; ++b, ++j) a[j] += partials[(long long)b * pf + src];
+    *dst += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
 }
 

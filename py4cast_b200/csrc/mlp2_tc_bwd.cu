@@ -1,6 +1,7 @@
 // Tensor-core engine of the fused 2-layer MLP — BACKWARD (bf16 storage, 64-wide sources).
 //
-// Per 128-row tile (thread i owns row i), five groups of tcgen05 MMAs with fp32 accumulators in
+// Per 128-row tile (256 threads: warp w owns TMEM lanes 32*(w%4).. = rows and columns 32*(w/4)..,
+// i.e. two threads per row with 32 columns each), five groups of tcgen05 MMAs with fp32 accumulators in
 // TMEM (256 columns per CTA: 192 persistent weight-gradient columns + one 64-column scratch):
 //   G1  h2   = a1 · W2^T                      (recomputed; LayerNorm input)      -> scratch
 //   G2  da1  = dh2 · W2                                                           -> scratch
@@ -21,7 +22,7 @@ namespace p4c {
 namespace tc {
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 128;
+constexpr int NTHREADS = 256;
 constexpr int HID = P4C_HIDDEN;
 constexpr int BLK = TM * 128;    // 16 KB: one 128x64 bf16 tile
 constexpr int WBLK = HID * 128;  // 8 KB: one 64x64 bf16 tile
@@ -33,6 +34,7 @@ struct BwdCtl {
   float b2[HID], gamma[HID];
   uint32_t row_off[2][P4C_MAX_SRC][TM];  // source row offset in units of 8 elements; ~0u = invalid row
   int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid row
+  float2 ln_part[2][TM];                 // LayerNorm-backward row sums of each column half
   uint64_t mbar[4];
   uint32_t tmem_base;
 };
@@ -69,6 +71,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 __device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, long long tile_row0, long long total_rows,
                                              uint32_t (*row_off)[TM], int32_t* orow, int tid) {
+  if (tid >= TM) return;
   const long long g = tile_row0 + tid;
   long long o = -1, b = 0;
   int rr = 0;
@@ -94,7 +97,7 @@ __device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const uint32_t (*
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[s].ptr);
     const uint32_t xs = smem_u32(xbase + s * BLK);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
       const int idx = i * NTHREADS + tid;
       const int r = idx >> 3, j = idx & 7;
       const uint32_t off = row_off[s][r];
@@ -124,6 +127,8 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   BwdCtl& C = *reinterpret_cast<BwdCtl*>(W1T + ndx * WBLK);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column half
+  const int row = quad * 32 + lane, col0 = hsel * 32;
   const long long total_rows = static_cast<long long>(m.rows) * m.batch;
   const long long ntiles = (total_rows + TM - 1) / TM;
   const int OUT = m.out_features;
@@ -141,8 +146,9 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     const int s = dxs[d];
     for (int i = tid; i < HID * HID; i += NTHREADS) {
       const int c = i >> 6, k = i & 63;  // W1T_s[n=k][K=c] = w1[c][64 s + k]
+      const int kg = s * HID + k;
       *reinterpret_cast<__nv_bfloat16*>(W1T + d * WBLK + sw128_offset(k, c >> 3) + (c & 7) * 2) =
-          __float2bfloat16_rn(m.w1[static_cast<long long>(c) * m.k1 + s * HID + k]);
+          __float2bfloat16_rn(kg < m.k1 ? m.w1[static_cast<long long>(c) * m.k1 + kg] : 0.f);
     }
   }
   if (tid < HID) {
@@ -160,7 +166,7 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = C.tmem_base;
-  const uint32_t tmem_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
   constexpr uint32_t IDESC_KK = make_idesc_bf16(TM, HID, 0, 0);  // A, B K-major
   constexpr uint32_t IDESC_MM = make_idesc_bf16(TM, HID, 1, 1);  // A, B MN-major (transposed reads)
 
@@ -169,10 +175,8 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(g.dy_b);
   __nv_bfloat16* dh1_out = reinterpret_cast<__nv_bfloat16*>(g.dh1_out);
 
-  // per-thread column-sum accumulators: [vector: db1, db2, dgamma, dbeta][half]
-  float vacc[4][2];
-#pragma unroll
-  for (int v = 0; v < 4; ++v) vacc[v][0] = vacc[v][1] = 0.f;
+  // per-thread column-sum accumulators (column col0 + lane, rows of this warp): db1, db2, dgamma, dbeta
+  float vacc[4] = {0.f, 0.f, 0.f, 0.f};
 
   long long tile = blockIdx.x;
   if (tile < ntiles) {
@@ -186,22 +190,23 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     const int p = it & 1;
     const uint32_t parity = static_cast<uint32_t>(it & 1);
     const uint32_t acc = it ? 1u : 0u;  // weight-gradient accumulators: overwrite on the first tile
-    const long long orow = C.orow[p][tid];  // -1 = row beyond the problem
-    const long long grow = tile * TM + tid;  // global row (for dy_a indexing)
+    const long long orow = C.orow[p][row];  // -1 = row beyond the problem
+    const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
-    // ---- a. h1 row -> registers (packed bf16), a1 = SiLU(h1) -> A1 tile
-    uint4 h1r[8];
+    // ---- a. h1 half-row -> registers (packed bf16), a1 = SiLU(h1) -> A1 tile
+    uint4 h1r[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      h1r[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(h1p + orow * HID + j * 8) : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = col0 + j * 8;
+      h1r[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(h1p + orow * HID + c0) : make_uint4(0, 0, 0, 0);
       float h[8];
       unpack8(h1r[j], h);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] = silu(h[q]);
-      *reinterpret_cast<uint4*>(A1 + sw128_offset(tid, j)) = pack8(h);
+      for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+      *reinterpret_cast<uint4*>(A1 + sw128_offset(row, c0 >> 3)) = pack8(h);
     }
-    // dy row -> packed bf16 registers (dy_a gathered and scaled, + dy_b)
-    uint4 dyr[8];
+    // dy half-row -> packed bf16 registers (dy_a gathered and scaled, + dy_b)
+    uint4 dyr[4];
     {
       long long ia = -1, bb = 0;
       float sc = 1.f;
@@ -211,46 +216,39 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
         ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
         if (g.dy_a_scale) sc = g.dy_a_scale[ia];
       }
-      if (OUT == HID) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (orow >= 0) {
-            unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + j * 8), d);
-            if (g.dy_a_scale) {
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = col0 + j * 8;
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (orow >= 0) {
+          if (OUT == HID) {
+            unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + c0), d);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) d[q] *= sc;
-            }
+            for (int q = 0; q < 8; ++q) d[q] *= sc;
             if (dyb) {
               float e[8];
-              unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + j * 8), e);
+              unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
 #pragma unroll
               for (int q = 0; q < 8; ++q) d[q] += e[q];
             }
-          }
-          dyr[j] = pack8(d);
-        }
-      } else {
+          } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float d[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c = j * 8 + q;
-            float v = 0.f;
-            if (orow >= 0 && c < OUT) {
-              v = __bfloat162float(dya[bb * g.dy_a_batch_stride + ia * OUT + c]) * sc;
-              if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
+            for (int q = 0; q < 8; ++q) {
+              const int c = c0 + q;
+              if (c < OUT) {
+                float v = __bfloat162float(dya[bb * g.dy_a_batch_stride + ia * OUT + c]) * sc;
+                if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
+                d[q] = v;
+              }
             }
-            d[q] = v;
           }
-          dyr[j] = pack8(d);
         }
+        dyr[j] = pack8(d);
       }
     }
 
-    float mean = 0.f, rstd = 0.f;
     if (ln) {
+      float mean = 0.f, rstd = 0.f;
       if (orow >= 0) {
         mean = g.stats[2 * orow];
         rstd = g.stats[2 * orow + 1];
@@ -270,63 +268,60 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
       }
       mbar_wait(&C.mbar[0], parity);
       tc_fence_after();
-      // ---- c. LayerNorm backward, row-local; two passes over the TMEM row
+      // ---- c. LayerNorm backward: xhat from the recomputed h2, row sums exchanged between the
+      //         two threads of a row, then dh2 (kept in dyr), dgamma / dbeta column sums
+      float xh[32];
+      tmem_ld32(tmem_row + COL_SCRATCH, xh);
+      tmem_ld_wait();
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
-        tmem_ld_wait();
+      for (int j = 0; j < 4; ++j) {
+        float d[8];
+        unpack8(dyr[j], d);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float d[8];
-          unpack8(dyr[half * 4 + j], d);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c = half * 32 + j * 8 + q;
-            const float xh = (v[j * 8 + q] + C.b2[c] - mean) * rstd;
-            const float dxh = d[q] * C.gamma[c];
-            s1 += dxh;
-            s2 += dxh * xh;
-          }
+        for (int q = 0; q < 8; ++q) {
+          const int c = col0 + j * 8 + q;
+          xh[j * 8 + q] = (xh[j * 8 + q] + C.b2[c] - mean) * rstd;
+          const float dxh = d[q] * C.gamma[c];
+          s1 += dxh;
+          s2 = fmaf(dxh, xh[j * 8 + q], s2);
         }
       }
-      s1 *= (1.0f / HID);
-      s2 *= (1.0f / HID);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32], t0[32], t1[32];
-        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float d[8], o[8];
-          unpack8(dyr[half * 4 + j], d);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c = half * 32 + j * 8 + q;
-            const float xh = (v[j * 8 + q] + C.b2[c] - mean) * rstd;
-            const float dxh = d[q] * C.gamma[c];
-            t0[j * 8 + q] = d[q] * xh;  // dgamma contribution
-            t1[j * 8 + q] = d[q];       // dbeta contribution
-            o[q] = rstd * (dxh - s1 - xh * s2);
-          }
-          dyr[half * 4 + j] = pack8(o);  // dyr now holds dh2
-        }
-        vacc[2][half] += warp_colsum32(t0, lane);
-        vacc[3][half] += warp_colsum32(t1, lane);
+      C.ln_part[hsel][row] = make_float2(s1, s2);
+      __syncthreads();
+      {
+        const float2 lo = C.ln_part[0][row], hi = C.ln_part[1][row];
+        s1 = (lo.x + hi.x) * (1.0f / HID);
+        s2 = (lo.y + hi.y) * (1.0f / HID);
       }
+      float t1[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d[8], o[8];
+        unpack8(dyr[j], d);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = col0 + j * 8 + q;
+          const float x = xh[j * 8 + q];
+          const float dxh = d[q] * C.gamma[c];
+          o[q] = rstd * (dxh - s1 - x * s2);
+          xh[j * 8 + q] = d[q] * x;  // dgamma contribution
+          t1[j * 8 + q] = d[q];      // dbeta contribution
+        }
+        dyr[j] = pack8(o);  // dyr now holds dh2
+      }
+      vacc[2] += warp_colsum32(xh, lane);
+      vacc[3] += warp_colsum32(t1, lane);
     }
     // db2 column sums + dh2 -> DH tile
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       float t[32];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        unpack8(dyr[half * 4 + j], t + j * 8);
-        *reinterpret_cast<uint4*>(DH + sw128_offset(tid, half * 4 + j)) = dyr[half * 4 + j];
+        unpack8(dyr[j], t + j * 8);
+        *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
       }
-      vacc[1][half] += warp_colsum32(t, lane);
+      vacc[1] += warp_colsum32(t, lane);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -352,22 +347,21 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     tc_fence_after();
 
     // ---- e. dh1 = da1 * SiLU'(h1): db1 sums, global store, DH tile (overwrites dh2)
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       float v[32];
-      tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
+      tmem_ld32(tmem_row + COL_SCRATCH, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float h[8];
-        unpack8(h1r[half * 4 + j], h);
+        unpack8(h1r[j], h);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * silu_grad(h[q]) : 0.f;
+        for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * fast_silu_grad(h[q]) : 0.f;
         const uint4 packed = pack8(v + j * 8);
-        *reinterpret_cast<uint4*>(DH + sw128_offset(tid, half * 4 + j)) = packed;
-        if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + (half * 4 + j) * 8) = packed;
+        *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = packed;
+        if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + col0 + j * 8) = packed;
       }
-      vacc[0][half] += warp_colsum32(v, lane);
+      vacc[0] += warp_colsum32(v, lane);
     }
     cp_async_wait<0>();  // X(tile) landed (issued one tile ago)
     fence_proxy_async();
@@ -429,16 +423,14 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
       __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(g.dx[s]);
       const int ld = g.dx_ld[s];
       const bool add_dy = (s == 0 && g.dx0_add_dy != 0);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tmem_ld32(tmem_row + COL_SCRATCH + half * 32, v);
-        tmem_ld_wait();
-        if (orow < 0) continue;
+      float v[32];
+      tmem_ld32(tmem_row + COL_SCRATCH, v);
+      tmem_ld_wait();
+      if (orow >= 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float* o = v + j * 8;
-          const int c0 = (half * 4 + j) * 8;
+          const int c0 = col0 + j * 8;
           __nv_bfloat16* dst = dxp + orow * ld + c0;
           if (g.dx_accumulate[s]) {
             float e[8];
@@ -456,7 +448,7 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
               unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + c0), e);
               const float sc = g.dy_a_scale ? g.dy_a_scale[ia] : 1.f;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] += e[q] * sc;
+              for (int q = 0; q < 8; ++q) o[q] = fmaf(e[q], sc, o[q]);
             }
             if (dyb) {
               unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
@@ -480,42 +472,37 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   float* part = g.wgrad_partials + static_cast<long long>(blockIdx.x) * pf;
   {
     float v[32];
+    // dW1[k = row][c] for sources 0,1 (TMEM lane = k)
+    tmem_ld32(tmem_row + COL_DW1A, v);
+    tmem_ld_wait();
+    if (row < m.k1) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      // dW1[k = tid][c] for sources 0,1
-      tmem_ld32(tmem_row + COL_DW1A + half * 32, v);
-      tmem_ld_wait();
-      if (tid < m.k1) {
+      for (int q = 0; q < 32; ++q) part[static_cast<long long>(row) * HID + col0 + q] = v[q];
+    }
+    tmem_ld32(tmem_row + COL_DW1B, v);
+    tmem_ld_wait();
+    if (nsrc == 3 && row < HID && 2 * HID + row < m.k1) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) part[static_cast<long long>(tid) * HID + half * 32 + q] = v[q];
-      }
-      tmem_ld32(tmem_row + COL_DW1B + half * 32, v);
-      tmem_ld_wait();
-      if (nsrc == 3 && tid < HID) {
+      for (int q = 0; q < 32; ++q) part[static_cast<long long>(2 * HID + row) * HID + col0 + q] = v[q];
+    }
+    tmem_ld32(tmem_row + COL_DW2, v);
+    tmem_ld_wait();
+    if (row < HID) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) part[static_cast<long long>(2 * HID + tid) * HID + half * 32 + q] = v[q];
-      }
-      tmem_ld32(tmem_row + COL_DW2 + half * 32, v);
-      tmem_ld_wait();
-      if (tid < HID) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          part[static_cast<long long>(k1pad) * HID + static_cast<long long>(tid) * HID + half * 32 + q] = v[q];
-      }
+      for (int q = 0; q < 32; ++q)
+        part[static_cast<long long>(k1pad) * HID + static_cast<long long>(row) * HID + col0 + q] = v[q];
     }
   }
   // cross-warp sums in a fixed order; the A1 tile is free by now and serves as scratch
-  float (*red)[4][HID] = reinterpret_cast<float (*)[4][HID]>(A1);  // [warp][vector][column]
+  float (*red)[4][32] = reinterpret_cast<float (*)[4][32]>(A1);  // [warp][vector][lane]
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    red[warp][v][lane] = vacc[v][0];
-    red[warp][v][32 + lane] = vacc[v][1];
-  }
+  for (int v = 0; v < 4; ++v) red[warp][v][lane] = vacc[v];
   __syncthreads();
   if (tid < HID) {
     float* pv = part + static_cast<long long>(k1pad) * HID + HID * HID;
+    const int w0 = (tid >> 5) * 4, l = tid & 31;  // column tid lives in warps w0..w0+3 (same hsel)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) pv[v * HID + tid] = red[0][v][tid] + red[1][v][tid] + red[2][v][tid] + red[3][v][tid];
+    for (int v = 0; v < 4; ++v) pv[v * HID + tid] = (red[w0][v][l] + red[w0 + 1][v][l]) + (red[w0 + 2][v][l] + red[w0 + 3][v][l]);
   }
   tc_fence_before();
   __syncthreads();

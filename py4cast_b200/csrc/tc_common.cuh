@@ -132,6 +132,19 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
 }
 
+// bf16-path activation: sigmoid through ONE MUFU op (tanh.approx, rel. error ~2^-11, well below
+// the bf16 rounding of the stored result); the fp32 engine keeps expf + IEEE division.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
+__device__ __forceinline__ float fast_silu_grad(float x) {
+  const float s = fast_sigmoid(x);
+  return s * fmaf(x, 1.0f - s, 1.0f);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -393,6 +393,8 @@ class AutoRegressiveLightning(nn.Module):
         x_dtype = self._x_dtype()
 
         slab = torch.empty(B, T, N, F, dtype=torch.float32, device=dev)
+        if hasattr(self.model, "begin_rollout"):
+            self.model.begin_rollout()  # batch-independent embeddings: once per rollout, not per step
         prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
         x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
         states = []
@@ -417,6 +419,8 @@ class AutoRegressiveLightning(nn.Module):
                 else:
                     new_state = res
             states.append(new_state)
+        if hasattr(self.model, "end_rollout"):
+            self.model.end_rollout()
         prediction = _SlabFn.apply(slab, *states).view(B, T, *spatial, F)
 
         if inference:

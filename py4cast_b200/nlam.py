@@ -297,6 +297,26 @@ class BaseGraphModel(ModelABC, nn.Module):
     def settings(self) -> GraphLamSettings:
         return self._settings
 
+    # ---- rollout-level cache of the batch-independent embeddings ---------------------------
+    # Edge / mesh-node embeddings depend on the weights and on static graph features only.  The
+    # reference recomputes them in every forward call (T times per AR rollout, 1.3 M edges for
+    # m2g); between `begin_rollout()` and `end_rollout()` they are computed once and shared by
+    # all AR steps (autograd accumulates their gradient over the steps).
+    def begin_rollout(self) -> None:
+        self._rollout_cache = {}
+
+    def end_rollout(self) -> None:
+        self._rollout_cache = None
+
+    def _static_embedding(self, key: str, mlp: "FusedMLP", feats_name: str, dt: torch.dtype) -> torch.Tensor:
+        cache = getattr(self, "_rollout_cache", None)
+        if cache is None:
+            return mlp(self._feats(feats_name, dt))
+        k = (key, dt)
+        if k not in cache:
+            cache[k] = mlp(self._feats(feats_name, dt))
+        return cache[k]
+
     def _compute_dtype(self, x: torch.Tensor) -> torch.dtype:
         # reference: the model runs under torch.amp.autocast("cuda", dtype=str_to_dtype[precision])
         # (lightning.py:485-487); bf16 autocast or a bf16 input selects bf16 activation storage.
@@ -312,8 +332,8 @@ class BaseGraphModel(ModelABC, nn.Module):
         dt = self._compute_dtype(x)
         x = ops.cast_autograd(x.contiguous(), dt)
         grid_emb = self.grid_embedder(x)
-        g2m_emb = self.g2m_embedder(self._feats("g2m_features", dt))
-        m2g_emb = self.m2g_embedder(self._feats("m2g_features", dt))
+        g2m_emb = self._static_embedding("g2m", self.g2m_embedder, "g2m_features", dt)
+        m2g_emb = self._static_embedding("m2g", self.m2g_embedder, "m2g_features", dt)
         mesh_emb = self.embedd_mesh_nodes(dt)
         mesh_rep = self.g2m_gnn(grid_emb, mesh_emb, g2m_emb)
         grid_rep = self.encoding_grid_mlp(grid_emb, residual=True)
@@ -342,10 +362,10 @@ class GraphLAM(BaseGraphModel):
         )
 
     def embedd_mesh_nodes(self, dt):
-        return self.mesh_embedder(self._feats("mesh_static_features", dt))
+        return self._static_embedding("mesh", self.mesh_embedder, "mesh_static_features", dt)
 
     def process_step(self, mesh_rep, dt):
-        edge_rep = self.m2m_embedder(self._feats("m2m_features", dt))
+        edge_rep = self._static_embedding("m2m", self.m2m_embedder, "m2m_features", dt)
         for net in self.processor:
             mesh_rep, edge_rep = net(mesh_rep, mesh_rep, edge_rep)
         return mesh_rep
@@ -379,14 +399,15 @@ class BaseHiGraphModel(BaseGraphModel):
         self._build_processor(graph, settings)
 
     def embedd_mesh_nodes(self, dt):
-        return self.mesh_embedders[0](self._feats("mesh_static_0", dt))
+        return self._static_embedding("mesh0", self.mesh_embedders[0], "mesh_static_0", dt)
 
     def process_step(self, mesh_rep, dt):
         L = self.num_levels
-        rep = [mesh_rep] + [self.mesh_embedders[l](self._feats(f"mesh_static_{l}", dt)) for l in range(1, L)]
-        same = [self.mesh_same_embedders[l](self._feats(f"m2m_features_{l}", dt)) for l in range(L)]
-        up = [self.mesh_up_embedders[l](self._feats(f"up_features_{l}", dt)) for l in range(L - 1)]
-        down = [self.mesh_down_embedders[l](self._feats(f"down_features_{l}", dt)) for l in range(L - 1)]
+        emb = self._static_embedding
+        rep = [mesh_rep] + [emb(f"mesh{l}", self.mesh_embedders[l], f"mesh_static_{l}", dt) for l in range(1, L)]
+        same = [emb(f"same{l}", self.mesh_same_embedders[l], f"m2m_features_{l}", dt) for l in range(L)]
+        up = [emb(f"up{l}", self.mesh_up_embedders[l], f"up_features_{l}", dt) for l in range(L - 1)]
+        down = [emb(f"down{l}", self.mesh_down_embedders[l], f"down_features_{l}", dt) for l in range(L - 1)]
         for l in range(1, L):  # init sweep, upward
             rep[l], up[l - 1] = self.mesh_init_gnns[l - 1](rep[l - 1], rep[l], up[l - 1])
         rep, same, up, down = self.hi_processor_step(rep, same, up, down)
