@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop after warm-up and exit "
+                         "(for `ncu --profile-from-start off`; prints no bench line)")
     return ap.parse_args()
 
 
@@ -272,6 +275,16 @@ def gpu_arm(args):
     B, T = args.batch_per_gpu, args.pred_steps
     dev_batch = synthetic_batch(info, B, 2, T, seed=100 + rank, device=dev)
     host_batches = [synthetic_batch(info, B, 2, T, seed=200 + rank + 10 * i, pin=True) for i in range(2)]
+
+    if args.profile_step:
+        for _ in range(3):
+            trainer.train_step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.train_step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return None
 
     use_graph = not args.no_graph
     # launches of OUR kernels per step, counted on an eager step (graph replays bypass the counter)
