@@ -45,6 +45,9 @@ int p4c_version(void);
 /* number of kernels launched by this library since load / last reset (host counter) */
 int64_t p4c_launch_count(void);
 void p4c_reset_launch_count(void);
+/* sizeof() of the ABI structs as compiled (binding self-check): 0 p4c_src_t, 1 p4c_mlp_t,
+ * 2 p4c_mlp_bwd_t, 3 p4c_ar_x_t, 4 p4c_adamw_state_t, 5 p4c_pack_t, 6 p4c_wgrad_t; -1 otherwise */
+int p4c_sizeof(int which);
 
 /* ------------------------------------------------------------------------
  * CSR construction (bit-exact w.r.t. a stable sort by key).
@@ -86,6 +89,15 @@ typedef struct {
   int64_t batch_stride; /* elements between samples (0 = shared by all samples)  */
   int32_t ld;
   int32_t width;
+  /* Segment-sum source (forward only, 64-wide, tensor-core engine): when seg_rowptr != NULL, input
+   * row r is  seg_scale[r] * sum_{j in [seg_rowptr[r], seg_rowptr[r+1])} ptr[b][seg_perm ? seg_perm[j] : j][:]
+   * i.e. InteractionNet.aggregate (K3) fused into the prologue of the node MLP (K4); `index` must be
+   * NULL.  seg_out (optional, [batch][full_rows][64], same dtype) receives the summed rows (they are
+   * the saved activation the backward needs).                                                     */
+  const int32_t* seg_rowptr;
+  const int32_t* seg_perm;
+  const float* seg_scale;
+  void* seg_out;
 } p4c_src_t;
 
 typedef struct {
@@ -107,7 +119,32 @@ typedef struct {
   const float* gamma; /* [64] or NULL */
   const float* beta;  /* [64] or NULL */
   float ln_eps;
+  /* optional P4C_PACK_BYTES image of the weights produced by p4c_pack_weights (bf16, laid out
+   * for the tensor-core engine); NULL = the kernels convert w1/w2 themselves (slower set-up).
+   * The image must have been packed from the current values of w1..beta.                       */
+  const void* packed;
 } p4c_mlp_t;
+
+/* ------------------------------------------------------------------------
+ * Weight images for the tensor-core engine.  One image per MLP:
+ *   [W1 k-block 0..2 : 3 x 8 KB][W2 : 8 KB][W2^T : 8 KB][W1^T k-block 0..2 : 3 x 8 KB]
+ *   [b1, b2, gamma, beta : 4 x 64 fp32]
+ * every 8 KB block is a 64x64 bf16 matrix in the 128-byte-swizzled K-major shared-memory layout
+ * tcgen05.mma reads, so a CTA stages it with plain 16-byte copies.  K-blocks follow the sources:
+ * a source of width w contributes ceil(w/64) blocks (columns beyond w are zero).
+ * p4c_pack_weights converts `n` MLPs in ONE launch from a DEVICE table of descriptors.
+ * ---------------------------------------------------------------------- */
+#define P4C_PACK_BYTES (8 * 8192 + 4 * 64 * 4)
+typedef struct {
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  const float* gamma; const float* beta; /* NULL -> 1 / 0 */
+  void* dst;                               /* P4C_PACK_BYTES, 16-byte aligned */
+  int32_t k1;
+  int32_t out_features;
+  int32_t nsrc;
+  int32_t width[P4C_MAX_SRC];
+} p4c_pack_t;
+int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* stream);
 
 /*   residual  : optional [batch][rows][out_features] added to the output (K4 "rec + aggr_mlp(..)")
  *   out       : [batch][rows][out_features]
@@ -123,6 +160,16 @@ int p4c_get_engine(void);
 
 int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,
                     void* save_h1, float* save_stats, void* stream);
+
+/* p4c_mlp_forward with the aggregation of InteractionNet fused into the epilogue (K2+K3), for edge
+ * sets whose edges are sorted by receiver with a uniform in-degree `group` (a power of two <= 32
+ * that divides rows and full_rows, e.g. the 4 nearest mesh nodes of every grid node in m2g):
+ *   aggr_out[b][r / group][:] = scale * sum of the `group` consecutive messages y[b][r..][:]
+ * (fp32 sum of the un-rounded messages, fixed butterfly order).  `out` (the messages) may be NULL:
+ * they are then never written to memory.  Tensor-core engine, bf16 storage, out_features = 64. */
+int p4c_mlp_forward_aggregate(const p4c_mlp_t* m, void* out, void* out2, void* save_h1,
+                              float* save_stats, void* aggr_out, int32_t group, float scale,
+                              void* stream);
 
 /* Backward.
  *   dy_a (+ dy_b): gradient w.r.t. y; dy_a may be gathered through dy_a_index
@@ -151,7 +198,38 @@ typedef struct {
   float* g_w1; float* g_b1; float* g_w2; float* g_b2; float* g_gamma; float* g_beta;
   float* wgrad_partials;
   int64_t wgrad_partials_floats;
+  /* 0: partials are overwritten and reduced into g_* by this call (self-contained);
+   * 1: partials are overwritten, the reduction is deferred to p4c_wgrad_reduce_batched;
+   * 2: this call ADDS to the partials already in the workspace (same grid), reduction deferred.
+   * Deferred modes need a workspace that belongs to this MLP alone (g_* are ignored).          */
+  int32_t partials_mode;
 } p4c_mlp_bwd_t;
+
+/* number of per-CTA partial blocks p4c_mlp_backward writes for this problem (its grid) */
+int32_t p4c_mlp_wgrad_blocks(const p4c_mlp_t* m);
+
+/* Deferred weight-gradient reduction of `n` MLPs in ONE launch (DEVICE table): g_* += sum over the
+ * per-CTA partial blocks, in a fixed order.  Any g_* pointer may be NULL.                        */
+typedef struct {
+  const float* partials;
+  float* g_w1; float* g_b1; float* g_w2; float* g_b2; float* g_gamma; float* g_beta;
+  int32_t nblocks;
+  int32_t k1;
+  int32_t out_features;
+  int32_t _pad;
+} p4c_wgrad_t;
+int p4c_wgrad_reduce_batched(const p4c_wgrad_t* table_dev, int32_t n, void* stream);
+
+/* out[b, r, :] (+)= ( scale[r] * sum_{j in seg r} src[b, perm ? perm[j] : j, :] ) x W[:, col0 : col0+64]
+ * with W = w1 [64][k1]: segment sum + input-gradient GEMM of one 64-wide gathered source in one
+ * kernel (replaces p4c_segment_sum + p4c_rows_matmul in the InteractionNet backward).  Tensor-core
+ * engine, bf16 storage only (fp32 callers keep the two-call form).  `packed` (optional) is the weight
+ * image of the MLP w1 belongs to and `kblock` the K-block of it that starts at column col0 (the
+ * kernel converts w1 itself when packed is NULL).                                                */
+int p4c_seg_linear(const void* src, int64_t src_batch_stride, const int32_t* rowptr,
+                   const int32_t* perm, const float* scale, int32_t num_seg, int32_t batch,
+                   const float* w1, int32_t k1, int32_t col0, const void* packed, int32_t kblock,
+                   void* out, int64_t out_batch_stride, int accumulate, int dtype, void* stream);
 
 int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m);
 int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream);
@@ -183,6 +261,8 @@ typedef struct {
   int64_t stat_batch_stride; /* 0 if shared */
   const float* forcing;  /* [batch][nodes][F_f] for the step the x is built for */
   int64_t forcing_batch_stride;
+  int32_t x_ld;          /* row stride of x (elements); 0 = dense (T_in*F + F_s + F_f).  Padding
+                            columns are written as zeros (the tensor-core MLP reads them).       */
 } p4c_ar_x_t;
 
 /* x[b,n,:] = cat(prev[0..T_in-1], static, forcing)      (lightning.py:711-767 `_next_x`)
@@ -216,8 +296,8 @@ int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev_last,
 int p4c_ar_step_backward(const float* g_new, int64_t g_new_batch_stride, const void* g_xnext,
                          int x_dtype, const float* border, const float* diff_std,
                          int32_t batch, int32_t nodes, int32_t f_state, int32_t num_prev,
-                         int32_t f_in, void* dy, int y_dtype, float* const* d_prev,
-                         void* stream);
+                         int32_t f_in /* row stride of g_xnext */, void* dy, int y_dtype,
+                         float* const* d_prev, void* stream);
 
 /* ------------------------------------------------------------------------
  * Losses (reference py4cast/losses.py:103-210).

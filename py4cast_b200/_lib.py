@@ -28,6 +28,10 @@ class Src(C.Structure):
         ("batch_stride", C.c_int64),
         ("ld", C.c_int32),
         ("width", C.c_int32),
+        ("seg_rowptr", C.c_void_p),
+        ("seg_perm", C.c_void_p),
+        ("seg_scale", C.c_void_p),
+        ("seg_out", C.c_void_p),
     ]
 
 
@@ -49,6 +53,7 @@ class Mlp(C.Structure):
         ("gamma", C.c_void_p),
         ("beta", C.c_void_p),
         ("ln_eps", C.c_float),
+        ("packed", C.c_void_p),
     ]
 
 
@@ -74,6 +79,28 @@ class MlpBwd(C.Structure):
         ("g_beta", C.c_void_p),
         ("wgrad_partials", C.c_void_p),
         ("wgrad_partials_floats", C.c_int64),
+        ("partials_mode", C.c_int32),
+    ]
+
+
+PACK_BYTES = 8 * 8192 + 4 * 64 * 4
+
+
+class Pack(C.Structure):
+    _fields_ = [
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("dst", C.c_void_p),
+        ("k1", C.c_int32), ("out_features", C.c_int32), ("nsrc", C.c_int32),
+        ("width", C.c_int32 * MAX_SRC),
+    ]
+
+
+class WGrad(C.Structure):
+    _fields_ = [
+        ("partials", C.c_void_p),
+        ("g_w1", C.c_void_p), ("g_b1", C.c_void_p), ("g_w2", C.c_void_p), ("g_b2", C.c_void_p),
+        ("g_gamma", C.c_void_p), ("g_beta", C.c_void_p),
+        ("nblocks", C.c_int32), ("k1", C.c_int32), ("out_features", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -91,6 +118,7 @@ class ArX(C.Structure):
         ("stat_batch_stride", C.c_int64),
         ("forcing", C.c_void_p),
         ("forcing_batch_stride", C.c_int64),
+        ("x_ld", C.c_int32),
     ]
 
 
@@ -111,13 +139,21 @@ SYMBOLS = {
     "p4c_version": (_int, []),
     "p4c_launch_count": (_i64, []),
     "p4c_reset_launch_count": (None, []),
+    "p4c_sizeof": (_int, [_int]),
     "p4c_csr_build": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "p4c_index_to_i32": (_int, [_vp, _vp, _i64, _vp]),
     "p4c_segment_sum": (_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _int, _int, _int, _vp]),
     "p4c_set_engine": (None, [_int]),
     "p4c_get_engine": (_int, []),
     "p4c_mlp_forward": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p4c_mlp_forward_aggregate": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),
     "p4c_mlp_wgrad_partial_floats": (_i64, [C.POINTER(Mlp)]),
+    "p4c_mlp_wgrad_blocks": (_i32, [C.POINTER(Mlp)]),
+    "p4c_pack_weights": (_int, [_vp, _i32, _vp]),
+    "p4c_wgrad_reduce_batched": (_int, [_vp, _i32, _vp]),
+    "p4c_seg_linear": (
+        _int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _int, _int, _vp]
+    ),
     "p4c_mlp_backward": (_int, [C.POINTER(Mlp), C.POINTER(MlpBwd), _vp]),
     "p4c_rows_matmul": (_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _int, _int, _vp]),
     "p4c_batch_sum": (_int, [_vp, _i64, _i32, _i64, _vp, _int, _int, _vp]),
@@ -170,6 +206,12 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
+    for which, st in enumerate((Src, Mlp, MlpBwd, ArX, AdamWState, Pack, WGrad)):
+        if lib.p4c_sizeof(which) != C.sizeof(st):
+            raise RuntimeError(
+                f"py4cast_b200: ctypes layout of {st.__name__} ({C.sizeof(st)} B) does not match the "
+                f"compiled library ({lib.p4c_sizeof(which)} B): rebuild it"
+            )
     _lib = lib
     return lib
 

@@ -45,13 +45,18 @@ __global__ void __launch_bounds__(256)
 ar_concat_kernel(const p4c_ar_x_t a, TX* __restrict__ x) {
   const int F = a.f_state;
   const int f_in = a.num_prev * F + a.f_static + a.f_forcing;
-  const long long per_b = (long long)a.nodes * f_in;
+  const int ld = a.x_ld > 0 ? a.x_ld : f_in;  // padded row stride: padding columns are zeroed
+  const long long per_b = (long long)a.nodes * ld;
   const long long total = per_b * a.batch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per_b);
     const long long rem = i - (long long)b * per_b;
-    const int n = (int)(rem / f_in), k = (int)(rem - (long long)n * f_in);
+    const int n = (int)(rem / ld), k = (int)(rem - (long long)n * ld);
+    if (k >= f_in) {
+      x[i] = from_f32<TX>(0.f);
+      continue;
+    }
     bool last;
     int f;
     float v = ar_x_value<TX>(a, b, n, k, &last, &f);
@@ -111,13 +116,18 @@ __global__ void __launch_bounds__(256)
 ar_step_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x) {
   const int F = a.f_state;
   const int f_in = a.num_prev * F + a.f_static + a.f_forcing;
-  const long long per_b = (long long)a.nodes * f_in;
+  const int ld = a.x_ld > 0 ? a.x_ld : f_in;  // padded row stride: padding columns are zeroed
+  const long long per_b = (long long)a.nodes * ld;
   const long long total = per_b * a.batch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per_b);
     const long long rem = i - (long long)b * per_b;
-    const int n = (int)(rem / f_in), k = (int)(rem - (long long)n * f_in);
+    const int n = (int)(rem / ld), k = (int)(rem - (long long)n * ld);
+    if (k >= f_in) {
+      x[i] = from_f32<TX>(0.f);
+      continue;
+    }
     bool last;
     int f;
     float v = ar_x_value<TX>(a, b, n, k, &last, &f);
@@ -369,6 +379,8 @@ static int check_ar_x(const p4c_ar_x_t* a, bool last_may_be_null) {
                 "ar: prev[%d] is null", t);
   P4C_REQUIRE(a->f_static == 0 || a->stat, "ar: static features missing");
   P4C_REQUIRE(a->f_forcing == 0 || a->forcing, "ar: forcing missing");
+  P4C_REQUIRE(a->x_ld == 0 || a->x_ld >= a->num_prev * a->f_state + a->f_static + a->f_forcing,
+              "ar: x_ld=%d smaller than the row width", a->x_ld);
   return P4C_OK;
 }
 
@@ -380,8 +392,8 @@ extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* st
   int rc = check_ar_x(a, false);
   if (rc) return rc;
   P4C_REQUIRE(x != nullptr, "ar_concat: x is null");
-  const long long total =
-      (long long)a->batch * a->nodes * (a->num_prev * a->f_state + a->f_static + a->f_forcing);
+  const int f_in = a->num_prev * a->f_state + a->f_static + a->f_forcing;
+  const long long total = (long long)a->batch * a->nodes * (a->x_ld > 0 ? a->x_ld : f_in);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == P4C_F32)
     ar_concat_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(*a, (float*)x);
@@ -421,8 +433,8 @@ extern "C" int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev
   P4C_REQUIRE(next->batch == batch && next->nodes == nodes && next->f_state == f_state,
               "ar_step_forward: next-x descriptor does not match the state shape");
   P4C_REQUIRE(x_dtype == P4C_F32 || x_dtype == P4C_BF16, "ar_step_forward: bad x dtype");
-  const long long total =
-      (long long)batch * nodes * (next->num_prev * f_state + next->f_static + next->f_forcing);
+  const int f_in = next->num_prev * f_state + next->f_static + next->f_forcing;
+  const long long total = (long long)batch * nodes * (next->x_ld > 0 ? next->x_ld : f_in);
   const int grid = grid_for(total, 256);
   if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
     ar_step_kernel<float, float><<<grid, 256, 0, st>>>(s, *next, (float*)x_next);

@@ -624,47 +624,6 @@ mlp2_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g) {
   }
 }
 
-// g_* += sum over CTAs (fixed order) of the partials; transposes W partials to nn.Linear layout
-__global__ void mlp2_wgrad_reduce_kernel(const float* __restrict__ partials, int nblocks, int k1,
-                                         int out_features, float* g_w1, float* g_b1, float* g_w2,
-                                         float* g_b2, float* g_gamma, float* g_beta) {
-  const int k1pad = (k1 + KC - 1) / KC * KC;
-  const long long pf = partial_floats(k1);
-  const long long n_w1 = (long long)k1 * HID, n_w2 = (long long)out_features * HID;
-  const long long total = n_w1 + n_w2 + 4 * HID;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long src;
-    float* dst;
-    if (i < n_w1) {  // g_w1[c][k]  <- partial dW1[k][c]
-      const int c = (int)(i / k1), k = (int)(i % k1);
-      src = (long long)k * HID + c;
-      dst = g_w1 ? g_w1 + i : nullptr;
-    } else if (i < n_w1 + n_w2) {  // g_w2[c][k] <- partial dW2[k][c]
-      const long long j = i - n_w1;
-      const int c = (int)(j / HID), k = (int)(j % HID);
-      src = (long long)k1pad * HID + (long long)k * HID + c;
-      dst = g_w2 ? g_w2 + j : nullptr;
-    } else {
-      const long long j = i - n_w1 - n_w2;
-      const int v = (int)(j / HID), c = (int)(j % HID);
-      src = (long long)k1pad * HID + HID * HID + j;
-      float* base = v == 0 ? g_b1 : v == 1 ? g_b2 : v == 2 ? g_gamma : g_beta;
-      dst = (base && (v != 1 || c < out_features)) ? base + c : nullptr;
-    }
-    if (!dst) continue;
-    // fixed-shape reduction tree: 8 interleaved partial sums (8 independent loads in flight)
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int b = 0;
-    for (; b + 8 <= nblocks; b += 8) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] += partials[(long long)(b + j) * pf + src];
-    }
-    for (int j = 0; b < nblocks; ++b, ++j) a[j] += partials[(long long)b * pf + src];
-    *dst += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  }
-}
-
 // out[b,r,:] (+)= in[b,r,:] x w1[:, col0:col0+64]      (64x64 slice of the layer-1 weight)
 struct RmSmem {
   float Xs[TM * HS_LD];
@@ -738,6 +697,9 @@ static int validate(const p4c_mlp_t* m) {
   P4C_REQUIRE(m->nsrc > 1 || m->src[0].index == nullptr || m->src[0].width == HID,
               "mlp: dense (non-64) source cannot be gathered");
   P4C_REQUIRE(m->w1 && m->b1 && m->w2 && m->b2, "mlp: null weights");
+  for (int s = 0; s < m->nsrc; ++s)
+    P4C_REQUIRE(!m->src[s].seg_rowptr || (m->dtype == P4C_BF16 && tc_engine_enabled()),
+                "mlp: segment-sum sources need the tensor-core engine (bf16 storage)");
   return P4C_OK;
 }
 
@@ -774,6 +736,26 @@ using namespace p4c;
 extern "C" void p4c_set_engine(int tensor_cores) { g_tc_enabled = tensor_cores ? 1 : 0; }
 extern "C" int p4c_get_engine(void) { return tc_engine_enabled() ? 1 : 0; }
 
+extern "C" int p4c_mlp_forward_aggregate(const p4c_mlp_t* m, void* out, void* out2, void* save_h1,
+                                         float* save_stats, void* aggr_out, int32_t group, float scale,
+                                         void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  P4C_REQUIRE(aggr_out != nullptr, "mlp_forward_aggregate: aggr_out is null");
+  P4C_REQUIRE(group >= 1 && group <= 32 && (group & (group - 1)) == 0,
+              "mlp_forward_aggregate: group=%d must be a power of two <= 32", group);
+  const int full = m->full_rows > 0 ? m->full_rows : m->rows;
+  P4C_REQUIRE(m->rows % group == 0 && full % group == 0, "mlp_forward_aggregate: rows=%d / full_rows=%d not a multiple of group=%d",
+              m->rows, full, group);
+  P4C_REQUIRE(m->out_features == HID, "mlp_forward_aggregate: out_features must be 64");
+  P4C_REQUIRE(!out2 || (m->src[0].width == HID && m->src[0].index == nullptr),
+              "mlp_forward: out2 needs a 64-wide identity-indexed src[0]");
+  P4C_REQUIRE(tc_engine_enabled() && tc_forward_supported(m) && reinterpret_cast<uintptr_t>(aggr_out) % 16 == 0,
+              "mlp_forward_aggregate: needs the tensor-core engine (bf16 storage, aligned 64-wide sources)");
+  return launch_mlp2_tc_forward(m, nullptr, out, out2, save_h1, save_stats, aggr_out, group, scale,
+                                (cudaStream_t)stream);
+}
+
 extern "C" int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,
                                void* save_h1, float* save_stats, void* stream) {
   int rc = validate(m);
@@ -783,7 +765,9 @@ extern "C" int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* o
               "mlp_forward: out2 needs a 64-wide identity-indexed src[0]");
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_engine_enabled() && tc_forward_supported(m))
-    return launch_mlp2_tc_forward(m, residual, out, out2, save_h1, save_stats, st);
+    return launch_mlp2_tc_forward(m, residual, out, out2, save_h1, save_stats, nullptr, 0, 0.f, st);
+  for (int s = 0; s < m->nsrc; ++s)
+    P4C_REQUIRE(!m->src[s].seg_rowptr, "mlp_forward: segment-sum source not supported for this shape / alignment");
   const long long total = (long long)m->rows * m->batch;
   const long long ntiles = (total + TM - 1) / TM;
   const int grid = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
@@ -811,6 +795,12 @@ static int bwd_grid(const p4c_mlp_t* m) {
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 
+extern "C" int32_t p4c_mlp_wgrad_blocks(const p4c_mlp_t* m) {
+  if (!m || m->rows <= 0 || m->batch <= 0) return 0;
+  const int g_simt = bwd_grid(m), g_tc = tc_backward_grid(m);
+  return g_simt > g_tc ? g_simt : g_tc;
+}
+
 extern "C" int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m) {
   if (!m || m->rows <= 0 || m->batch <= 0) return 0;
   const int g_simt = bwd_grid(m), g_tc = tc_backward_grid(m);  // either engine may serve the call
@@ -828,13 +818,18 @@ extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void
   for (int s = 0; s < m->nsrc; ++s)
     P4C_REQUIRE(!g->dx[s] || m->src[s].index == nullptr,
                 "mlp_backward: dx[%d] requested for a gathered source (use dh1 + segment_sum)", s);
+  P4C_REQUIRE(g->partials_mode >= 0 && g->partials_mode <= 2, "mlp_backward: bad partials_mode %d", g->partials_mode);
   cudaStream_t st = (cudaStream_t)stream;
   int grid;
   if (tc_engine_enabled() && tc_backward_supported(m, g)) {
     grid = tc_backward_grid(m);
     rc = launch_mlp2_tc_backward(m, g, st);
     if (rc) return rc;
+    if (g->partials_mode != 0) return P4C_OK;  // reduction deferred to p4c_wgrad_reduce_batched
   } else {
+  P4C_REQUIRE(g->partials_mode == 0, "mlp_backward: deferred weight-gradient reduction needs the tensor-core engine");
+  for (int s = 0; s < m->nsrc; ++s)
+    P4C_REQUIRE(!m->src[s].seg_rowptr, "mlp_backward: segment-sum sources are forward-only (pass the saved sums)");
   const int k1pad = (m->k1 + KC - 1) / KC * KC;
   const size_t smem = sizeof(BwdSmemFixed) + (size_t)k1pad * HID * sizeof(float);
   P4C_REQUIRE(smem <= 227 * 1024, "mlp_backward: k1=%d needs %zu B of shared memory", m->k1, smem);
@@ -853,13 +848,12 @@ extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void
 #undef LAUNCH_BWD
   P4C_CHECK_LAUNCH("mlp_backward");
   }
-  const long long total = (long long)m->k1 * HID + (long long)m->out_features * HID + 4 * HID;
-  const int rgrid = (int)((total + 255) / 256);
-  mlp2_wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(g->wgrad_partials, grid, m->k1, m->out_features,
-                                                  g->g_w1, g->g_b1, g->g_w2, g->g_b2, g->g_gamma,
-                                                  g->g_beta);
-  P4C_CHECK_LAUNCH("mlp_wgrad_reduce");
-  return P4C_OK;
+  p4c_wgrad_t e;
+  e.partials = g->wgrad_partials;
+  e.g_w1 = g->g_w1; e.g_b1 = g->g_b1; e.g_w2 = g->g_w2; e.g_b2 = g->g_b2;
+  e.g_gamma = g->g_gamma; e.g_beta = g->g_beta;
+  e.nblocks = grid; e.k1 = m->k1; e.out_features = m->out_features; e._pad = 0;
+  return launch_wgrad_reduce_single(&e, st);
 }
 
 extern "C" int p4c_rows_matmul(const void* in, int64_t in_bs, const float* w, int32_t k1,

@@ -1,13 +1,21 @@
-// Tensor-core engine of the fused 2-layer MLP (bf16 storage, 64-wide sources):
-//   gather prologue (cp.async, 128-byte-swizzled smem tiles)  ->  tcgen05.mma (M=128, N=64, K=64 per
-//   source, fp32 accumulators in TMEM)  ->  epilogue from TMEM (bias, SiLU, second GEMM operand
-//   written back to smem)  ->  tcgen05.mma  ->  epilogue (bias, LayerNorm, residual / edge update).
+// Tensor-core engine of the fused 2-layer MLP — FORWARD (bf16 storage):
+//   gather prologue (cp.async into 128-byte-swizzled smem tiles; or an in-prologue segment sum)
+//   -> tcgen05.mma (M=128, N=64, K=64 per K-block, fp32 accumulators in TMEM)
+//   -> epilogue from TMEM (bias, SiLU, second GEMM operand written back to smem)
+//   -> tcgen05.mma -> epilogue (bias, LayerNorm, residual / edge update, optional fused
+//      aggregation over groups of consecutive rows).
 //
 // One CTA = 256 threads = one 128-row tile at a time, persistent over tiles, 2 CTAs per SM.  In the
 // epilogues warp w owns TMEM lanes 32*(w%4).. (rows) and columns 32*(w/4).. : two threads per row,
 // 32 columns each (LayerNorm needs one exchange of partial sums between them).  The gather of tile
 // t+1 is issued as soon as the first GEMM of tile t has drained the X buffer, so it overlaps both
 // epilogues and the second GEMM.
+//
+// Layer-1 input = up to 3 K-blocks of 64 columns (tc_common.cuh KBlocks): 64-wide sources (plain,
+// gathered through an index, or segment sums of another tensor) and dense sources of any width whose
+// row stride is a multiple of 8 elements (the padding must be finite: it is multiplied by zero
+// weights).  Weights come from a pre-packed bf16 image (p4c_pack_weights) with 16-byte copies, or
+// are converted in the kernel when no image is given.
 //
 // Same inputs / outputs / saved activations as the SIMT engine (mlp2.cu): the two are
 // interchangeable per call and cross-checked in tests/test_gpu_kernels.py.
@@ -30,17 +38,38 @@ struct FwdSmem {
   uint8_t A2[XBLK];
   uint8_t W1[P4C_MAX_SRC][WBLK];  // [n = hidden unit][k]  K-major, swizzled
   uint8_t W2[WBLK];               // [n = output unit][k]
-  float b1[HID], b2[HID], gamma[HID], beta[HID];
-  uint32_t row_off[2][P4C_MAX_SRC][TM];  // source row offset / 8 elements; ~0u = invalid row
+  float vec[4][HID];              // b1, b2, gamma, beta (image order)
+  uint32_t row_off[2][P4C_MAX_SRC][TM];  // block row offset / 8 elements (segment source: first
+                                         // edge of the segment); ~0u = invalid row
+  uint32_t seg_hi[2][TM];                // segment source: one past the last edge
+  uint32_t seg_base[2][TM];              // segment source: sample offset / 8 elements
+  float seg_sc[2][TM];                   // segment source: row scale (1/deg for mean aggregation)
   int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid
   float2 ln_part[2][TM];  // per-row partial (sum, sum of squares) of each column half
   uint64_t mbar[2];
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void row_info(const p4c_mlp_t& m, long long tile_row0, long long total_rows,
-                                         uint32_t (*row_off)[TM], int32_t* orow, int tid) {
+struct FwdArgs {
+  p4c_mlp_t m;
+  KBlocks kb;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out2;
+  __nv_bfloat16* save_h1;
+  float* save_stats;
+  // fused aggregation (optional): rows come in groups of `agg_group` consecutive rows (a power of
+  // two <= 32 dividing the sample's row count) whose y are summed into aggr_out[row / agg_group]
+  __nv_bfloat16* aggr_out;
+  int agg_group;
+  float agg_scale;
+  int zero_x;  // some block fetches fewer than 8 chunks per row: clear the tiles once
+};
+
+__device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, long long total_rows,
+                                         FwdSmem& S, int p, int tid) {
   if (tid >= TM) return;
+  const p4c_mlp_t& m = a.m;
   const long long g = tile_row0 + tid;
   long long o = -1;
   long long b = 0;
@@ -50,67 +79,105 @@ __device__ __forceinline__ void row_info(const p4c_mlp_t& m, long long tile_row0
     rr = static_cast<int>(g - b * m.rows);
     o = b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr;
   }
-  orow[tid] = static_cast<int32_t>(o);
-  for (int s = 0; s < m.nsrc; ++s) {
+  S.orow[p][tid] = static_cast<int32_t>(o);
+  for (int k = 0; k < a.kb.nblk; ++k) {
+    const p4c_src_t& src = m.src[a.kb.src[k]];
     uint32_t off = kNoRow;
-    if (o >= 0) {
-      const long long idx = m.src[s].index ? static_cast<long long>(m.src[s].index[rr]) : static_cast<long long>(rr);
-      off = static_cast<uint32_t>((b * m.src[s].batch_stride + idx * m.src[s].ld) >> 3);
+    if (src.seg_rowptr) {
+      uint32_t hi = 0, sbase = 0;
+      float sc = 1.f;
+      if (o >= 0) {
+        off = static_cast<uint32_t>(src.seg_rowptr[rr]);
+        hi = static_cast<uint32_t>(src.seg_rowptr[rr + 1]);
+        sbase = static_cast<uint32_t>((b * src.batch_stride) >> 3);
+        if (src.seg_scale) sc = src.seg_scale[rr];
+      }
+      S.seg_hi[p][tid] = hi;
+      S.seg_base[p][tid] = sbase;
+      S.seg_sc[p][tid] = sc;
+    } else if (o >= 0) {
+      const long long idx = src.index ? static_cast<long long>(src.index[rr]) : static_cast<long long>(rr);
+      off = static_cast<uint32_t>((b * src.batch_stride + idx * src.ld + a.kb.col0[k]) >> 3);
     }
-    row_off[s][tid] = off;
+    S.row_off[p][k][tid] = off;
   }
 }
 
-// 128 rows x 64 bf16 per source -> swizzled smem; 8 consecutive threads fetch one 128-byte row
-__device__ __forceinline__ void issue_gather(const p4c_mlp_t& m, const uint32_t (*row_off)[TM], uint8_t (*X)[XBLK],
-                                             int tid) {
-  for (int s = 0; s < m.nsrc; ++s) {
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[s].ptr);
-    const uint32_t xs = smem_u32(X[s]);
+// 128 rows x 64 bf16 per block -> swizzled smem; 8 consecutive threads handle one 128-byte row
+__device__ __forceinline__ void issue_gather(const FwdArgs& a, FwdSmem& S, int p, int tid) {
+  for (int k = 0; k < a.kb.nblk; ++k) {
+    const p4c_src_t& src = a.m.src[a.kb.src[k]];
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
+    const uint32_t xs = smem_u32(S.X[k]);
+    if (src.seg_rowptr) {
+      // InteractionNet.aggregate fused into the prologue (fixed summation order)
+      seg_sum_tile<NTHREADS>(base, src.seg_perm, S.row_off[p][k], S.seg_hi[p], S.seg_base[p], S.seg_sc[p],
+                             S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid);
+      continue;
+    }
+    const int nch = a.kb.nchunks[k];
 #pragma unroll
     for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
       const int idx = i * NTHREADS + tid;
       const int r = idx >> 3, j = idx & 7;
-      const uint32_t off = row_off[s][r];
-      const __nv_bfloat16* src = off != kNoRow ? base + (static_cast<long long>(off) << 3) + j * 8 : base;
-      cp_async16(xs + sw128_offset(r, j), src, off != kNoRow ? 16u : 0u);
+      if (j < nch) {
+        const uint32_t off = S.row_off[p][k][r];
+        const __nv_bfloat16* sp = off != kNoRow ? base + (static_cast<long long>(off) << 3) + j * 8 : base;
+        cp_async16(xs + sw128_offset(r, j), sp, off != kNoRow ? 16u : 0u);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
-mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                   __nv_bfloat16* __restrict__ out2, __nv_bfloat16* __restrict__ save_h1,
-                   float* __restrict__ save_stats) {
+__global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte swizzle needs 1024-byte aligned tiles
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(
       smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const p4c_mlp_t& m = a.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column half
   const int row = quad * 32 + lane, col0 = hsel * 32;
   const long long total_rows = static_cast<long long>(m.rows) * m.batch;
   const long long ntiles = (total_rows + TM - 1) / TM;
   const int OUT = m.out_features;
-  const int nsrc = m.nsrc;
+  const int nblk = a.kb.nblk;
+  __nv_bfloat16* const out = a.out;
+  __nv_bfloat16* const out2 = a.out2;
+  __nv_bfloat16* const save_h1 = a.save_h1;
+  const __nv_bfloat16* const residual = a.residual;
 
-  // ---- one-time set-up: weights -> bf16 swizzled tiles, vectors, barriers, TMEM
-  for (int i = tid; i < HID * m.k1; i += NTHREADS) {
-    const int c = i / m.k1, k = i - c * m.k1;
-    const int kb = k >> 6, kk = k & 63;
-    *reinterpret_cast<__nv_bfloat16*>(S.W1[kb] + sw128_offset(c, kk >> 3) + (kk & 7) * 2) =
-        __float2bfloat16_rn(m.w1[i]);
+  // ---- one-time set-up: weights (image: 16-byte async copies), barriers, TMEM
+  if (a.zero_x) {
+    uint4* xz = reinterpret_cast<uint4*>(S.X);
+    for (int i = tid; i < nblk * XBLK / 16; i += NTHREADS) xz[i] = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < HID * HID; i += NTHREADS) {
-    const int c = i >> 6, k = i & 63;
-    *reinterpret_cast<__nv_bfloat16*>(S.W2 + sw128_offset(c, k >> 3) + (k & 7) * 2) =
-        __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
-  }
-  if (tid < HID) {
-    S.b1[tid] = m.b1[tid];
-    S.b2[tid] = tid < OUT ? m.b2[tid] : 0.f;
-    S.gamma[tid] = m.gamma ? m.gamma[tid] : 1.f;
-    S.beta[tid] = m.beta ? m.beta[tid] : 0.f;
+  if (m.packed) {
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(m.packed);
+    for (int i = tid; i < nblk * (WBLK / 16); i += NTHREADS)
+      cp_async16(smem_u32(S.W1) + i * 16, img + PK_W1 + i * 16, 16u);
+    for (int i = tid; i < WBLK / 16; i += NTHREADS) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
+    if (tid < 64) cp_async16(smem_u32(S.vec) + tid * 16, img + PK_VEC + tid * 16, 16u);
+  } else {
+    for (int k = 0; k < nblk; ++k) {
+      const int ks = a.kb.kstart[k], kv = a.kb.kvalid[k];
+      for (int i = tid; i < HID * HID; i += NTHREADS) {
+        const int c = i >> 6, kk = i & 63;
+        *reinterpret_cast<__nv_bfloat16*>(S.W1[k] + sw128_offset(c, kk >> 3) + (kk & 7) * 2) =
+            __float2bfloat16_rn(kk < kv ? m.w1[static_cast<long long>(c) * m.k1 + ks + kk] : 0.f);
+      }
+    }
+    for (int i = tid; i < HID * HID; i += NTHREADS) {
+      const int c = i >> 6, k = i & 63;
+      *reinterpret_cast<__nv_bfloat16*>(S.W2 + sw128_offset(c, k >> 3) + (k & 7) * 2) =
+          __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
+    }
+    if (tid < HID) {
+      S.vec[0][tid] = m.b1[tid];
+      S.vec[1][tid] = tid < OUT ? m.b2[tid] : 0.f;
+      S.vec[2][tid] = m.gamma ? m.gamma[tid] : 1.f;
+      S.vec[3][tid] = m.beta ? m.beta[tid] : 0.f;
+    }
   }
   if (tid == 0) {
     mbar_init(&S.mbar[0], 1);
@@ -126,12 +193,16 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
   const uint32_t tmem = S.tmem_base;
   const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
   constexpr uint32_t IDESC = make_idesc_bf16(TM, HID, 0, 0);
+  const float* const b1 = S.vec[0];
+  const float* const b2 = S.vec[1];
+  const float* const gamma = S.vec[2];
+  const float* const beta = S.vec[3];
 
   long long tile = blockIdx.x;
   if (tile < ntiles) {
-    row_info(m, tile * TM, total_rows, S.row_off[0], S.orow[0], tid);
+    row_info(a, tile * TM, total_rows, S, 0, tid);
     __syncthreads();
-    issue_gather(m, S.row_off[0], S.X, tid);
+    issue_gather(a, S, 0, tid);
   }
   cp_async_commit();
 
@@ -140,27 +211,27 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
     const uint32_t parity = static_cast<uint32_t>(it & 1);
     cp_async_wait<0>();
     fence_proxy_async();
-    __syncthreads();  // X(tile) complete and visible to the tensor core
+    __syncthreads();  // X(tile) (and, first time, the weights) complete and visible to the tensor core
 
-    // ---- GEMM 1: D1[128x64] = X[128 x 64*nsrc] * W1^T
+    // ---- GEMM 1: D1[128x64] = X[128 x 64*nblk] * W1^T
     if (tid == 0) {
       tc_fence_after();
-      for (int s = 0; s < nsrc; ++s) {
-        const uint32_t xa = smem_u32(S.X[s]), wa = smem_u32(S.W1[s]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+      for (int k = 0; k < nblk; ++k) {
+        const uint32_t xa = smem_u32(S.X[k]), wa = smem_u32(S.W1[k]);
+        const int nk = (a.kb.kvalid[k] + 15) >> 4;  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+        for (int j = 0; j < nk; ++j)
           mma_bf16_ss(tmem, make_desc_sw128(xa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024),
-                      IDESC, (s | j) ? 1u : 0u);
+                      IDESC, (k | j) ? 1u : 0u);
       }
       mma_commit(&S.mbar[0]);
     }
     // meanwhile: addressing of the next tile
     const long long next = tile + gridDim.x;
-    if (next < ntiles) row_info(m, next * TM, total_rows, S.row_off[p ^ 1], S.orow[p ^ 1], tid);
+    if (next < ntiles) row_info(a, next * TM, total_rows, S, p ^ 1, tid);
     mbar_wait(&S.mbar[0], parity);
     tc_fence_after();
     __syncthreads();  // row_off[p^1] visible; X is free again
-    if (next < ntiles) issue_gather(m, S.row_off[p ^ 1], S.X, tid);
+    if (next < ntiles) issue_gather(a, S, p ^ 1, tid);
     cp_async_commit();
 
     // ---- epilogue 1: h1 = D1 + b1 (saved), a1 = SiLU(h1) -> A2 (bf16, swizzled)
@@ -174,7 +245,7 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
         const int c0 = col0 + j * 8;
         float h[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = v[j * 8 + q] + S.b1[c0 + q];
+        for (int q = 0; q < 8; ++q) h[q] = v[j * 8 + q] + b1[c0 + q];
         uint4 hb;
         hb.x = pack_bf16x2(h[0], h[1]); hb.y = pack_bf16x2(h[2], h[3]);
         hb.z = pack_bf16x2(h[4], h[5]); hb.w = pack_bf16x2(h[6], h[7]);
@@ -216,7 +287,7 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
       tmem_ld32(tmem_row + HID, y);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 32; ++q) y[q] += S.b2[col0 + q];
+      for (int q = 0; q < 32; ++q) y[q] += b2[col0 + q];
       if (m.layer_norm) {
         float ps = 0.f, pq = 0.f;
 #pragma unroll
@@ -231,21 +302,23 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
         const float var = fmaxf((lo.y + hi.y) * (1.0f / HID) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + m.ln_eps);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) y[q] = (y[q] - mean) * rstd * S.gamma[col0 + q] + S.beta[col0 + q];
-        if (save_stats && orow >= 0 && hsel == 0) {
-          save_stats[2 * orow] = mean;
-          save_stats[2 * orow + 1] = rstd;
+        for (int q = 0; q < 32; ++q) y[q] = (y[q] - mean) * rstd * gamma[col0 + q] + beta[col0 + q];
+        if (a.save_stats && orow >= 0 && hsel == 0) {
+          a.save_stats[2 * orow] = mean;
+          a.save_stats[2 * orow + 1] = rstd;
         }
       }
-      if (orow >= 0) {
-        if (OUT == HID) {
+      if (OUT == HID) {
+        if (orow >= 0 && (out || out2)) {
           const __nv_bfloat16* e_row =
               out2 ? reinterpret_cast<const __nv_bfloat16*>(m.src[0].ptr) +
                          (static_cast<long long>(S.row_off[p][0][row]) << 3) + col0
                    : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float* yy = y + j * 8;
+            float yy[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) yy[q] = y[j * 8 + q];
             const int c0 = col0 + j * 8;
             if (out2) {
               const uint4 e = *reinterpret_cast<const uint4*>(e_row + j * 8);
@@ -256,27 +329,50 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
               o.z = pack_bf16x2(e2.x + yy[4], e2.y + yy[5]); o.w = pack_bf16x2(e3.x + yy[6], e3.y + yy[7]);
               *reinterpret_cast<uint4*>(out2 + orow * HID + c0) = o;
             }
-            if (residual) {
-              const uint4 e = *reinterpret_cast<const uint4*>(residual + orow * HID + c0);
-              const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z),
-                           e3 = unpack_bf16x2(e.w);
-              yy[0] += e0.x; yy[1] += e0.y; yy[2] += e1.x; yy[3] += e1.y;
-              yy[4] += e2.x; yy[5] += e2.y; yy[6] += e3.x; yy[7] += e3.y;
+            if (out) {
+              if (residual) {
+                const uint4 e = *reinterpret_cast<const uint4*>(residual + orow * HID + c0);
+                const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z),
+                             e3 = unpack_bf16x2(e.w);
+                yy[0] += e0.x; yy[1] += e0.y; yy[2] += e1.x; yy[3] += e1.y;
+                yy[4] += e2.x; yy[5] += e2.y; yy[6] += e3.x; yy[7] += e3.y;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(yy[0], yy[1]); o.y = pack_bf16x2(yy[2], yy[3]);
+              o.z = pack_bf16x2(yy[4], yy[5]); o.w = pack_bf16x2(yy[6], yy[7]);
+              *reinterpret_cast<uint4*>(out + orow * HID + c0) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(yy[0], yy[1]); o.y = pack_bf16x2(yy[2], yy[3]);
-            o.z = pack_bf16x2(yy[4], yy[5]); o.w = pack_bf16x2(yy[6], yy[7]);
-            *reinterpret_cast<uint4*>(out + orow * HID + c0) = o;
           }
-        } else {
+        }
+        if (a.aggr_out) {
+          // fused aggregation: sum the messages of `agg_group` consecutive rows (= lanes) with a
+          // fixed butterfly (fp32, before any rounding); invalid rows contribute zero
+          const int gsz = a.agg_group;
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
-            const int c = col0 + q;
-            if (c < OUT) {
-              float v = y[q];
-              if (residual) v += __bfloat162float(residual[orow * OUT + c]);
-              out[orow * OUT + c] = __float2bfloat16_rn(v);
+            float v = orow >= 0 ? y[q] : 0.f;
+            for (int off = 1; off < gsz; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            y[q] = v * a.agg_scale;
+          }
+          if (orow >= 0 && (lane & (gsz - 1)) == 0) {
+            __nv_bfloat16* dst = a.aggr_out + (orow / gsz) * HID + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(y[j * 8 + 0], y[j * 8 + 1]); o.y = pack_bf16x2(y[j * 8 + 2], y[j * 8 + 3]);
+              o.z = pack_bf16x2(y[j * 8 + 4], y[j * 8 + 5]); o.w = pack_bf16x2(y[j * 8 + 6], y[j * 8 + 7]);
+              *reinterpret_cast<uint4*>(dst + j * 8) = o;
             }
+          }
+        }
+      } else if (orow >= 0) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int c = col0 + q;
+          if (c < OUT) {
+            float v = y[q];
+            if (residual) v += __bfloat162float(residual[orow * OUT + c]);
+            out[orow * OUT + c] = __float2bfloat16_rn(v);
           }
         }
       }
@@ -291,18 +387,50 @@ mlp2_tc_fwd_kernel(const p4c_mlp_t m, const __nv_bfloat16* __restrict__ residual
 
 }  // namespace tc
 
+static bool tc_src_ok(const p4c_src_t& s) {
+  if ((s.ld % 8) != 0 || (s.batch_stride % 8) != 0 || (reinterpret_cast<uintptr_t>(s.ptr) % 16) != 0) return false;
+  if ((s.index || s.seg_rowptr) && s.width != P4C_HIDDEN) return false;
+  if (s.seg_rowptr && (s.index || s.ld != P4C_HIDDEN)) return false;
+  if (s.seg_out && (reinterpret_cast<uintptr_t>(s.seg_out) % 16) != 0) return false;
+  return true;
+}
+
+bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb) {
+  int widths[P4C_MAX_SRC] = {0, 0, 0};
+  for (int s = 0; s < m->nsrc; ++s) widths[s] = m->src[s].width;
+  return tc::make_kblocks(m->nsrc, widths, kb);
+}
+
 bool tc_forward_supported(const p4c_mlp_t* m) {
   if (m->dtype != P4C_BF16) return false;
-  for (int s = 0; s < m->nsrc; ++s)
-    if (m->src[s].width != P4C_HIDDEN || (m->src[s].ld % 8) != 0 || (m->src[s].batch_stride % 8) != 0 ||
-        (reinterpret_cast<uintptr_t>(m->src[s].ptr) % 16) != 0)
-      return false;
+  tc::KBlocks kb;
+  if (!tc_kblocks(m, &kb)) return false;
+  int nseg = 0;
+  for (int s = 0; s < m->nsrc; ++s) {
+    if (!tc_src_ok(m->src[s])) return false;
+    nseg += m->src[s].seg_rowptr != nullptr;
+  }
+  if (nseg > 1) return false;
+  if (m->packed && (reinterpret_cast<uintptr_t>(m->packed) % 16) != 0) return false;
   return true;
 }
 
 int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
-                           float* save_stats, cudaStream_t st) {
+                           float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st) {
   using namespace tc;
+  FwdArgs a;
+  a.m = *m;
+  tc_kblocks(m, &a.kb);
+  a.residual = static_cast<const __nv_bfloat16*>(residual);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out2 = static_cast<__nv_bfloat16*>(out2);
+  a.save_h1 = static_cast<__nv_bfloat16*>(save_h1);
+  a.save_stats = save_stats;
+  a.aggr_out = static_cast<__nv_bfloat16*>(aggr_out);
+  a.agg_group = agg_group;
+  a.agg_scale = agg_scale;
+  a.zero_x = 0;
+  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
   const long long total = static_cast<long long>(m->rows) * m->batch;
   const long long ntiles = (total + TM - 1) / TM;
   const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
@@ -316,9 +444,7 @@ int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, 
     }
     configured = true;
   }
-  mlp2_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(
-      *m, static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out),
-      static_cast<__nv_bfloat16*>(out2), static_cast<__nv_bfloat16*>(save_h1), save_stats);
+  mlp2_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(a);
   P4C_CHECK_LAUNCH("mlp_forward(tc)");
   return P4C_OK;
 }

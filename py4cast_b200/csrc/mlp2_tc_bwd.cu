@@ -69,8 +69,18 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
-__device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, long long tile_row0, long long total_rows,
-                                             uint32_t (*row_off)[TM], int32_t* orow, int tid) {
+struct BwdArgs {
+  p4c_mlp_t m;
+  p4c_mlp_bwd_t g;
+  KBlocks kb;
+  int ndx;         // K-blocks whose input gradient is produced (<= 2)
+  int dx_blk[2];   // their block ids
+  int zero_x;      // some block fetches fewer than 8 chunks per row: clear the tiles once
+};
+
+__device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
+                                             long long total_rows, uint32_t (*row_off)[TM], int32_t* orow,
+                                             int tid) {
   if (tid >= TM) return;
   const long long g = tile_row0 + tid;
   long long o = -1, b = 0;
@@ -81,45 +91,52 @@ __device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, long long tile_
     o = b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr;
   }
   orow[tid] = static_cast<int32_t>(o);
-  for (int s = 0; s < m.nsrc; ++s) {
+  for (int k = 0; k < kb.nblk; ++k) {
+    const p4c_src_t& src = m.src[kb.src[k]];
     uint32_t off = kNoRow;
     if (o >= 0) {
-      const long long idx = m.src[s].index ? static_cast<long long>(m.src[s].index[rr]) : static_cast<long long>(rr);
-      off = static_cast<uint32_t>((b * m.src[s].batch_stride + idx * m.src[s].ld) >> 3);
+      const long long idx = src.index ? static_cast<long long>(src.index[rr]) : static_cast<long long>(rr);
+      off = static_cast<uint32_t>((b * src.batch_stride + idx * src.ld + kb.col0[k]) >> 3);
     }
-    row_off[s][tid] = off;
+    row_off[k][tid] = off;
   }
 }
 
-__device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const uint32_t (*row_off)[TM], uint8_t* xbase,
-                                           int tid) {
-  for (int s = 0; s < m.nsrc; ++s) {
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[s].ptr);
-    const uint32_t xs = smem_u32(xbase + s * BLK);
+__device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const KBlocks& kb, const uint32_t (*row_off)[TM],
+                                           uint8_t* xbase, int tid) {
+  for (int k = 0; k < kb.nblk; ++k) {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[kb.src[k]].ptr);
+    const uint32_t xs = smem_u32(xbase + k * BLK);
+    const int nch = kb.nchunks[k];
 #pragma unroll
     for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
       const int idx = i * NTHREADS + tid;
       const int r = idx >> 3, j = idx & 7;
-      const uint32_t off = row_off[s][r];
-      const __nv_bfloat16* src = off != kNoRow ? base + (static_cast<long long>(off) << 3) + j * 8 : base;
-      cp_async16(xs + sw128_offset(r, j), src, off != kNoRow ? 16u : 0u);
+      if (j < nch) {
+        const uint32_t off = row_off[k][r];
+        const __nv_bfloat16* src = off != kNoRow ? base + (static_cast<long long>(off) << 3) + j * 8 : base;
+        cp_async16(xs + sw128_offset(r, j), src, off != kNoRow ? 16u : 0u);
+      }
     }
   }
 }
 
 // shared-memory map (all tiles 1024-byte aligned):
-//   [X0 .. X(nsrc-1)] [A1] [DH] [W2] [W2T] [W1T x ndx] [BwdCtl]
-__host__ __device__ inline size_t bwd_smem_bytes(int nsrc, int ndx) {
-  return static_cast<size_t>(nsrc + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + sizeof(BwdCtl);
+//   [X0 .. X(nblk-1)] [A1] [DH] [W2] [W2T] [W1T x ndx] [BwdCtl]
+__host__ __device__ inline size_t bwd_smem_bytes(int nblk, int ndx) {
+  return static_cast<size_t>(nblk + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + sizeof(BwdCtl);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
-mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src0, int dx_src1) {
+__global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_constant__ BwdArgs args) {
   extern __shared__ unsigned char smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int nsrc = m.nsrc;
+  const p4c_mlp_t& m = args.m;
+  const p4c_mlp_bwd_t& g = args.g;
+  const KBlocks& kb = args.kb;
+  const int ndx = args.ndx;
+  const int nblk = kb.nblk;
   uint8_t* Xs = base;
-  uint8_t* A1 = base + nsrc * BLK;
+  uint8_t* A1 = base + nblk * BLK;
   uint8_t* DH = A1 + BLK;
   uint8_t* W2s = DH + BLK;
   uint8_t* W2T = W2s + WBLK;
@@ -133,28 +150,44 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   const long long ntiles = (total_rows + TM - 1) / TM;
   const int OUT = m.out_features;
   const bool ln = m.layer_norm != 0;
-  const int dxs[2] = {dx_src0, dx_src1};
+  const bool need_w = g.partials_mode != 0;  // deferred reduction: every weight gradient is produced
+  const bool need_w1 = need_w || g.g_w1 != nullptr, need_w2 = need_w || g.g_w2 != nullptr;
 
   // ---- one-time set-up
-  for (int i = tid; i < HID * HID; i += NTHREADS) {
-    const int c = i >> 6, k = i & 63;
-    const __nv_bfloat16 w = __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
-    *reinterpret_cast<__nv_bfloat16*>(W2s + sw128_offset(c, k >> 3) + (k & 7) * 2) = w;  // [n=c][K=k]
-    *reinterpret_cast<__nv_bfloat16*>(W2T + sw128_offset(k, c >> 3) + (c & 7) * 2) = w;  // [n=k][K=c]
+  if (args.zero_x) {
+    uint4* xz = reinterpret_cast<uint4*>(Xs);
+    for (int i = tid; i < nblk * BLK / 16; i += NTHREADS) xz[i] = make_uint4(0, 0, 0, 0);
   }
-  for (int d = 0; d < ndx; ++d) {
-    const int s = dxs[d];
+  if (m.packed) {
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(m.packed);
+    for (int i = tid; i < 2 * (WBLK / 16); i += NTHREADS)  // W2, W2T are adjacent in the image and in smem
+      cp_async16(smem_u32(W2s) + i * 16, img + PK_W2 + i * 16, 16u);
+    for (int d = 0; d < ndx; ++d)
+      for (int i = tid; i < WBLK / 16; i += NTHREADS)
+        cp_async16(smem_u32(W1T + d * WBLK) + i * 16, img + PK_W1T + args.dx_blk[d] * WBLK + i * 16, 16u);
+    if (tid < 16) cp_async16(smem_u32(C.b2) + tid * 16, img + PK_VEC + 256 + tid * 16, 16u);
+    else if (tid < 32) cp_async16(smem_u32(C.gamma) + (tid - 16) * 16, img + PK_VEC + 512 + (tid - 16) * 16, 16u);
+  } else {
     for (int i = tid; i < HID * HID; i += NTHREADS) {
-      const int c = i >> 6, k = i & 63;  // W1T_s[n=k][K=c] = w1[c][64 s + k]
-      const int kg = s * HID + k;
-      *reinterpret_cast<__nv_bfloat16*>(W1T + d * WBLK + sw128_offset(k, c >> 3) + (c & 7) * 2) =
-          __float2bfloat16_rn(kg < m.k1 ? m.w1[static_cast<long long>(c) * m.k1 + kg] : 0.f);
+      const int c = i >> 6, k = i & 63;
+      const __nv_bfloat16 w = __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
+      *reinterpret_cast<__nv_bfloat16*>(W2s + sw128_offset(c, k >> 3) + (k & 7) * 2) = w;  // [n=c][K=k]
+      *reinterpret_cast<__nv_bfloat16*>(W2T + sw128_offset(k, c >> 3) + (c & 7) * 2) = w;  // [n=k][K=c]
+    }
+    for (int d = 0; d < ndx; ++d) {
+      const int ks = kb.kstart[args.dx_blk[d]], kv = kb.kvalid[args.dx_blk[d]];
+      for (int i = tid; i < HID * HID; i += NTHREADS) {
+        const int c = i >> 6, k = i & 63;  // W1T_blk[n=k][K=c] = w1[c][kstart + k]
+        *reinterpret_cast<__nv_bfloat16*>(W1T + d * WBLK + sw128_offset(k, c >> 3) + (c & 7) * 2) =
+            __float2bfloat16_rn(k < kv ? m.w1[static_cast<long long>(c) * m.k1 + ks + k] : 0.f);
+      }
+    }
+    if (tid < HID) {
+      C.b2[tid] = tid < OUT ? m.b2[tid] : 0.f;
+      C.gamma[tid] = m.gamma ? m.gamma[tid] : 1.f;
     }
   }
-  if (tid < HID) {
-    C.b2[tid] = tid < OUT ? m.b2[tid] : 0.f;
-    C.gamma[tid] = m.gamma ? m.gamma[tid] : 1.f;
-  }
+  cp_async_commit();  // group 0: the weight image (empty when converted in the kernel)
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&C.mbar[i], 1);
     mbar_fence_init();
@@ -180,9 +213,9 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
 
   long long tile = blockIdx.x;
   if (tile < ntiles) {
-    bwd_row_info(m, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);
+    bwd_row_info(m, kb, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);
     __syncthreads();
-    bwd_gather(m, C.row_off[0], Xs, tid);
+    bwd_gather(m, kb, C.row_off[0], Xs, tid);
   }
   cp_async_commit();
 
@@ -193,6 +226,9 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     const long long orow = C.orow[p][row];  // -1 = row beyond the problem
     const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
+    // the weight image (first commit group) must have landed before the first MMA; later on
+    // this only leaves the newest group (the next tile's gather) in flight
+    cp_async_wait<1>();
     // ---- a. h1 half-row -> registers (packed bf16), a1 = SiLU(h1) -> A1 tile
     uint4 h1r[4];
 #pragma unroll
@@ -335,7 +371,7 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
       for (int j = 0; j < 4; ++j)
         mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
                     make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
-      if (g.g_w2) {
+      if (need_w2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // K = 128 rows, 16 per MMA = 2 groups of 8 rows = 2048 bytes
           mma_bf16_ss(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, BLK, 1024),
@@ -372,12 +408,12 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     if (tid == 0) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), xa = smem_u32(Xs);
-      if (g.g_w1) {
+      if (need_w1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           mma_bf16_ss(tmem + COL_DW1A, make_desc_sw128(xa + j * 2048, BLK, 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
-        if (nsrc == 3) {
+        if (nblk == 3) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             mma_bf16_ss(tmem + COL_DW1B, make_desc_sw128(xa + 2 * BLK + j * 2048, BLK, 1024),
@@ -395,11 +431,11 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     }
     // meanwhile: addressing of the next tile
     const long long next = tile + gridDim.x;
-    if (next < ntiles) bwd_row_info(m, next * TM, total_rows, C.row_off[p ^ 1], C.orow[p ^ 1], tid);
+    if (next < ntiles) bwd_row_info(m, kb, next * TM, total_rows, C.row_off[p ^ 1], C.orow[p ^ 1], tid);
     mbar_wait(&C.mbar[2], parity);
     tc_fence_after();
     __syncthreads();  // next row_off visible; X, A1 are free (DH still feeds a possible second dX)
-    if (next < ntiles) bwd_gather(m, C.row_off[p ^ 1], Xs, tid);
+    if (next < ntiles) bwd_gather(m, kb, C.row_off[p ^ 1], Xs, tid);
     cp_async_commit();
 
     // ---- g. dX stores (one or two identity-indexed sources)
@@ -419,10 +455,12 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
         mbar_wait(&C.mbar[3], parity);
         tc_fence_after();
       }
-      const int s = dxs[d];
-      __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(g.dx[s]);
+      const int blk = args.dx_blk[d];
+      const int s = kb.src[blk];
+      __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(g.dx[s]) + kb.col0[blk];
       const int ld = g.dx_ld[s];
-      const bool add_dy = (s == 0 && g.dx0_add_dy != 0);
+      const int nch = kb.nchunks[blk];
+      const bool add_dy = (blk == 0 && g.dx0_add_dy != 0);
       float v[32];
       tmem_ld32(tmem_row + COL_SCRATCH, v);
       tmem_ld_wait();
@@ -431,6 +469,7 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
         for (int j = 0; j < 4; ++j) {
           float* o = v + j * 8;
           const int c0 = col0 + j * 8;
+          if ((c0 >> 3) >= nch) continue;  // beyond the (padded) width of this block
           __nv_bfloat16* dst = dxp + orow * ld + c0;
           if (g.dx_accumulate[s]) {
             float e[8];
@@ -470,28 +509,36 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
   const int k1pad = (m.k1 + 31) / 32 * 32;
   const long long pf = static_cast<long long>(k1pad) * HID + HID * HID + 4 * HID;
   float* part = g.wgrad_partials + static_cast<long long>(blockIdx.x) * pf;
+  const bool padd = g.partials_mode == 2;  // add to what earlier calls left in this CTA's block
+  auto put32 = [&](float* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+      float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+      if (padd) {
+        const float4 e = *reinterpret_cast<const float4*>(dst + q);
+        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      }
+      *reinterpret_cast<float4*>(dst + q) = o;
+    }
+  };
   {
     float v[32];
-    // dW1[k = row][c] for sources 0,1 (TMEM lane = k)
+    // dW1[k][c] for K-blocks 0,1 (TMEM lane = 64 * block + k)
     tmem_ld32(tmem_row + COL_DW1A, v);
     tmem_ld_wait();
-    if (row < m.k1) {
-#pragma unroll
-      for (int q = 0; q < 32; ++q) part[static_cast<long long>(row) * HID + col0 + q] = v[q];
+    {
+      const int blk = row >> 6, kk = row & 63;
+      if (need_w1 && blk < nblk && kk < kb.kvalid[blk])
+        put32(part + static_cast<long long>(kb.kstart[blk] + kk) * HID + col0, v);
     }
     tmem_ld32(tmem_row + COL_DW1B, v);
     tmem_ld_wait();
-    if (nsrc == 3 && row < HID && 2 * HID + row < m.k1) {
-#pragma unroll
-      for (int q = 0; q < 32; ++q) part[static_cast<long long>(2 * HID + row) * HID + col0 + q] = v[q];
-    }
+    if (need_w1 && nblk == 3 && row < kb.kvalid[2])
+      put32(part + static_cast<long long>(kb.kstart[2] + row) * HID + col0, v);
     tmem_ld32(tmem_row + COL_DW2, v);
     tmem_ld_wait();
-    if (row < HID) {
-#pragma unroll
-      for (int q = 0; q < 32; ++q)
-        part[static_cast<long long>(k1pad) * HID + static_cast<long long>(row) * HID + col0 + q] = v[q];
-    }
+    if (need_w2 && row < HID)
+      put32(part + static_cast<long long>(k1pad) * HID + static_cast<long long>(row) * HID + col0, v);
   }
   // cross-warp sums in a fixed order; the A1 tile is free by now and serves as scratch
   float (*red)[4][32] = reinterpret_cast<float (*)[4][32]>(A1);  // [warp][vector][lane]
@@ -502,7 +549,10 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
     float* pv = part + static_cast<long long>(k1pad) * HID + HID * HID;
     const int w0 = (tid >> 5) * 4, l = tid & 31;  // column tid lives in warps w0..w0+3 (same hsel)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) pv[v * HID + tid] = (red[w0][v][l] + red[w0 + 1][v][l]) + (red[w0 + 2][v][l] + red[w0 + 3][v][l]);
+    for (int v = 0; v < 4; ++v) {
+      const float sum = (red[w0][v][l] + red[w0 + 1][v][l]) + (red[w0 + 2][v][l] + red[w0 + 3][v][l]);
+      pv[v * HID + tid] = padd ? pv[v * HID + tid] + sum : sum;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -511,22 +561,35 @@ mlp2_tc_bwd_kernel(const p4c_mlp_t m, const p4c_mlp_bwd_t g, int ndx, int dx_src
 
 }  // namespace tc
 
+bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb);
+
+static int tc_bwd_dx_blocks(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, const tc::KBlocks& kb, int* blks) {
+  int ndx = 0;
+  for (int k = 0; k < kb.nblk; ++k)
+    if (g->dx[kb.src[k]]) {
+      if (ndx < 2) blks[ndx] = k;
+      ++ndx;
+    }
+  return ndx;
+}
+
 bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g) {
   if (!tc_forward_supported(m)) return false;
-  int ndx = 0;
+  tc::KBlocks kb;
+  tc_kblocks(m, &kb);
   for (int s = 0; s < m->nsrc; ++s) {
-    if (g->dx[s]) {
-      ++ndx;
-      if (g->dx_ld[s] % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dx[s]) % 16) != 0) return false;
-    }
+    if (m->src[s].seg_rowptr) return false;  // the backward reads the saved segment sums as plain rows
+    if (g->dx[s] && (g->dx_ld[s] % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dx[s]) % 16) != 0)) return false;
   }
-  if (ndx > 2) return false;
+  int blks[2];
+  if (tc_bwd_dx_blocks(m, g, kb, blks) > 2) return false;
   if (m->out_features == P4C_HIDDEN) {
     if (g->dy_a_batch_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dy_a) % 16) != 0) return false;
     if (g->dy_b && (reinterpret_cast<uintptr_t>(g->dy_b) % 16) != 0) return false;
   }
   if (g->dh1_out && (reinterpret_cast<uintptr_t>(g->dh1_out) % 16) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(g->h1) % 16) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(g->wgrad_partials) % 16) != 0) return false;
   return true;
 }
 
@@ -538,10 +601,15 @@ int tc_backward_grid(const p4c_mlp_t* m) {
 
 int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st) {
   using namespace tc;
-  int dxs[2] = {-1, -1}, ndx = 0;
-  for (int s = 0; s < m->nsrc; ++s)
-    if (g->dx[s]) dxs[ndx++] = s;
-  const size_t smem = bwd_smem_bytes(m->nsrc, ndx) + 1024;
+  BwdArgs a;
+  a.m = *m;
+  a.g = *g;
+  tc_kblocks(m, &a.kb);
+  a.dx_blk[0] = a.dx_blk[1] = 0;
+  a.ndx = tc_bwd_dx_blocks(m, g, a.kb, a.dx_blk);
+  a.zero_x = 0;
+  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  const size_t smem = bwd_smem_bytes(a.kb.nblk, a.ndx) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp2_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -551,7 +619,7 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
     }
     configured = smem;
   }
-  mlp2_tc_bwd_kernel<<<tc_backward_grid(m), NTHREADS, smem, st>>>(*m, *g, ndx, dxs[0], dxs[1]);
+  mlp2_tc_bwd_kernel<<<tc_backward_grid(m), NTHREADS, smem, st>>>(a);
   P4C_CHECK_LAUNCH("mlp_backward(tc)");
   return P4C_OK;
 }

@@ -1,0 +1,292 @@
+// Weight images for the tensor-core engine, the (batched) weight-gradient reduction and the fused
+// segment-sum + input-gradient GEMM of gathered sources.
+//
+//   p4c_pack_weights         fp32 nn.Linear / LayerNorm parameters -> bf16 images in the swizzled
+//                            shared-memory layout of tcgen05.mma (ONE launch for a whole model; the
+//                            forward / backward kernels then stage their weights with 16-byte copies
+//                            instead of converting 16k values per CTA).
+//   p4c_wgrad_reduce_batched per-CTA weight-gradient partials of many MLPs -> g_* in ONE launch,
+//                            fixed summation order (bit-reproducible, no float atomics).
+//   p4c_seg_linear           d_x(node) = (sum of dh1 over the node's edges) x W1 slice: the transpose
+//                            of the gather of InteractionNet (K1/K3 backward), one kernel.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace p4c {
+
+constexpr int HIDP = P4C_HIDDEN;
+
+// ------------------------------------------------------------------------------ weight images
+// grid (n, 8): blockIdx.y = 8 KB block of the image (0-2 W1, 3 W2, 4 W2T, 5-7 W1T); y == 0 also
+// writes the vectors.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const p4c_pack_t* __restrict__ table) {
+  const p4c_pack_t e = table[blockIdx.x];
+  const int y = blockIdx.y, tid = threadIdx.x;
+  uint8_t* img = reinterpret_cast<uint8_t*>(e.dst);
+  tc::KBlocks kb;
+  tc::make_kblocks(e.nsrc, e.width, &kb);
+  uint8_t* dst = img + y * 8192;
+  const int OUT = e.out_features;
+  for (int i = tid; i < HIDP * HIDP; i += 256) {
+    const int n = i >> 6, kk = i & 63;  // image element [n][kk]
+    float v = 0.f;
+    if (y < 3) {  // W1 block y: [n = hidden unit][kk = input column of the block]
+      if (y < kb.nblk && kk < kb.kvalid[y]) v = e.w1[static_cast<long long>(n) * e.k1 + kb.kstart[y] + kk];
+    } else if (y == 3) {  // W2: [n = output unit][kk = hidden unit]
+      if (n < OUT) v = e.w2[n * HIDP + kk];
+    } else if (y == 4) {  // W2T: [n = hidden unit][kk = output unit]
+      if (kk < OUT) v = e.w2[kk * HIDP + n];
+    } else {  // W1T block y-5: [n = input column of the block][kk = hidden unit]
+      const int b = y - 5;
+      if (b < kb.nblk && n < kb.kvalid[b]) v = e.w1[static_cast<long long>(kk) * e.k1 + kb.kstart[b] + n];
+    }
+    *reinterpret_cast<__nv_bfloat16*>(dst + tc::sw128_offset(n, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  if (y == 0 && tid < HIDP) {
+    float* vec = reinterpret_cast<float*>(img + tc::PK_VEC);
+    vec[tid] = e.b1[tid];
+    vec[HIDP + tid] = tid < OUT ? e.b2[tid] : 0.f;
+    vec[2 * HIDP + tid] = e.gamma ? e.gamma[tid] : 1.f;
+    vec[3 * HIDP + tid] = e.beta ? e.beta[tid] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------- weight-gradient reduction
+// Partial block layout (see mlp2.cu / mlp2_tc_bwd.cu): dW1[k1pad][64] (k-major), dW2[64 hidden][64 out],
+// db1, db2, dgamma, dbeta [64] each.  Threads walk the partial layout (coalesced reads over all
+// blocks); the transposition to the nn.Linear layout happens on the single write.
+__host__ __device__ inline long long wg_partial_floats(int k1) {
+  const int k1pad = (k1 + 31) / 32 * 32;
+  return static_cast<long long>(k1pad) * HIDP + HIDP * HIDP + 4 * HIDP;
+}
+
+__device__ __forceinline__ void wgrad_reduce_entry(const p4c_wgrad_t& e, long long i0, long long stride) {
+  const int k1pad = (e.k1 + 31) / 32 * 32;
+  const long long pf = wg_partial_floats(e.k1);
+  const long long n1 = static_cast<long long>(k1pad) * HIDP;
+  for (long long i = i0; i < pf; i += stride) {
+    float* dst = nullptr;
+    if (i < n1) {  // partial dW1[k][c] -> g_w1[c][k]
+      const int k = static_cast<int>(i >> 6), c = static_cast<int>(i & 63);
+      if (e.g_w1 && k < e.k1) dst = e.g_w1 + static_cast<long long>(c) * e.k1 + k;
+    } else if (i < n1 + HIDP * HIDP) {  // partial dW2[k][c] -> g_w2[c][k]
+      const int j = static_cast<int>(i - n1);
+      const int k = j >> 6, c = j & 63;
+      if (e.g_w2 && c < e.out_features) dst = e.g_w2 + c * HIDP + k;
+    } else {
+      const int j = static_cast<int>(i - n1 - HIDP * HIDP);
+      const int v = j >> 6, c = j & 63;
+      float* base = v == 0 ? e.g_b1 : v == 1 ? e.g_b2 : v == 2 ? e.g_gamma : e.g_beta;
+      if (base && (v != 1 || c < e.out_features)) dst = base + c;
+    }
+    if (!dst) continue;
+    // fixed-shape reduction tree: 8 interleaved partial sums (8 independent loads in flight)
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* p = e.partials + i;
+    int b = 0;
+    for (; b + 8 <= e.nblocks; b += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += p[static_cast<long long>(b + j) * pf];
+    }
+    for (int j = 0; b < e.nblocks; ++b, ++j) a[j] += p[static_cast<long long>(b) * pf];
+    *dst += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const p4c_wgrad_t* __restrict__ table) {
+  const p4c_wgrad_t e = table[blockIdx.y];
+  wgrad_reduce_entry(e, blockIdx.x * 256ll + threadIdx.x, static_cast<long long>(gridDim.x) * 256);
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_single_kernel(const p4c_wgrad_t e) {
+  wgrad_reduce_entry(e, blockIdx.x * 256ll + threadIdx.x, static_cast<long long>(gridDim.x) * 256);
+}
+
+int launch_wgrad_reduce_single(const p4c_wgrad_t* e, cudaStream_t st) {
+  const long long pf = wg_partial_floats(e->k1);
+  wgrad_reduce_single_kernel<<<static_cast<int>((pf + 255) / 256), 256, 0, st>>>(*e);
+  P4C_CHECK_LAUNCH("mlp_wgrad_reduce");
+  return P4C_OK;
+}
+
+// ------------------------------------------------------------------ segment sum + 64x64 GEMM (TC)
+namespace tc {
+
+struct SegLinSmem {
+  uint8_t A[128 * 128];  // summed rows, bf16, swizzled
+  uint8_t W[64 * 128];   // [n = input column][k = hidden unit] = W1T block
+  uint32_t lo[128], hi[128], sbase[128];
+  float sc[128];
+  int32_t orow[128];
+  uint64_t mbar;
+  uint32_t tmem_base;
+};
+
+struct SegLinArgs {
+  const __nv_bfloat16* src;
+  long long src_bs;
+  const int32_t* rowptr;
+  const int32_t* perm;
+  const float* scale;
+  int num_seg, batch;
+  const float* w1;
+  int k1, col0;
+  const uint8_t* packed_block;  // PK_W1T block of the image, or NULL
+  __nv_bfloat16* out;
+  long long out_bs;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_constant__ SegLinArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  SegLinSmem& S = *reinterpret_cast<SegLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, hsel = warp >> 2;
+  const int row = quad * 32 + lane, col0 = hsel * 32;
+  const long long total = static_cast<long long>(a.num_seg) * a.batch;
+  const long long ntiles = (total + 127) / 128;
+
+  if (a.packed_block) {
+    for (int i = tid; i < 512; i += 256) cp_async16(smem_u32(S.W) + i * 16, a.packed_block + i * 16, 16u);
+  } else {
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int c = i >> 6, k = i & 63;  // W[n=k][K=c] = w1[c][col0 + k]
+      *reinterpret_cast<__nv_bfloat16*>(S.W + sw128_offset(k, c >> 3) + (c & 7) * 2) =
+          __float2bfloat16_rn(a.w1[static_cast<long long>(c) * a.k1 + a.col0 + k]);
+    }
+  }
+  cp_async_commit();
+  if (tid == 0) {
+    mbar_init(&S.mbar, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&S.tmem_base, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, 64, 0, 0);
+
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    if (tid < 128) {
+      const long long g = tile * 128 + tid;
+      uint32_t lo = 0xFFFFFFFFu, hi = 0, sb = 0;
+      float sc = 1.f;
+      int32_t o = -1;
+      if (g < total) {
+        const long long b = g / a.num_seg;
+        const int rr = static_cast<int>(g - b * a.num_seg);
+        lo = static_cast<uint32_t>(a.rowptr[rr]);
+        hi = static_cast<uint32_t>(a.rowptr[rr + 1]);
+        sb = static_cast<uint32_t>((b * a.src_bs) >> 3);
+        if (a.scale) sc = a.scale[rr];
+        o = static_cast<int32_t>((b * a.out_bs) / 64 + rr);
+      }
+      S.lo[tid] = lo; S.hi[tid] = hi; S.sbase[tid] = sb; S.sc[tid] = sc; S.orow[tid] = o;
+    }
+    __syncthreads();
+    seg_sum_tile<256>(a.src, a.perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid);
+    cp_async_wait<0>();  // the weight block (first tile)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aa = smem_u32(S.A), wa = smem_u32(S.W);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mma_bf16_ss(tmem, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024), IDESC,
+                    j ? 1u : 0u);
+      mma_commit(&S.mbar);
+    }
+    mbar_wait(&S.mbar, it & 1u);
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(tmem_row, v);
+    tmem_ld_wait();
+    const long long orow = S.orow[row];
+    if (orow >= 0) {
+      __nv_bfloat16* dst = a.out + orow * 64 + col0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* o = v + j * 8;
+        if (a.accumulate) {
+          const uint4 e = *reinterpret_cast<const uint4*>(dst + j * 8);
+          float2 t;
+          t = unpack_bf16x2(e.x); o[0] += t.x; o[1] += t.y;
+          t = unpack_bf16x2(e.y); o[2] += t.x; o[3] += t.y;
+          t = unpack_bf16x2(e.z); o[4] += t.x; o[5] += t.y;
+          t = unpack_bf16x2(e.w); o[6] += t.x; o[7] += t.y;
+        }
+        uint4 u;
+        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+        u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dst + j * 8) = u;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // A, row info and the accumulator may be overwritten
+  }
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+}  // namespace tc
+}  // namespace p4c
+
+using namespace p4c;
+
+extern "C" int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* stream) {
+  P4C_REQUIRE(n >= 0 && (n == 0 || table_dev), "pack_weights: bad arguments");
+  if (n == 0) return P4C_OK;
+  pack_weights_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  P4C_CHECK_LAUNCH("pack_weights");
+  return P4C_OK;
+}
+
+extern "C" int p4c_wgrad_reduce_batched(const p4c_wgrad_t* table_dev, int32_t n, void* stream) {
+  P4C_REQUIRE(n >= 0 && (n == 0 || table_dev), "wgrad_reduce_batched: bad arguments");
+  if (n == 0) return P4C_OK;
+  // 66 blocks of 256 threads cover the largest partial block (k1 = 192: 16 640 floats)
+  wgrad_reduce_batched_kernel<<<dim3(66, n), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  P4C_CHECK_LAUNCH("wgrad_reduce_batched");
+  return P4C_OK;
+}
+
+extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* rowptr, const int32_t* perm,
+                              const float* scale, int32_t num_seg, int32_t batch, const float* w1, int32_t k1,
+                              int32_t col0, const void* packed, int32_t kblock, void* out, int64_t out_bs,
+                              int accumulate, int dtype, void* stream) {
+  P4C_REQUIRE(src && rowptr && out && w1, "seg_linear: null pointer");
+  P4C_REQUIRE(num_seg > 0 && batch > 0, "seg_linear: empty problem");
+  P4C_REQUIRE(dtype == P4C_BF16, "seg_linear: tensor-core engine, bf16 storage only (dtype=%d)", dtype);
+  P4C_REQUIRE(col0 >= 0 && col0 + HIDP <= k1, "seg_linear: column window [%d,%d) outside k1=%d", col0, col0 + HIDP, k1);
+  P4C_REQUIRE(src_bs % 8 == 0 && out_bs % 64 == 0, "seg_linear: batch strides must be multiples of 8 / 64 elements");
+  P4C_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+              "seg_linear: src / out must be 16-byte aligned");
+  P4C_REQUIRE(!packed || (kblock >= 0 && kblock < P4C_MAX_SRC), "seg_linear: bad kblock %d", kblock);
+  using namespace tc;
+  SegLinArgs a;
+  a.src = static_cast<const __nv_bfloat16*>(src);
+  a.src_bs = src_bs;
+  a.rowptr = rowptr;
+  a.perm = perm;
+  a.scale = scale;
+  a.num_seg = num_seg;
+  a.batch = batch;
+  a.w1 = w1;
+  a.k1 = k1;
+  a.col0 = col0;
+  a.packed_block = packed ? static_cast<const uint8_t*>(packed) + PK_W1T + kblock * 8192 : nullptr;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out_bs = out_bs;
+  a.accumulate = accumulate;
+  const long long ntiles = (static_cast<long long>(num_seg) * batch + 127) / 128;
+  const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+  const size_t smem = sizeof(SegLinSmem) + 1024;
+  seg_linear_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  P4C_CHECK_LAUNCH("seg_linear");
+  return P4C_OK;
+}

@@ -199,6 +199,18 @@ extern "C" const char* p4c_last_error(void) { return g_err; }
 extern "C" int p4c_version(void) { return 100; }
 extern "C" int64_t p4c_launch_count(void) { return g_launches.load(); }
 extern "C" void p4c_reset_launch_count(void) { g_launches = 0; }
+extern "C" int p4c_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(p4c_src_t);
+    case 1: return (int)sizeof(p4c_mlp_t);
+    case 2: return (int)sizeof(p4c_mlp_bwd_t);
+    case 3: return (int)sizeof(p4c_ar_x_t);
+    case 4: return (int)sizeof(p4c_adamw_state_t);
+    case 5: return (int)sizeof(p4c_pack_t);
+    case 6: return (int)sizeof(p4c_wgrad_t);
+    default: return -1;
+  }
+}
 
 extern "C" int p4c_csr_build(const int64_t* keys, int64_t E, int32_t num_keys, int32_t* rowptr,
                              int32_t* perm, int32_t* scratch, void* stream) {

@@ -104,9 +104,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  const long long t0 = clock64();
-  while (!done) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    if ((spin & 1023u) == 1023u) {  // try_wait suspends in hardware; look at the clock rarely
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -153,6 +156,108 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+
+// ---- segment sum of 64-wide bf16 rows into one 128-row swizzled smem tile ------------------------
+// Row r of the tile = sc[r] * sum_{e in [lo[r], hi[r])} src[sbase[r]*8 + (perm ? perm[e] : e) * 64 ..]
+// (lo[r] == ~0u: zero row).  One warp per row at a time: lane = 8 * g + j sums the edges
+// lo+g, lo+g+4, ... of 16-byte chunk j (two interleaved partial sums), the 4 edge groups are then
+// combined with two shuffles: a fixed order, so the result is bit-reproducible.  fp32 accumulation,
+// one rounding to bf16.  Optionally also stores the rows to out_rows[orow[r]] (global).
+template <int NTHREADS>
+__device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ perm,
+                                             const uint32_t* lo, const uint32_t* hi, const uint32_t* sbase,
+                                             const float* sc, const int32_t* orow, uint8_t* X,
+                                             __nv_bfloat16* out_rows, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, j = lane & 7;
+#pragma unroll 1
+  for (int r = warp; r < 128; r += NTHREADS / 32) {
+    const uint32_t l = lo[r];
+    float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (l != 0xFFFFFFFFu) {
+      const uint32_t h = hi[r];
+      const __nv_bfloat16* sb = src + (static_cast<long long>(sbase[r]) << 3) + j * 8;
+      uint32_t e = l + g;
+      for (; e + 4 < h; e += 8) {
+        const long long e0 = perm ? perm[e] : e;
+        const long long e1 = perm ? perm[e + 4] : e + 4;
+        const uint4 u0 = *reinterpret_cast<const uint4*>(sb + e0 * 64);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(sb + e1 * 64);
+        float2 t;
+        t = unpack_bf16x2(u0.x); s0[0] += t.x; s0[1] += t.y;
+        t = unpack_bf16x2(u0.y); s0[2] += t.x; s0[3] += t.y;
+        t = unpack_bf16x2(u0.z); s0[4] += t.x; s0[5] += t.y;
+        t = unpack_bf16x2(u0.w); s0[6] += t.x; s0[7] += t.y;
+        t = unpack_bf16x2(u1.x); s1[0] += t.x; s1[1] += t.y;
+        t = unpack_bf16x2(u1.y); s1[2] += t.x; s1[3] += t.y;
+        t = unpack_bf16x2(u1.z); s1[4] += t.x; s1[5] += t.y;
+        t = unpack_bf16x2(u1.w); s1[6] += t.x; s1[7] += t.y;
+      }
+      if (e < h) {
+        const long long e0 = perm ? perm[e] : e;
+        const uint4 u0 = *reinterpret_cast<const uint4*>(sb + e0 * 64);
+        float2 t;
+        t = unpack_bf16x2(u0.x); s0[0] += t.x; s0[1] += t.y;
+        t = unpack_bf16x2(u0.y); s0[2] += t.x; s0[3] += t.y;
+        t = unpack_bf16x2(u0.z); s0[4] += t.x; s0[5] += t.y;
+        t = unpack_bf16x2(u0.w); s0[6] += t.x; s0[7] += t.y;
+      }
+    }
+    const float scale = sc[r];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = s0[q] + s1[q];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      s0[q] = v * scale;
+    }
+    if (g == 0) {
+      uint4 o;
+      o.x = pack_bf16x2(s0[0], s0[1]); o.y = pack_bf16x2(s0[2], s0[3]);
+      o.z = pack_bf16x2(s0[4], s0[5]); o.w = pack_bf16x2(s0[6], s0[7]);
+      *reinterpret_cast<uint4*>(X + sw128_offset(r, j)) = o;
+      if (out_rows && l != 0xFFFFFFFFu)
+        *reinterpret_cast<uint4*>(out_rows + static_cast<long long>(orow[r]) * 64 + j * 8) = o;
+    }
+  }
+}
+
+// ---- K-blocks of the layer-1 input ----------------------------------------------------------------
+// A source of width w contributes ceil(w/64) blocks of 64 columns (the last one zero-padded): the
+// unit of the gather (one 128x64 bf16 smem tile), of the W1 image and of the dW1 / dX products.
+struct KBlocks {
+  int nblk;
+  int src[P4C_MAX_SRC];      // source the block belongs to
+  int col0[P4C_MAX_SRC];     // first column inside the source (multiple of 64)
+  int kstart[P4C_MAX_SRC];   // first column of w1 the block multiplies
+  int kvalid[P4C_MAX_SRC];   // valid columns (1..64)
+  int nchunks[P4C_MAX_SRC];  // 16-byte chunks to fetch per row: ceil(kvalid/8); reads up to ld
+};
+inline __host__ __device__ bool make_kblocks(int nsrc, const int* widths, KBlocks* kb) {
+  int n = 0, k = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    for (int c0 = 0; c0 < widths[s]; c0 += 64) {
+      if (n >= P4C_MAX_SRC) return false;
+      kb->src[n] = s;
+      kb->col0[n] = c0;
+      kb->kstart[n] = k + c0;
+      kb->kvalid[n] = widths[s] - c0 < 64 ? widths[s] - c0 : 64;
+      kb->nchunks[n] = (kb->kvalid[n] + 7) / 8;
+      ++n;
+    }
+    k += widths[s];
+  }
+  kb->nblk = n;
+  for (int i = n; i < P4C_MAX_SRC; ++i) kb->src[i] = kb->col0[i] = kb->kstart[i] = kb->kvalid[i] = kb->nchunks[i] = 0;
+  return true;
+}
+
+// byte offsets inside a P4C_PACK_BYTES weight image
+constexpr int PK_W1 = 0;                 // 3 x 8 KB  [n = hidden unit][k]   (forward GEMM 1)
+constexpr int PK_W2 = 3 * 8192;          // [n = output unit][k = hidden]     (forward GEMM 2, bwd recompute)
+constexpr int PK_W2T = 4 * 8192;         // [n = hidden][k = output unit]     (bwd: da1 = dh2 W2)
+constexpr int PK_W1T = 5 * 8192;         // 3 x 8 KB  [n = input col][k = hidden unit]  (bwd: dX = dh1 W1)
+constexpr int PK_VEC = 8 * 8192;         // b1, b2, gamma, beta (4 x 64 fp32)
+static_assert(PK_VEC + 4 * 64 * 4 == P4C_PACK_BYTES, "weight image layout");
 
 }  // namespace tc
 }  // namespace p4c

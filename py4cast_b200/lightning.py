@@ -28,7 +28,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, ops
 from ._lib import MAX_PREV, ArX, check, dtype_code, ptr, stream
 from .base import ModelType, expand_to_batch, features_last_to_second, features_second_to_last
 from .datasets import DatasetInfo, ItemBatch, Statics
@@ -72,6 +72,15 @@ def _fill_arx(a: ArX, prevs: List[Optional[torch.Tensor]], static: torch.Tensor,
     a.stat_batch_stride = 0 if static.dim() == 2 else _bstride(static)
     a.forcing = ptr(forcing)
     a.forcing_batch_stride = _bstride(forcing)
+    a.x_ld = 0
+
+
+def _new_x(B: int, N: int, f_in: int, x_dtype: torch.dtype, device, a: ArX) -> torch.Tensor:
+    """(B,N,f_in) model input whose rows are padded for the tensor-core MLP (bf16: to a multiple of
+    8 elements; the AR kernels write zeros into the padding)."""
+    x = ops.empty_rows((B, N, f_in), x_dtype, device)
+    a.x_ld = x.stride(1)
+    return x
 
 
 def ar_concat(prevs: List[torch.Tensor], static: torch.Tensor, forcing: torch.Tensor,
@@ -81,9 +90,9 @@ def ar_concat(prevs: List[torch.Tensor], static: torch.Tensor, forcing: torch.Te
     if len(prevs) > MAX_PREV:
         raise ValueError(f"at most {MAX_PREV} input steps are supported")
     f_in = len(prevs) * F + static.shape[-1] + forcing.shape[-1]
-    x = torch.empty(B, N, f_in, dtype=x_dtype, device=prevs[0].device)
     a = ArX()
     _fill_arx(a, prevs, static, forcing, B, N, F)
+    x = _new_x(B, N, f_in, x_dtype, prevs[0].device, a)
     check(_lib.load().p4c_ar_concat(C.byref(a), ptr(x), dtype_code(x_dtype), stream()), "p4c_ar_concat")
     return x
 
@@ -107,9 +116,9 @@ class _ARStepFn(torch.autograd.Function):
             static, forcing = cfg["static"], cfg["forcing_next"]
             x_dtype = cfg["x_dtype"]
             f_in = len(prevs) * F + static.shape[-1] + forcing.shape[-1]
-            x_next = torch.empty(B, N, f_in, dtype=x_dtype, device=y.device)
             a = ArX()
             _fill_arx(a, list(prevs[1:]) + [None], static, forcing, B, N, F)
+            x_next = _new_x(B, N, f_in, x_dtype, y.device, a)
             ctx.f_in, ctx.x_dtype = f_in, x_dtype
         check(
             lib.p4c_ar_step_forward(
@@ -141,8 +150,13 @@ class _ARStepFn(torch.autograd.Function):
                 g_new = g_new.float()
             if not (g_new.stride(2) == 1 and g_new.stride(1) == F):
                 g_new = g_new.contiguous()
+        x_ld = 0
         if g_x is not None:
-            g_x = g_x.contiguous()
+            # rows may be padded (the gradient of a padded x comes back with the same row stride)
+            if not (g_x.stride(2) == 1 and g_x.stride(1) >= ctx.f_in
+                    and (B == 1 or g_x.stride(0) == N * g_x.stride(1))):
+                g_x = g_x.contiguous()
+            x_ld = g_x.stride(1)
         dy = torch.empty(B, N, F, dtype=ctx.y_dtype, device=dev)
         d_prev: List[Optional[torch.Tensor]] = [None] * T
         arr = (C.c_void_p * T)()
@@ -156,7 +170,7 @@ class _ARStepFn(torch.autograd.Function):
             lib.p4c_ar_step_backward(
                 ptr(g_new), _bstride(g_new) if g_new is not None else 0, ptr(g_x),
                 dtype_code(g_x.dtype) if g_x is not None else 0, ptr(ctx.border), ptr(ctx.std),
-                B, N, F, T, ctx.f_in if g_x is not None else 0, ptr(dy), dtype_code(ctx.y_dtype),
+                B, N, F, T, x_ld, ptr(dy), dtype_code(ctx.y_dtype),
                 arr, stream(),
             ),
             "p4c_ar_step_backward",
@@ -394,7 +408,8 @@ class AutoRegressiveLightning(nn.Module):
 
         slab = torch.empty(B, T, N, F, dtype=torch.float32, device=dev)
         if hasattr(self.model, "begin_rollout"):
-            self.model.begin_rollout()  # batch-independent embeddings: once per rollout, not per step
+            # batch-independent embeddings and weight images: once per rollout, not per step
+            self.model.begin_rollout(x_dtype)
         prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
         x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
         states = []

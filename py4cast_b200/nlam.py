@@ -77,12 +77,24 @@ class GraphLamSettings:
 class FusedMLP(nn.Sequential):
     """`make_mlp([in, d, out])`: Linear, SiLU, Linear, [LayerNorm] — executed as ONE kernel."""
 
-    def __init__(self, in_dim: int, hidden: int, out_dim: int, layer_norm: bool = True):
+    def __init__(self, in_dim: int, hidden: int, out_dim: int, layer_norm: bool = True,
+                 widths: Optional[Sequence[int]] = None):
         layers: List[nn.Module] = [nn.Linear(in_dim, hidden), nn.SiLU(), nn.Linear(hidden, out_dim)]
         if layer_norm:
             layers.append(nn.LayerNorm(out_dim))
         super().__init__(*layers)
         self.has_ln = layer_norm
+        # widths of the concatenated inputs of layer 1 (edge MLP: edge, sender, receiver)
+        self.widths = tuple(widths) if widths is not None else (in_dim,)
+        assert sum(self.widths) == in_dim
+        self._meta: Optional[ops.MlpMeta] = None
+
+    @property
+    def meta(self) -> ops.MlpMeta:
+        """Packed-weight image / deferred weight-gradient state of this MLP (tensor-core engine)."""
+        if self._meta is None:
+            self._meta = ops.MlpMeta(self.weights(), self.widths, self[2].out_features)
+        return self._meta
 
     def weights(self) -> Tuple[Optional[torch.Tensor], ...]:
         ln = self[3] if self.has_ln else None
@@ -92,17 +104,17 @@ class FusedMLP(nn.Sequential):
         )
 
     def forward(self, x: torch.Tensor, residual: bool = False) -> torch.Tensor:
-        return ops.fused_mlp(x, self.weights(), residual=residual)
+        return ops.fused_mlp(x, self.weights(), residual=residual, meta=self.meta)
 
 
-def make_mlp(blueprint: Sequence[int], layer_norm: bool = True) -> FusedMLP:
+def make_mlp(blueprint: Sequence[int], layer_norm: bool = True, widths: Optional[Sequence[int]] = None) -> FusedMLP:
     if len(blueprint) != 3:
         raise NotImplementedError(
             f"fused MLP kernels implement hidden_layers=1 (blueprint of 3 widths), got {list(blueprint)}"
         )
     if blueprint[1] != HIDDEN:
         raise NotImplementedError(f"fused MLP kernels are built for hidden_dims={HIDDEN}, got {blueprint[1]}")
-    return FusedMLP(blueprint[0], blueprint[1], blueprint[2], layer_norm)
+    return FusedMLP(blueprint[0], blueprint[1], blueprint[2], layer_norm, widths)
 
 
 class SplitMLPs(nn.Module):
@@ -138,14 +150,15 @@ class InteractionNet(nn.Module):
         self.num_send, self.num_rec = edge_set.num_send, edge_set.num_rec
         edge_bp = [3 * input_dim, hidden_dim, hidden_dim]
         aggr_bp = [2 * input_dim, hidden_dim, hidden_dim]
+        ew, aw = [input_dim] * 3, [input_dim] * 2
         if edge_chunk_sizes is None:
-            self.edge_mlp = make_mlp(edge_bp)
+            self.edge_mlp = make_mlp(edge_bp, widths=ew)
         else:
-            self.edge_mlp = SplitMLPs([make_mlp(edge_bp) for _ in edge_chunk_sizes], edge_chunk_sizes)
+            self.edge_mlp = SplitMLPs([make_mlp(edge_bp, widths=ew) for _ in edge_chunk_sizes], edge_chunk_sizes)
         if aggr_chunk_sizes is None:
-            self.aggr_mlp = make_mlp(aggr_bp)
+            self.aggr_mlp = make_mlp(aggr_bp, widths=aw)
         else:
-            self.aggr_mlp = SplitMLPs([make_mlp(aggr_bp) for _ in aggr_chunk_sizes], aggr_chunk_sizes)
+            self.aggr_mlp = SplitMLPs([make_mlp(aggr_bp, widths=aw) for _ in aggr_chunk_sizes], aggr_chunk_sizes)
         self.edge_chunk_sizes = None if edge_chunk_sizes is None else list(edge_chunk_sizes)
         self.aggr_chunk_sizes = None if aggr_chunk_sizes is None else list(aggr_chunk_sizes)
         self.aggr = aggr
@@ -172,10 +185,17 @@ class InteractionNet(nn.Module):
                 ws.extend(mlp.weights())
         return ws
 
+    def _metas(self) -> List[ops.MlpMeta]:
+        ms: List[ops.MlpMeta] = []
+        for m in (self.edge_mlp, self.aggr_mlp):
+            for mlp in (m.mlps if isinstance(m, SplitMLPs) else [m]):
+                ms.append(mlp.meta)
+        return ms
+
     def forward(self, send_rep, rec_rep, edge_rep):
         return ops.interaction_net(
             self.graph_index(), send_rep, rec_rep, edge_rep, self._weights(),
-            self.update_edges, self.aggr == "mean",
+            self.update_edges, self.aggr == "mean", self._metas(),
         )
 
 
@@ -290,7 +310,10 @@ class BaseGraphModel(ModelABC, nn.Module):
             return base
         key = (name, dtype, base.device)
         if key not in self._feat_cache:
-            self._feat_cache[key] = ops.cast(base, dtype)
+            # rows padded with zeros to 16 bytes: the tensor-core MLP fetches them as one chunk
+            padded = ops.empty_rows(base.shape, dtype, base.device, zero=True)
+            padded.copy_(ops.cast(base, dtype))
+            self._feat_cache[key] = padded
         return self._feat_cache[key]
 
     @property
@@ -302,8 +325,20 @@ class BaseGraphModel(ModelABC, nn.Module):
     # reference recomputes them in every forward call (T times per AR rollout, 1.3 M edges for
     # m2g); between `begin_rollout()` and `end_rollout()` they are computed once and shared by
     # all AR steps (autograd accumulates their gradient over the steps).
-    def begin_rollout(self) -> None:
+    def pack_weights(self) -> None:
+        """bf16 weight images of every MLP of the model, ONE kernel launch (the tensor-core kernels
+        then stage weights with 16-byte copies).  Must run after every weight update and before the
+        next forward: `forward` does it itself outside a rollout, `begin_rollout` once per rollout."""
+        packer = getattr(self, "_packer", None)
+        if packer is None:
+            packer = ops.WeightPacker([m.meta for m in self.modules() if isinstance(m, FusedMLP)])
+            self._packer = packer
+        packer.pack()
+
+    def begin_rollout(self, dtype: Optional[torch.dtype] = None) -> None:
         self._rollout_cache = {}
+        if dtype is None or dtype == torch.bfloat16:
+            self.pack_weights()
 
     def end_rollout(self) -> None:
         self._rollout_cache = None
@@ -330,7 +365,9 @@ class BaseGraphModel(ModelABC, nn.Module):
         if x.dim() != 3:
             raise ValueError(f"graph models expect (B, N_grid, F_in), got {tuple(x.shape)}")
         dt = self._compute_dtype(x)
-        x = ops.cast_autograd(x.contiguous(), dt)
+        if getattr(self, "_rollout_cache", None) is None and dt == torch.bfloat16:
+            self.pack_weights()
+        x = ops.cast_autograd(x if x.stride(-1) == 1 else x.contiguous(), dt)
         grid_emb = self.grid_embedder(x)
         g2m_emb = self._static_embedding("g2m", self.g2m_embedder, "g2m_features", dt)
         m2g_emb = self._static_embedding("m2g", self.m2g_embedder, "m2g_features", dt)

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import HIDDEN, ArX, Mlp, MlpBwd, check, dtype_code, ptr, stream
+from ._lib import HIDDEN, PACK_BYTES, ArX, Mlp, MlpBwd, Pack, WGrad, check, dtype_code, ptr, stream
 
 # ------------------------------------------------------------------ workspaces
 _WGRAD_WS: dict = {}
@@ -40,6 +40,137 @@ def _esize(t: torch.Tensor) -> int:
 def _off(t: torch.Tensor, elements: int) -> int:
     """device pointer of `t` advanced by `elements` elements"""
     return ptr(t) + elements * _esize(t)
+
+
+# --------------------------------------------------- per-MLP side state (tensor-core engine)
+def _table_to_device(entries, device: torch.device) -> torch.Tensor:
+    """ctypes structs -> one uint8 device tensor (a DEVICE table for the batched kernels)."""
+    raw = b"".join(bytes(e) for e in entries)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+class MlpMeta:
+    """Side state of one 2-layer MLP: the packed bf16 weight image (p4c_pack_weights) and the
+    per-CTA weight-gradient partials whose reduction is deferred to ONE batched launch per
+    backward pass (`flush_wgrads`).  Both are optional accelerations: a call without meta converts
+    the weights in the kernel and reduces its partials itself."""
+
+    def __init__(self, params: Sequence[Optional[torch.Tensor]], widths: Sequence[int], out_features: int):
+        self.params = tuple(params)  # w1, b1, w2, b2, gamma, beta
+        self.widths = tuple(int(w) for w in widths)
+        self.k1 = int(sum(self.widths))
+        self.out_features = int(out_features)
+        self.image: Optional[torch.Tensor] = None  # uint8 [PACK_BYTES] view, valid after pack()
+        self.partials: Optional[torch.Tensor] = None
+        self.partials_blocks = 0
+        self.partials_used = False
+
+    def image_ptr(self, dtype: torch.dtype) -> Optional[int]:
+        if self.image is None or dtype != torch.bfloat16:
+            return None
+        return self.image.data_ptr()
+
+    def sinks(self) -> Optional[List[Optional[torch.Tensor]]]:
+        """The flat-gradient views of the parameters, if every parameter has one."""
+        out = []
+        for p in self.params:
+            if p is None:
+                out.append(None)
+                continue
+            g = getattr(p, "_p4c_grad", None)
+            if g is None or not p.requires_grad:
+                return None
+            out.append(g)
+        return out
+
+
+class WeightPacker:
+    """Packs the weights of a set of MLPs into their images with ONE kernel launch."""
+
+    def __init__(self, metas: Sequence[MlpMeta]):
+        self.metas = list(metas)
+        self._images: Optional[torch.Tensor] = None
+        self._table: Optional[torch.Tensor] = None
+        self._key = None
+
+    def _build(self, device: torch.device) -> None:
+        n = len(self.metas)
+        self._images = torch.empty(n, PACK_BYTES, dtype=torch.uint8, device=device)
+        entries = []
+        for i, m in enumerate(self.metas):
+            e = Pack()
+            w1, b1, w2, b2, gamma, beta = m.params
+            e.w1, e.b1, e.w2, e.b2 = ptr(w1), ptr(b1), ptr(w2), ptr(b2)
+            e.gamma, e.beta = ptr(gamma), ptr(beta)
+            e.dst = self._images[i].data_ptr()
+            e.k1, e.out_features, e.nsrc = m.k1, m.out_features, len(m.widths)
+            for j, w in enumerate(m.widths):
+                e.width[j] = w
+            entries.append(e)
+            m.image = self._images[i]
+        self._table = _table_to_device(entries, device)
+
+    def pack(self) -> None:
+        if not self.metas:
+            return
+        w = self.metas[0].params[0]
+        key = tuple(p.data_ptr() for m in self.metas for p in m.params if p is not None)
+        if self._table is None or key != self._key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("WeightPacker: parameters moved; run one eager step before CUDA-graph capture")
+            self._build(w.device)
+            self._key = key
+        check(_lib.load().p4c_pack_weights(ptr(self._table), len(self.metas), stream()), "p4c_pack_weights")
+
+
+_DEFERRED: List[MlpMeta] = []
+_DEFERRED_TABLES: dict = {}
+
+
+def _deferred_mode(meta: Optional[MlpMeta], nblocks: int, partial_floats: int, device) -> int:
+    """0 = reduce in the call; 1 / 2 = overwrite / accumulate this MLP's own partials (deferred)."""
+    if meta is None or meta.sinks() is None:
+        return 0
+    if meta.partials is None:
+        if torch.cuda.is_current_stream_capturing():
+            return 0
+        meta.partials = torch.empty(partial_floats, dtype=torch.float32, device=device)
+        meta.partials_blocks = nblocks
+    if meta.partials_blocks != nblocks or meta.partials.numel() < partial_floats:
+        return 0  # same weights used with another problem size: keep that call self-contained
+    if not meta.partials_used:
+        meta.partials_used = True
+        _DEFERRED.append(meta)
+        return 1
+    return 2
+
+
+def flush_wgrads() -> None:
+    """Reduces the deferred weight-gradient partials of every MLP touched since the last flush
+    into the parameters' gradient sinks: ONE launch (the trainer calls it after backward)."""
+    if not _DEFERRED:
+        return
+    key = tuple(id(m) for m in _DEFERRED)
+    ent = _DEFERRED_TABLES.get(key)
+    if ent is None or ent[1] != tuple(m.partials.data_ptr() for m in _DEFERRED):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("flush_wgrads: run one eager step before CUDA-graph capture")
+        entries = []
+        for m in _DEFERRED:
+            e = WGrad()
+            e.partials = ptr(m.partials)
+            sinks = m.sinks()
+            for name, g in zip(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta"), sinks):
+                setattr(e, name, ptr(g))
+            e.nblocks, e.k1, e.out_features = m.partials_blocks, m.k1, m.out_features
+            entries.append(e)
+        dev = _DEFERRED[0].partials.device
+        ent = (_table_to_device(entries, dev), tuple(m.partials.data_ptr() for m in _DEFERRED), list(_DEFERRED))
+        _DEFERRED_TABLES[key] = ent
+    check(_lib.load().p4c_wgrad_reduce_batched(ptr(ent[0]), len(_DEFERRED), stream()), "p4c_wgrad_reduce_batched")
+    for m in _DEFERRED:
+        m.partials_used = False
+    _DEFERRED.clear()
 
 
 # -------------------------------------------------------------------------- CSR
@@ -105,6 +236,10 @@ class GraphIndex:
     by_rec: Csr  # all edges keyed by receiver
     groups: List[EdgeGroup] = field(default_factory=list)
     node_chunks: Optional[List[Tuple[int, int]]] = None  # receiver ranges with own node-MLP weights
+    # > 0: edges are sorted by receiver and every receiver has exactly this many (a power of two
+    # <= 32): edge e belongs to receiver e // uniform_deg, so the aggregation can run in the
+    # epilogue of the edge kernel (m2g: 4 nearest mesh nodes; up / down edges: 1)
+    uniform_deg: int = 0
 
     @staticmethod
     def build(
@@ -142,8 +277,15 @@ class GraphIndex:
                 node_chunks.append((s, s + int(n)))
                 s += int(n)
             assert s == num_rec
+        uniform = 0
+        if edge_chunk_sizes is None and by_rec.perm is None and num_rec > 0 and E % num_rec == 0:
+            d = E // num_rec
+            if d in (1, 2, 4, 8, 16, 32):
+                expect = torch.arange(num_rec + 1, dtype=torch.int32, device=rec.device) * d
+                if bool(torch.equal(by_rec.rowptr, expect)):
+                    uniform = d
         return GraphIndex(
-            num_send, num_rec, E, index_to_i32(send), index_to_i32(rec), by_rec, groups, node_chunks
+            num_send, num_rec, E, index_to_i32(send), index_to_i32(rec), by_rec, groups, node_chunks, uniform
         )
 
 
@@ -219,14 +361,42 @@ def cast_autograd(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # ------------------------------------------------------------------- descriptors
 @dataclass
 class _SrcSpec:
-    tensor: torch.Tensor  # (B,R,W) or (R,W) shared across the batch
+    tensor: torch.Tensor  # (B,R,W) or (R,W) shared across the batch; rows may be strided (ld >= W)
     index: Optional[torch.Tensor] = None  # int32 gather index (already offset to the row range)
     row_offset: int = 0  # first row (identity sources covering a sub-range)
     index_offset: int = 0  # first entry of `index` used
+    seg: Optional[Csr] = None  # segment-sum source: input row r = sum of tensor rows of segment r
+    seg_row_offset: int = 0  # first segment used
+    seg_mean: bool = False
+    seg_out: Optional[torch.Tensor] = None  # (B, full_rows, 64) receives the summed rows
+
+
+def _row_layout(t: torch.Tensor) -> Tuple[int, int]:
+    """(ld, batch_stride) in elements of a (B,R,W) / (R,W) tensor with unit-stride features."""
+    assert t.stride(-1) == 1, "feature dimension must be contiguous"
+    ld = t.stride(-2) if t.shape[-2] > 1 else t.shape[-1]
+    if t.dim() == 2:
+        return ld, 0
+    bs = t.stride(0) if t.shape[0] > 1 else t.shape[-2] * ld
+    return ld, bs
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    """Row-strided layouts the kernels take without a copy: unit feature stride, ld >= width."""
+    if t.dim() not in (2, 3) or t.stride(-1) != 1:
+        return False
+    if t.shape[-2] > 1 and t.stride(-2) < t.shape[-1]:
+        return False
+    return True
+
+
+def _as_rows(t: torch.Tensor) -> torch.Tensor:
+    return t if _rows_ok(t) else t.contiguous()
 
 
 def _fill_mlp(desc: Mlp, rows: int, batch: int, full_rows: int, srcs: Sequence[_SrcSpec],
-              weights: Sequence[Optional[torch.Tensor]], out_features: int, dtype: torch.dtype) -> None:
+              weights: Sequence[Optional[torch.Tensor]], out_features: int, dtype: torch.dtype,
+              meta: Optional[MlpMeta] = None) -> None:
     w1, b1, w2, b2, gamma, beta = weights
     desc.rows, desc.batch, desc.nsrc = rows, batch, len(srcs)
     desc.out_features = out_features
@@ -237,15 +407,21 @@ def _fill_mlp(desc: Mlp, rows: int, batch: int, full_rows: int, srcs: Sequence[_
     for i, s in enumerate(srcs):
         t = s.tensor
         assert t.dtype == dtype, f"source {i} dtype {t.dtype} != {dtype}"
-        assert t.is_contiguous()
         width = t.shape[-1]
-        shared = t.dim() == 2
-        n_rows = t.shape[-2]
-        desc.src[i].ptr = _off(t, s.row_offset * width)
+        ld, bs = _row_layout(t)
+        desc.src[i].ptr = _off(t, s.row_offset * ld)
         desc.src[i].index = None if s.index is None else _off(s.index, s.index_offset)
-        desc.src[i].batch_stride = 0 if shared else n_rows * width
-        desc.src[i].ld = width
+        desc.src[i].batch_stride = bs
+        desc.src[i].ld = ld
         desc.src[i].width = width
+        if s.seg is not None:
+            assert width == HIDDEN and ld == HIDDEN and s.index is None
+            desc.src[i].seg_rowptr = _off(s.seg.rowptr, s.seg_row_offset)
+            desc.src[i].seg_perm = ptr(s.seg.perm)
+            desc.src[i].seg_scale = _off(s.seg.inv_deg, s.seg_row_offset) if s.seg_mean else None
+            desc.src[i].seg_out = None if s.seg_out is None else _off(s.seg_out, s.seg_row_offset * HIDDEN)
+        else:
+            desc.src[i].seg_rowptr = desc.src[i].seg_perm = desc.src[i].seg_scale = desc.src[i].seg_out = None
         k1 += width
     desc.k1 = k1
     assert w1.shape == (HIDDEN, k1), f"w1 shape {tuple(w1.shape)} != (64,{k1})"
@@ -253,6 +429,10 @@ def _fill_mlp(desc: Mlp, rows: int, batch: int, full_rows: int, srcs: Sequence[_
     desc.w1, desc.b1, desc.w2, desc.b2 = ptr(w1), ptr(b1), ptr(w2), ptr(b2)
     desc.gamma, desc.beta = ptr(gamma), ptr(beta)
     desc.ln_eps = 1e-5
+    desc.packed = None
+    if meta is not None:
+        assert meta.widths == tuple(s.tensor.shape[-1] for s in srcs), "weight image packed for other source widths"
+        desc.packed = meta.image_ptr(dtype)
 
 
 def _grad_target(p: Optional[torch.Tensor], needed: bool):
@@ -266,6 +446,29 @@ def _grad_target(p: Optional[torch.Tensor], needed: bool):
     return buf, buf
 
 
+def _bind_wgrads(lib, desc: Mlp, g: MlpBwd, ws: Sequence[Optional[torch.Tensor]], needed: Sequence[bool],
+                 meta: Optional[MlpMeta], device) -> List[Optional[torch.Tensor]]:
+    """Weight-gradient outputs of one backward call: deferred partials when the MLP has gradient
+    sinks (trainer), otherwise the shared workspace + in-call reduction.  Returns the 6 values to
+    hand back to autograd."""
+    nfl = lib.p4c_mlp_wgrad_partial_floats(C.byref(desc))
+    rets: List[Optional[torch.Tensor]] = [None] * 6
+    mode = 0
+    if desc.dtype == _lib.P4C_BF16 and all(needed[j] or ws[j] is None for j in range(6)):
+        mode = _deferred_mode(meta, lib.p4c_mlp_wgrad_blocks(C.byref(desc)), nfl, device)
+    g.partials_mode = mode
+    if mode != 0:
+        g.wgrad_partials, g.wgrad_partials_floats = ptr(meta.partials), meta.partials.numel()
+        return rets
+    for j, slot in enumerate(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta")):
+        buf, ret = _grad_target(ws[j], needed[j])
+        setattr(g, slot, ptr(buf))
+        rets[j] = ret
+    wsp = _wgrad_workspace(device, nfl)
+    g.wgrad_partials, g.wgrad_partials_floats = ptr(wsp), wsp.numel()
+    return rets
+
+
 def _check_hidden(t: torch.Tensor, what: str) -> None:
     if t.shape[-1] != HIDDEN:
         raise NotImplementedError(
@@ -273,15 +476,32 @@ def _check_hidden(t: torch.Tensor, what: str) -> None:
         )
 
 
+def padded_width(width: int, dtype: torch.dtype) -> int:
+    """Row stride that lets the tensor-core engine fetch a `width`-wide row in 16-byte chunks."""
+    return (width + 7) // 8 * 8 if dtype == torch.bfloat16 else width
+
+
+def empty_rows(shape: Sequence[int], dtype: torch.dtype, device, zero: bool = False) -> torch.Tensor:
+    """(…, R, W) tensor whose rows are padded to `padded_width`, returned as the (…, R, W) view:
+    what the tensor-core MLP reads / writes without a copy.  The padding must hold finite values
+    before the tensor is READ by a kernel (`zero=True`, or a producer kernel that writes it)."""
+    *lead, w = shape
+    ld = padded_width(w, dtype)
+    if ld == w:
+        return torch.empty(*lead, w, dtype=dtype, device=device)
+    buf = (torch.zeros if zero else torch.empty)(*lead, ld, dtype=dtype, device=device)
+    return buf[..., :w]
+
+
 # -------------------------------------------------------------------- fused MLP
 class _MLPFn(torch.autograd.Function):
     """y = [LN](W2 silu(W1 x + b1) + b2) [+ x]   for one dense, identity-indexed source."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, residual: bool):
+    def forward(ctx, meta: Optional[MlpMeta], x, w1, b1, w2, b2, gamma, beta, residual: bool):
         lib = _lib.load()
         shared = x.dim() == 2
-        x = x.contiguous()
+        x = _as_rows(x)
         B = 1 if shared else x.shape[0]
         R, K = x.shape[-2], x.shape[-1]
         out_features = w2.shape[0]
@@ -289,6 +509,8 @@ class _MLPFn(torch.autograd.Function):
             raise NotImplementedError(f"fused MLP needs hidden width {HIDDEN}, got {w1.shape[0]}")
         if residual and (K != HIDDEN or out_features != HIDDEN):
             raise ValueError("residual needs 64-wide input and output")
+        if residual and not x.is_contiguous():
+            x = x.contiguous()
         dt = x.dtype
         need_grad = any(ctx.needs_input_grad)
         out = torch.empty((R, out_features) if shared else (B, R, out_features), dtype=dt, device=x.device)
@@ -299,7 +521,7 @@ class _MLPFn(torch.autograd.Function):
             else None
         )
         desc = Mlp()
-        _fill_mlp(desc, R, B, 0, [_SrcSpec(x)], (w1, b1, w2, b2, gamma, beta), out_features, dt)
+        _fill_mlp(desc, R, B, 0, [_SrcSpec(x)], (w1, b1, w2, b2, gamma, beta), out_features, dt, meta)
         check(
             lib.p4c_mlp_forward(C.byref(desc), ptr(x) if residual else None, ptr(out), None,
                                 ptr(h1), ptr(stats), stream()),
@@ -307,6 +529,7 @@ class _MLPFn(torch.autograd.Function):
         )
         ctx.save_for_backward(x, w1, b1, w2, b2, gamma, beta, h1, stats)
         ctx.residual = residual
+        ctx.meta = meta
         return out
 
     @staticmethod
@@ -321,42 +544,47 @@ class _MLPFn(torch.autograd.Function):
         dy = dy.contiguous()
         if dy.dtype != dt:
             dy = cast(dy, dt)
+        ws = (w1, b1, w2, b2, gamma, beta)
         desc = Mlp()
-        _fill_mlp(desc, R, B, 0, [_SrcSpec(x)], (w1, b1, w2, b2, gamma, beta), out_features, dt)
+        _fill_mlp(desc, R, B, 0, [_SrcSpec(x)], ws, out_features, dt, ctx.meta)
         g = MlpBwd()
         g.dy_a, g.dy_a_batch_stride = ptr(dy), R * out_features
         g.h1, g.stats = ptr(h1), ptr(stats)
         dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = ptr(dx), K, 0
+        if ctx.needs_input_grad[1]:
+            dx = empty_rows(x.shape, dt, x.device)
+            g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = ptr(dx), _row_layout(dx)[0], 0
             g.dx0_add_dy = 2 if ctx.residual else 0
         elif ctx.residual:
             raise RuntimeError("residual MLP with a non-differentiable input is not supported")
-        rets = []
-        for p, slot, needed in (
-            (w1, "g_w1", ctx.needs_input_grad[1]), (b1, "g_b1", ctx.needs_input_grad[2]),
-            (w2, "g_w2", ctx.needs_input_grad[3]), (b2, "g_b2", ctx.needs_input_grad[4]),
-            (gamma, "g_gamma", ctx.needs_input_grad[5]), (beta, "g_beta", ctx.needs_input_grad[6]),
-        ):
-            buf, ret = _grad_target(p, needed)
-            setattr(g, slot, ptr(buf))
-            rets.append(ret)
-        nfl = lib.p4c_mlp_wgrad_partial_floats(C.byref(desc))
-        ws = _wgrad_workspace(x.device, nfl)
-        g.wgrad_partials, g.wgrad_partials_floats = ptr(ws), ws.numel()
+        rets = _bind_wgrads(lib, desc, g, ws, ctx.needs_input_grad[2:8], ctx.meta, x.device)
         check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward")
-        return (dx, *rets, None)
+        return (None, dx, *rets, None)
 
 
-def fused_mlp(x: torch.Tensor, weights: Sequence[Optional[torch.Tensor]], residual: bool = False) -> torch.Tensor:
+def fused_mlp(x: torch.Tensor, weights: Sequence[Optional[torch.Tensor]], residual: bool = False,
+              meta: Optional[MlpMeta] = None) -> torch.Tensor:
     w1, b1, w2, b2, gamma, beta = weights
-    return _MLPFn.apply(x, w1, b1, w2, b2, gamma, beta, residual)
+    return _MLPFn.apply(meta, x, w1, b1, w2, b2, gamma, beta, residual)
 
 
 # --------------------------------------------------------------- InteractionNet
 def _rows(t: torch.Tensor) -> int:
     return t.shape[-2]
+
+
+def seg_linear(src: torch.Tensor, csr: Csr, batch: int, w1: torch.Tensor, col0: int, out: torch.Tensor,
+               accumulate: bool, mean: bool = False, meta: Optional[MlpMeta] = None) -> None:
+    """out[b,r,:] (+)= (segment sum of src rows of segment r) @ w1[:, col0:col0+64]  (bf16, one kernel)."""
+    packed = meta.image_ptr(src.dtype) if meta is not None else None
+    check(
+        _lib.load().p4c_seg_linear(
+            ptr(src), src.shape[1] * HIDDEN, ptr(csr.rowptr), ptr(csr.perm), ptr(csr.inv_deg) if mean else None,
+            csr.num_seg, batch, ptr(w1), w1.shape[1], col0, packed, col0 // HIDDEN, ptr(out),
+            out.shape[1] * HIDDEN, int(accumulate), dtype_code(src.dtype), stream(),
+        ),
+        "p4c_seg_linear",
+    )
 
 
 class _InteractionNetFn(torch.autograd.Function):
@@ -366,14 +594,22 @@ class _InteractionNetFn(torch.autograd.Function):
         aggr     = segment_{sum|mean}(msg by receiver)
         rec_out  = rec + aggr_mlp(cat(rec, aggr))
         edge_out = edge + msg                       (update_edges)
-    Weights: 6 tensors per edge group followed by 6 per node chunk.
+    Weights: 6 tensors per edge group followed by 6 per node chunk; `metas` (optional) holds the
+    MlpMeta of each, in the same order.
+
+    bf16 (tensor-core engine): 2 launches forward — the aggregation runs in the epilogue of the
+    edge kernel when the edges are receiver-sorted with a uniform in-degree (m2g, up / down
+    edges), otherwise in the prologue of the node kernel — and 4 backward (node MLP, edge MLP,
+    and one fused segment-sum + GEMM per gathered source).  fp32 keeps separate segment sums.
     """
 
     @staticmethod
-    def forward(ctx, gi: GraphIndex, update_edges: bool, mean: bool, send, rec, edge, *weights):
+    def forward(ctx, gi: GraphIndex, update_edges: bool, mean: bool, metas, send, rec, edge, *weights):
         lib = _lib.load()
         for t, n in ((send, "send"), (rec, "rec"), (edge, "edge")):
             _check_hidden(t, f"InteractionNet {n} representation")
+        same_nodes = (send.data_ptr() == rec.data_ptr() and send.shape == rec.shape
+                      and send.stride() == rec.stride())
         send, rec, edge = send.contiguous(), rec.contiguous(), edge.contiguous()
         dt = rec.dtype
         assert send.dtype == dt and edge.dtype == dt
@@ -387,15 +623,19 @@ class _InteractionNetFn(torch.autograd.Function):
         node_chunks = gi.node_chunks or [(0, Nr)]
         ew = [weights[6 * i: 6 * i + 6] for i in range(n_eg)]
         nw = [weights[6 * (n_eg + i): 6 * (n_eg + i) + 6] for i in range(len(node_chunks))]
+        metas = list(metas) if metas is not None else [None] * (n_eg + len(node_chunks))
         dev = rec.device
         need_grad = any(ctx.needs_input_grad)
         ctx.set_materialize_grads(False)
+        tc = dt == torch.bfloat16 and bool(lib.p4c_get_engine())
+        fuse_epilogue = tc and gi.uniform_deg > 0 and n_eg == 1
 
-        msg = torch.empty(B, E, HIDDEN, dtype=dt, device=dev)
+        msg = None if fuse_epilogue else torch.empty(B, E, HIDDEN, dtype=dt, device=dev)
+        aggr = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
         edge_out = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if update_edges else None
         h1_e = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if need_grad else None
         st_e = torch.empty(B, E, 2, dtype=torch.float32, device=dev) if need_grad else None
-        for grp, w in zip(gi.groups, ew):
+        for gidx, (grp, w) in enumerate(zip(gi.groups, ew)):
             n = grp.stop - grp.start
             if n == 0:
                 continue
@@ -407,32 +647,41 @@ class _InteractionNetFn(torch.autograd.Function):
                     _SrcSpec(send, index=gi.send_idx, index_offset=grp.start),
                     _SrcSpec(rec, index=gi.rec_idx, index_offset=grp.start),
                 ],
-                w, HIDDEN, dt,
+                w, HIDDEN, dt, metas[gidx],
             )
             o = grp.start * HIDDEN
-            check(
-                lib.p4c_mlp_forward(
-                    C.byref(desc), None, _off(msg, o),
-                    _off(edge_out, o) if update_edges else None,
-                    _off(h1_e, o) if need_grad else None,
-                    _off(st_e, grp.start * 2) if need_grad else None, stream(),
-                ),
-                "p4c_mlp_forward(edge)",
+            args = (
+                _off(edge_out, o) if update_edges else None,
+                _off(h1_e, o) if need_grad else None,
+                _off(st_e, grp.start * 2) if need_grad else None,
             )
-        aggr = segment_sum(msg, gi.by_rec, B, mean=mean)
-        del msg
+            if fuse_epilogue:
+                check(
+                    lib.p4c_mlp_forward_aggregate(
+                        C.byref(desc), None, *args, ptr(aggr), gi.uniform_deg,
+                        1.0 / gi.uniform_deg if mean else 1.0, stream(),
+                    ),
+                    "p4c_mlp_forward_aggregate(edge)",
+                )
+            else:
+                check(lib.p4c_mlp_forward(C.byref(desc), None, _off(msg, o), *args, stream()),
+                      "p4c_mlp_forward(edge)")
+        seg_in_prologue = tc and not fuse_epilogue
+        if not tc:
+            segment_sum(msg, gi.by_rec, B, mean=mean, out=aggr)
 
         rec_b = rec if rec.dim() == 3 else rec.unsqueeze(0).expand(B, Nr, HIDDEN).contiguous()
         rec_out = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
         h1_n = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev) if need_grad else None
         st_n = torch.empty(B, Nr, 2, dtype=torch.float32, device=dev) if need_grad else None
-        for (n0, n1), w in zip(node_chunks, nw):
+        for ci, ((n0, n1), w) in enumerate(zip(node_chunks, nw)):
             desc = Mlp()
-            _fill_mlp(
-                desc, n1 - n0, B, Nr,
-                [_SrcSpec(rec_b, row_offset=n0), _SrcSpec(aggr, row_offset=n0)],
-                w, HIDDEN, dt,
-            )
+            if seg_in_prologue:
+                aggr_src = _SrcSpec(msg, seg=gi.by_rec, seg_row_offset=n0, seg_mean=mean, seg_out=aggr)
+            else:
+                aggr_src = _SrcSpec(aggr, row_offset=n0)
+            _fill_mlp(desc, n1 - n0, B, Nr, [_SrcSpec(rec_b, row_offset=n0), aggr_src], w, HIDDEN, dt,
+                      metas[n_eg + ci])
             o = n0 * HIDDEN
             check(
                 lib.p4c_mlp_forward(
@@ -442,9 +691,11 @@ class _InteractionNetFn(torch.autograd.Function):
                 ),
                 "p4c_mlp_forward(node)",
             )
+        del msg
         ctx.gi, ctx.update_edges, ctx.mean, ctx.B = gi, update_edges, mean, B
         ctx.rec_shared = rec.dim() == 2
-        ctx.n_weights = len(weights)
+        ctx.same_nodes = same_nodes and rec.dim() == 3
+        ctx.metas, ctx.tc = metas, tc
         ctx.save_for_backward(send, rec_b, edge, aggr, h1_e, st_e, h1_n, st_n, *weights)
         if update_edges:
             return rec_out, edge_out
@@ -463,8 +714,10 @@ class _InteractionNetFn(torch.autograd.Function):
         node_chunks = gi.node_chunks or [(0, Nr)]
         ew = [weights[6 * i: 6 * i + 6] for i in range(n_eg)]
         nw = [weights[6 * (n_eg + i): 6 * (n_eg + i) + 6] for i in range(len(node_chunks))]
-        need_send, need_rec, need_edge = ctx.needs_input_grad[3:6]
-        wneed = ctx.needs_input_grad[6:]
+        metas, tc = ctx.metas, ctx.tc
+        need_send, need_rec, need_edge = ctx.needs_input_grad[4:7]
+        wneed = ctx.needs_input_grad[7:]
+        same_nodes = ctx.same_nodes and need_send and need_rec
 
         if d_rec_out is None:
             d_rec_out = torch.zeros(B, Nr, HIDDEN, dtype=dt, device=dev)
@@ -478,12 +731,6 @@ class _InteractionNetFn(torch.autograd.Function):
 
         wgrads: List[Optional[torch.Tensor]] = [None] * len(weights)
 
-        def bind_wgrads(g: MlpBwd, base: int, ws: Sequence[Optional[torch.Tensor]]):
-            for j, slot in enumerate(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta")):
-                buf, ret = _grad_target(ws[j], wneed[base + j])
-                setattr(g, slot, ptr(buf))
-                wgrads[base + j] = ret
-
         # ---- node MLP backward: d_rec (incl. residual pass-through) and d_aggr
         d_rec = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
         d_aggr = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
@@ -491,7 +738,7 @@ class _InteractionNetFn(torch.autograd.Function):
             desc = Mlp()
             _fill_mlp(
                 desc, n1 - n0, B, Nr,
-                [_SrcSpec(rec_b, row_offset=n0), _SrcSpec(aggr, row_offset=n0)], w, HIDDEN, dt,
+                [_SrcSpec(rec_b, row_offset=n0), _SrcSpec(aggr, row_offset=n0)], w, HIDDEN, dt, metas[n_eg + ci],
             )
             o = n0 * HIDDEN
             g = MlpBwd()
@@ -500,16 +747,16 @@ class _InteractionNetFn(torch.autograd.Function):
             g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_rec, o), HIDDEN, 0
             g.dx[1], g.dx_ld[1], g.dx_accumulate[1] = _off(d_aggr, o), HIDDEN, 0
             g.dx0_add_dy = 2
-            bind_wgrads(g, 6 * (n_eg + ci), w)
-            nfl = lib.p4c_mlp_wgrad_partial_floats(C.byref(desc))
-            ws = _wgrad_workspace(dev, nfl)
-            g.wgrad_partials, g.wgrad_partials_floats = ptr(ws), ws.numel()
+            base = 6 * (n_eg + ci)
+            wgrads[base: base + 6] = _bind_wgrads(lib, desc, g, w, wneed[base: base + 6], metas[n_eg + ci], dev)
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(node)")
 
         # ---- edge MLP backward
         dh1 = torch.empty(B, E, HIDDEN, dtype=dt, device=dev)
         d_edge = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if need_edge else None
-        d_send = torch.empty(B, Ns, HIDDEN, dtype=dt, device=dev) if need_send else None
+        d_send = None
+        if need_send and not same_nodes:
+            d_send = torch.empty(B, Ns, HIDDEN, dtype=dt, device=dev)
         first_send = True
         for gidx, (grp, w) in enumerate(zip(gi.groups, ew)):
             n = grp.stop - grp.start
@@ -523,7 +770,7 @@ class _InteractionNetFn(torch.autograd.Function):
                     _SrcSpec(send, index=gi.send_idx, index_offset=grp.start),
                     _SrcSpec(rec_b, index=gi.rec_idx, index_offset=grp.start),
                 ],
-                w, HIDDEN, dt,
+                w, HIDDEN, dt, metas[gidx],
             )
             o = grp.start * HIDDEN
             g = MlpBwd()
@@ -537,28 +784,41 @@ class _InteractionNetFn(torch.autograd.Function):
             if need_edge:
                 g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_edge, o), HIDDEN, 0
                 g.dx0_add_dy = 1 if d_edge_out is not None else 0
-            bind_wgrads(g, 6 * gidx, w)
-            nfl = lib.p4c_mlp_wgrad_partial_floats(C.byref(desc))
-            ws = _wgrad_workspace(dev, nfl)
-            g.wgrad_partials, g.wgrad_partials_floats = ptr(ws), ws.numel()
+            wgrads[6 * gidx: 6 * gidx + 6] = _bind_wgrads(lib, desc, g, w, wneed[6 * gidx: 6 * gidx + 6],
+                                                          metas[gidx], dev)
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(edge)")
             # sender / receiver gradients by linearity: (segment-sum of dh1) x W1 slice
-            if need_rec:
-                s_r = segment_sum(dh1, grp.by_rec, B)
-                rows_matmul(s_r, w[0], 2 * HIDDEN, d_rec, accumulate=True)
-            if need_send:
-                s_s = segment_sum(dh1, grp.by_send, B)
-                rows_matmul(s_s, w[0], HIDDEN, d_send, accumulate=not first_send)
-                first_send = False
-        if need_send and first_send:
+            if tc:
+                if need_rec:
+                    seg_linear(dh1, grp.by_rec, B, w[0], 2 * HIDDEN, d_rec, True, meta=metas[gidx])
+                if need_send:
+                    if same_nodes:
+                        seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_rec, True, meta=metas[gidx])
+                    else:
+                        seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_send, not first_send, meta=metas[gidx])
+                    first_send = False
+            else:
+                if need_rec:
+                    s_r = segment_sum(dh1, grp.by_rec, B)
+                    rows_matmul(s_r, w[0], 2 * HIDDEN, d_rec, accumulate=True)
+                if need_send:
+                    s_s = segment_sum(dh1, grp.by_send, B)
+                    if same_nodes:
+                        rows_matmul(s_s, w[0], HIDDEN, d_rec, accumulate=True)
+                    else:
+                        rows_matmul(s_s, w[0], HIDDEN, d_send, accumulate=not first_send)
+                    first_send = False
+        if d_send is not None and first_send:
             d_send.zero_()
 
-        g_send = (batch_sum(d_send) if send.dim() == 2 else d_send) if need_send else None
+        g_send = None
+        if need_send and not same_nodes:
+            g_send = batch_sum(d_send) if send.dim() == 2 else d_send
         g_rec = (batch_sum(d_rec) if ctx.rec_shared else d_rec) if need_rec else None
         g_edge = (batch_sum(d_edge) if edge.dim() == 2 else d_edge) if need_edge else None
-        return (None, None, None, g_send, g_rec, g_edge, *wgrads)
+        return (None, None, None, None, g_send, g_rec, g_edge, *wgrads)
 
 
 def interaction_net(gi: GraphIndex, send, rec, edge, weights: Sequence[torch.Tensor],
-                    update_edges: bool, mean: bool):
-    return _InteractionNetFn.apply(gi, update_edges, mean, send, rec, edge, *weights)
+                    update_edges: bool, mean: bool, metas: Optional[Sequence[Optional[MlpMeta]]] = None):
+    return _InteractionNetFn.apply(gi, update_edges, mean, metas, send, rec, edge, *weights)

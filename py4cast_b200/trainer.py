@@ -26,7 +26,7 @@ from typing import Callable, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, ops
 from ._lib import AdamWState, check, ptr, stream
 from .datasets import ItemBatch
 from .namedtensor import NamedTensor
@@ -137,6 +137,7 @@ class DataParallelTrainer:
         loss = self.lm.training_step(batch, 1)
         self.lm.training_step_losses.clear()
         loss.backward()
+        ops.flush_wgrads()  # ONE batched reduction of the deferred weight-gradient partials
         return loss.detach()
 
     # one optimiser step on `batch` (this rank's shard)

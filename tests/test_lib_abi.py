@@ -33,11 +33,16 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (LP64): see include/py4cast_b200.h
-    assert ctypes.sizeof(_lib.Src) == 32
-    assert ctypes.sizeof(_lib.Mlp) == 8 * 4 + 3 * 32 + 6 * 8 + 8
-    assert ctypes.sizeof(_lib.MlpBwd) == 8 * 8 + 3 * 8 + 3 * 4 + 3 * 4 + 4 + 4 + 6 * 8 + 8 + 8
-    assert ctypes.sizeof(_lib.ArX) == 6 * 4 + 8 * 8 + 8 * 8 + 4 * 8
+    assert ctypes.sizeof(_lib.Src) == 64
+    assert ctypes.sizeof(_lib.Mlp) == 8 * 4 + 3 * 64 + 6 * 8 + 8 + 8
     assert ctypes.sizeof(_lib.AdamWState) == 24
+    assert ctypes.sizeof(_lib.Pack) == 7 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.WGrad) == 7 * 8 + 4 * 4
+    # and against the compiled library itself
+    lib = _lib.load()
+    for which, st in enumerate((_lib.Src, _lib.Mlp, _lib.MlpBwd, _lib.ArX, _lib.AdamWState, _lib.Pack, _lib.WGrad)):
+        assert lib.p4c_sizeof(which) == ctypes.sizeof(st), st.__name__
+    assert lib.p4c_sizeof(99) == -1
 
 
 def test_host_only_entry_points():
