@@ -123,6 +123,9 @@ typedef struct {
    * for the tensor-core engine); NULL = the kernels convert w1/w2 themselves (slower set-up).
    * The image must have been packed from the current values of w1..beta.                       */
   const void* packed;
+  /* tuning hint (tensor-core forward only): valid rows per 128-row CTA tile, one of 16/32/64/128
+   * (0 = 128).  Smaller tiles spread long segment sums (hundreds of edges per row) over more CTAs. */
+  int32_t tile_rows;
 } p4c_mlp_t;
 
 /* ------------------------------------------------------------------------
@@ -162,8 +165,8 @@ int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* o
                     void* save_h1, float* save_stats, void* stream);
 
 /* p4c_mlp_forward with the aggregation of InteractionNet fused into the epilogue (K2+K3), for edge
- * sets whose edges are sorted by receiver with a uniform in-degree `group` (a power of two <= 32
- * that divides rows and full_rows, e.g. the 4 nearest mesh nodes of every grid node in m2g):
+ * sets whose edges are sorted by receiver with a uniform in-degree `group` (1, 2, 4 or 8, dividing
+ * rows and full_rows; e.g. the 4 nearest mesh nodes of every grid node in m2g):
  *   aggr_out[b][r / group][:] = scale * sum of the `group` consecutive messages y[b][r..][:]
  * (fp32 sum of the un-rounded messages, fixed butterfly order).  `out` (the messages) may be NULL:
  * they are then never written to memory.  Tensor-core engine, bf16 storage, out_features = 64. */
@@ -229,7 +232,8 @@ int p4c_wgrad_reduce_batched(const p4c_wgrad_t* table_dev, int32_t n, void* stre
 int p4c_seg_linear(const void* src, int64_t src_batch_stride, const int32_t* rowptr,
                    const int32_t* perm, const float* scale, int32_t num_seg, int32_t batch,
                    const float* w1, int32_t k1, int32_t col0, const void* packed, int32_t kblock,
-                   void* out, int64_t out_batch_stride, int accumulate, int dtype, void* stream);
+                   void* out, int64_t out_batch_stride, int accumulate, int32_t tile_rows /* as in
+                   p4c_mlp_t */, int dtype, void* stream);
 
 int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m);
 int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream);

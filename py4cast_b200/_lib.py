@@ -54,6 +54,7 @@ class Mlp(C.Structure):
         ("beta", C.c_void_p),
         ("ln_eps", C.c_float),
         ("packed", C.c_void_p),
+        ("tile_rows", C.c_int32),
     ]
 
 
@@ -152,7 +153,7 @@ SYMBOLS = {
     "p4c_pack_weights": (_int, [_vp, _i32, _vp]),
     "p4c_wgrad_reduce_batched": (_int, [_vp, _i32, _vp]),
     "p4c_seg_linear": (
-        _int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _int, _int, _vp]
+        _int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _int, _i32, _int, _vp]
     ),
     "p4c_mlp_backward": (_int, [C.POINTER(Mlp), C.POINTER(MlpBwd), _vp]),
     "p4c_rows_matmul": (_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _int, _int, _vp]),

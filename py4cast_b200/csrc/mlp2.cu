@@ -697,6 +697,8 @@ static int validate(const p4c_mlp_t* m) {
   P4C_REQUIRE(m->nsrc > 1 || m->src[0].index == nullptr || m->src[0].width == HID,
               "mlp: dense (non-64) source cannot be gathered");
   P4C_REQUIRE(m->w1 && m->b1 && m->w2 && m->b2, "mlp: null weights");
+  P4C_REQUIRE(m->tile_rows == 0 || m->tile_rows == 16 || m->tile_rows == 32 || m->tile_rows == 64 ||
+                  m->tile_rows == 128, "mlp: tile_rows=%d not in {0,16,32,64,128}", m->tile_rows);
   for (int s = 0; s < m->nsrc; ++s)
     P4C_REQUIRE(!m->src[s].seg_rowptr || (m->dtype == P4C_BF16 && tc_engine_enabled()),
                 "mlp: segment-sum sources need the tensor-core engine (bf16 storage)");
@@ -742,8 +744,8 @@ extern "C" int p4c_mlp_forward_aggregate(const p4c_mlp_t* m, void* out, void* ou
   int rc = validate(m);
   if (rc) return rc;
   P4C_REQUIRE(aggr_out != nullptr, "mlp_forward_aggregate: aggr_out is null");
-  P4C_REQUIRE(group >= 1 && group <= 32 && (group & (group - 1)) == 0,
-              "mlp_forward_aggregate: group=%d must be a power of two <= 32", group);
+  P4C_REQUIRE(group >= 1 && group <= 8 && (group & (group - 1)) == 0,
+              "mlp_forward_aggregate: group=%d must be 1, 2, 4 or 8", group);
   const int full = m->full_rows > 0 ? m->full_rows : m->rows;
   P4C_REQUIRE(m->rows % group == 0 && full % group == 0, "mlp_forward_aggregate: rows=%d / full_rows=%d not a multiple of group=%d",
               m->rows, full, group);

@@ -26,7 +26,6 @@ namespace p4c {
 namespace tc {
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 256;
 constexpr int HID = P4C_HIDDEN;
 constexpr int XBLK = TM * 128;   // bytes of one 128x64 bf16 tile
 constexpr int WBLK = HID * 128;  // bytes of one 64x64 bf16 tile
@@ -45,7 +44,7 @@ struct FwdSmem {
   uint32_t seg_base[2][TM];              // segment source: sample offset / 8 elements
   float seg_sc[2][TM];                   // segment source: row scale (1/deg for mean aggregation)
   int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid
-  float2 ln_part[2][TM];  // per-row partial (sum, sum of squares) of each column half
+  float2 ln_part[4][TM];  // per-row partial (sum, sum of squares) of each column group
   uint64_t mbar[2];
   uint32_t tmem_base;
 };
@@ -64,6 +63,7 @@ struct FwdArgs {
   int agg_group;
   float agg_scale;
   int zero_x;  // some block fetches fewer than 8 chunks per row: clear the tiles once
+  int tile_rows;  // valid rows per 128-row tile (16..128)
 };
 
 __device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, long long total_rows,
@@ -74,7 +74,7 @@ __device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, 
   long long o = -1;
   long long b = 0;
   int rr = 0;
-  if (g < total_rows) {
+  if (tid < a.tile_rows && g < total_rows) {
     b = g / m.rows;
     rr = static_cast<int>(g - b * m.rows);
     o = b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr;
@@ -104,21 +104,22 @@ __device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, 
 }
 
 // 128 rows x 64 bf16 per block -> swizzled smem; 8 consecutive threads handle one 128-byte row
+template <int NT, bool SEG>
 __device__ __forceinline__ void issue_gather(const FwdArgs& a, FwdSmem& S, int p, int tid) {
   for (int k = 0; k < a.kb.nblk; ++k) {
     const p4c_src_t& src = a.m.src[a.kb.src[k]];
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
     const uint32_t xs = smem_u32(S.X[k]);
-    if (src.seg_rowptr) {
+    if (SEG && src.seg_rowptr) {
       // InteractionNet.aggregate fused into the prologue (fixed summation order)
-      seg_sum_tile<NTHREADS>(base, src.seg_perm, S.row_off[p][k], S.seg_hi[p], S.seg_base[p], S.seg_sc[p],
-                             S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid);
+      seg_sum_tile<NT>(base, src.seg_perm, S.row_off[p][k], S.seg_hi[p], S.seg_base[p], S.seg_sc[p],
+                       S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid, a.tile_rows);
       continue;
     }
     const int nch = a.kb.nchunks[k];
 #pragma unroll
-    for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
-      const int idx = i * NTHREADS + tid;
+    for (int i = 0; i < (TM * 8) / NT; ++i) {
+      const int idx = i * NT + tid;
       const int r = idx >> 3, j = idx & 7;
       if (j < nch) {
         const uint32_t off = S.row_off[p][k][r];
@@ -129,17 +130,38 @@ __device__ __forceinline__ void issue_gather(const FwdArgs& a, FwdSmem& S, int p
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// NT threads = NT/128 threads per row, CPT = 8192/NT columns each (256 -> 32, 512 -> 16).
+// SEG: the instantiation that can sum segments in its prologue (it needs the registers of the
+// 256-thread shape); plain / gathered sources run with 512 threads (twice the warps to hide latency).
+template <int NT, bool SEG>
+__global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constant__ FwdArgs a) {
+  constexpr int CPT = TM * HID / NT;  // columns per thread
+  constexpr int NCG = NT / TM;        // column groups (threads per row)
   extern __shared__ unsigned char smem_raw[];
   // 128-byte swizzle needs 1024-byte aligned tiles
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(
       smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const p4c_mlp_t& m = a.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column half
-  const int row = quad * 32 + lane, col0 = hsel * 32;
+  const int quad = warp & 3, cg = warp >> 2;  // TMEM lane quadrant (rows) / column group
+  const int row = quad * 32 + lane, col0 = cg * CPT;
   const long long total_rows = static_cast<long long>(m.rows) * m.batch;
-  const long long ntiles = (total_rows + TM - 1) / TM;
+  const int TR = a.tile_rows;
+  const long long ntiles = (total_rows + TR - 1) / TR;
   const int OUT = m.out_features;
   const int nblk = a.kb.nblk;
   __nv_bfloat16* const out = a.out;
@@ -150,24 +172,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_c
   // ---- one-time set-up: weights (image: 16-byte async copies), barriers, TMEM
   if (a.zero_x) {
     uint4* xz = reinterpret_cast<uint4*>(S.X);
-    for (int i = tid; i < nblk * XBLK / 16; i += NTHREADS) xz[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < nblk * XBLK / 16; i += NT) xz[i] = make_uint4(0, 0, 0, 0);
   }
   if (m.packed) {
     const uint8_t* img = reinterpret_cast<const uint8_t*>(m.packed);
-    for (int i = tid; i < nblk * (WBLK / 16); i += NTHREADS)
+    for (int i = tid; i < nblk * (WBLK / 16); i += NT)
       cp_async16(smem_u32(S.W1) + i * 16, img + PK_W1 + i * 16, 16u);
-    for (int i = tid; i < WBLK / 16; i += NTHREADS) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
+    for (int i = tid; i < WBLK / 16; i += NT) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
     if (tid < 64) cp_async16(smem_u32(S.vec) + tid * 16, img + PK_VEC + tid * 16, 16u);
   } else {
     for (int k = 0; k < nblk; ++k) {
       const int ks = a.kb.kstart[k], kv = a.kb.kvalid[k];
-      for (int i = tid; i < HID * HID; i += NTHREADS) {
+      for (int i = tid; i < HID * HID; i += NT) {
         const int c = i >> 6, kk = i & 63;
         *reinterpret_cast<__nv_bfloat16*>(S.W1[k] + sw128_offset(c, kk >> 3) + (kk & 7) * 2) =
             __float2bfloat16_rn(kk < kv ? m.w1[static_cast<long long>(c) * m.k1 + ks + kk] : 0.f);
       }
     }
-    for (int i = tid; i < HID * HID; i += NTHREADS) {
+    for (int i = tid; i < HID * HID; i += NT) {
       const int c = i >> 6, k = i & 63;
       *reinterpret_cast<__nv_bfloat16*>(S.W2 + sw128_offset(c, k >> 3) + (k & 7) * 2) =
           __float2bfloat16_rn(c < OUT ? m.w2[c * HID + k] : 0.f);
@@ -193,16 +215,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_c
   const uint32_t tmem = S.tmem_base;
   const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
   constexpr uint32_t IDESC = make_idesc_bf16(TM, HID, 0, 0);
-  const float* const b1 = S.vec[0];
-  const float* const b2 = S.vec[1];
-  const float* const gamma = S.vec[2];
-  const float* const beta = S.vec[3];
+  const float* const b1 = S.vec[0] + col0;
+  const float* const b2 = S.vec[1] + col0;
+  const float* const gamma = S.vec[2] + col0;
+  const float* const beta = S.vec[3] + col0;
 
   long long tile = blockIdx.x;
   if (tile < ntiles) {
-    row_info(a, tile * TM, total_rows, S, 0, tid);
+    row_info(a, tile * TR, total_rows, S, 0, tid);
     __syncthreads();
-    issue_gather(a, S, 0, tid);
+    issue_gather<NT, SEG>(a, S, 0, tid);
   }
   cp_async_commit();
 
@@ -227,41 +249,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_c
     }
     // meanwhile: addressing of the next tile
     const long long next = tile + gridDim.x;
-    if (next < ntiles) row_info(a, next * TM, total_rows, S, p ^ 1, tid);
+    if (next < ntiles) row_info(a, next * TR, total_rows, S, p ^ 1, tid);
     mbar_wait(&S.mbar[0], parity);
     tc_fence_after();
     __syncthreads();  // row_off[p^1] visible; X is free again
-    if (next < ntiles) issue_gather(a, S, p ^ 1, tid);
+    if (next < ntiles) issue_gather<NT, SEG>(a, S, p ^ 1, tid);
     cp_async_commit();
 
     // ---- epilogue 1: h1 = D1 + b1 (saved), a1 = SiLU(h1) -> A2 (bf16, swizzled)
     const long long orow = S.orow[p][row];
     {
-      float v[32];
-      tmem_ld32(tmem_row, v);
+      float v[CPT];
+      tmem_ld<CPT>(tmem_row, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c0 = col0 + j * 8;
+      for (int j = 0; j < CPT / 8; ++j) {
         float h[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = v[j * 8 + q] + b1[c0 + q];
-        uint4 hb;
-        hb.x = pack_bf16x2(h[0], h[1]); hb.y = pack_bf16x2(h[2], h[3]);
-        hb.z = pack_bf16x2(h[4], h[5]); hb.w = pack_bf16x2(h[6], h[7]);
+        for (int q = 0; q < 8; ++q) h[q] = v[j * 8 + q] + b1[j * 8 + q];
+        const uint4 hb = pack8f(h);
         if (save_h1) {
-          if (orow >= 0) *reinterpret_cast<uint4*>(save_h1 + orow * HID + c0) = hb;
-          // backward recomputes from the stored (rounded) value
-          float2 t;
-          t = unpack_bf16x2(hb.x); h[0] = t.x; h[1] = t.y;
-          t = unpack_bf16x2(hb.y); h[2] = t.x; h[3] = t.y;
-          t = unpack_bf16x2(hb.z); h[4] = t.x; h[5] = t.y;
-          t = unpack_bf16x2(hb.w); h[6] = t.x; h[7] = t.y;
+          if (orow >= 0) *reinterpret_cast<uint4*>(save_h1 + orow * HID + col0 + j * 8) = hb;
+          unpack8f(hb, h);  // backward recomputes from the stored (rounded) value
         }
-        uint4 ab;
-        ab.x = pack_bf16x2(fast_silu(h[0]), fast_silu(h[1])); ab.y = pack_bf16x2(fast_silu(h[2]), fast_silu(h[3]));
-        ab.z = pack_bf16x2(fast_silu(h[4]), fast_silu(h[5])); ab.w = pack_bf16x2(fast_silu(h[6]), fast_silu(h[7]));
-        *reinterpret_cast<uint4*>(S.A2 + sw128_offset(row, c0 >> 3)) = ab;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+        *reinterpret_cast<uint4*>(S.A2 + sw128_offset(row, (col0 >> 3) + j)) = pack8f(h);
       }
     }
     fence_proxy_async();
@@ -281,31 +294,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_c
     mbar_wait(&S.mbar[1], parity);
     tc_fence_after();
 
-    // ---- epilogue 2: y = D2 + b2, LayerNorm (two threads per row), residual, stores
+    // ---- epilogue 2: y = D2 + b2, LayerNorm (NCG threads per row), residual, stores
     {
-      float y[32];
-      tmem_ld32(tmem_row + HID, y);
+      float y[CPT];
+      tmem_ld<CPT>(tmem_row + HID, y);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 32; ++q) y[q] += b2[col0 + q];
+      for (int q = 0; q < CPT; ++q) y[q] += b2[q];
       if (m.layer_norm) {
-        float ps = 0.f, pq = 0.f;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          ps += y[q];
-          pq = fmaf(y[q], y[q], pq);
+        for (int q = 0; q < CPT; ++q) {
+          ps[q & 3] += y[q];
+          pq[q & 3] = fmaf(y[q], y[q], pq[q & 3]);
         }
-        S.ln_part[hsel][row] = make_float2(ps, pq);
+        S.ln_part[cg][row] = make_float2((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]));
         __syncthreads();
-        const float2 lo = S.ln_part[0][row], hi = S.ln_part[1][row];  // same order in both threads
-        const float mean = (lo.x + hi.x) * (1.0f / HID);
-        const float var = fmaxf((lo.y + hi.y) * (1.0f / HID) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + m.ln_eps);
+        float sx = 0.f, sq = 0.f;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) y[q] = (y[q] - mean) * rstd * gamma[col0 + q] + beta[col0 + q];
-        if (a.save_stats && orow >= 0 && hsel == 0) {
-          a.save_stats[2 * orow] = mean;
-          a.save_stats[2 * orow + 1] = rstd;
+        for (int c = 0; c < NCG; ++c) {  // same order in every thread of the row
+          const float2 t = S.ln_part[c][row];
+          sx += t.x;
+          sq += t.y;
+        }
+        const float mean = sx * (1.0f / HID);
+        const float var = fmaxf(sq * (1.0f / HID) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + m.ln_eps);
+        const float nm = -mean * rstd;
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) y[q] = fmaf(fmaf(y[q], rstd, nm), gamma[q], beta[q]);
+        if (a.save_stats && orow >= 0 && cg == 0) {
+          *reinterpret_cast<float2*>(a.save_stats + 2 * orow) = make_float2(mean, rstd);
         }
       }
       if (OUT == HID) {
@@ -315,59 +334,77 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_fwd_kernel(const __grid_c
                          (static_cast<long long>(S.row_off[p][0][row]) << 3) + col0
                    : nullptr;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CPT / 8; ++j) {
             float yy[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) yy[q] = y[j * 8 + q];
             const int c0 = col0 + j * 8;
             if (out2) {
-              const uint4 e = *reinterpret_cast<const uint4*>(e_row + j * 8);
-              const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z),
-                           e3 = unpack_bf16x2(e.w);
-              uint4 o;
-              o.x = pack_bf16x2(e0.x + yy[0], e0.y + yy[1]); o.y = pack_bf16x2(e1.x + yy[2], e1.y + yy[3]);
-              o.z = pack_bf16x2(e2.x + yy[4], e2.y + yy[5]); o.w = pack_bf16x2(e3.x + yy[6], e3.y + yy[7]);
-              *reinterpret_cast<uint4*>(out2 + orow * HID + c0) = o;
+              float e[8];
+              unpack8f(*reinterpret_cast<const uint4*>(e_row + j * 8), e);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) e[q] += yy[q];
+              *reinterpret_cast<uint4*>(out2 + orow * HID + c0) = pack8f(e);
             }
             if (out) {
               if (residual) {
-                const uint4 e = *reinterpret_cast<const uint4*>(residual + orow * HID + c0);
-                const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z),
-                             e3 = unpack_bf16x2(e.w);
-                yy[0] += e0.x; yy[1] += e0.y; yy[2] += e1.x; yy[3] += e1.y;
-                yy[4] += e2.x; yy[5] += e2.y; yy[6] += e3.x; yy[7] += e3.y;
+                float e[8];
+                unpack8f(*reinterpret_cast<const uint4*>(residual + orow * HID + c0), e);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) yy[q] += e[q];
               }
-              uint4 o;
-              o.x = pack_bf16x2(yy[0], yy[1]); o.y = pack_bf16x2(yy[2], yy[3]);
-              o.z = pack_bf16x2(yy[4], yy[5]); o.w = pack_bf16x2(yy[6], yy[7]);
-              *reinterpret_cast<uint4*>(out + orow * HID + c0) = o;
+              *reinterpret_cast<uint4*>(out + orow * HID + c0) = pack8f(yy);
             }
           }
         }
         if (a.aggr_out) {
           // fused aggregation: sum the messages of `agg_group` consecutive rows (= lanes) with a
-          // fixed butterfly (fp32, before any rounding); invalid rows contribute zero
+          // transposing butterfly: at every step a lane hands one half of its columns to its
+          // partner and adds the partner's other half, so after log2(group) steps each lane holds
+          // CPT/group columns summed over the group (fp32, fixed order; invalid rows add zero).
           const int gsz = a.agg_group;
+          if (orow < 0) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            float v = orow >= 0 ? y[q] : 0.f;
-            for (int off = 1; off < gsz; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            y[q] = v * a.agg_scale;
+            for (int q = 0; q < CPT; ++q) y[q] = 0.f;
           }
-          if (orow >= 0 && (lane & (gsz - 1)) == 0) {
-            __nv_bfloat16* dst = a.aggr_out + (orow / gsz) * HID + col0;
+          int cbase = 0;  // first column (relative to col0) this lane ends up with
+#define P4C_AGG_STEP(OFF, N)                                                     \
+          if ((N) >= 2 && gsz > OFF) {                                           \
+            const bool up = (lane & OFF) != 0;                                   \
+            _Pragma("unroll") for (int i = 0; i < (N) / 2; ++i) {                \
+              const float send = up ? y[i] : y[i + (N) / 2];                     \
+              const float keep = up ? y[i + (N) / 2] : y[i];                     \
+              y[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);             \
+            }                                                                    \
+            if (up) cbase += (N) / 2;                                            \
+          }
+          P4C_AGG_STEP(1, CPT)
+          P4C_AGG_STEP(2, CPT / 2)
+          P4C_AGG_STEP(4, CPT / 4)
+          P4C_AGG_STEP(8, CPT / 8)
+#undef P4C_AGG_STEP
+          if (orow >= 0) {
+            const int ncol = CPT / gsz;
+            __nv_bfloat16* dst = a.aggr_out + (orow / gsz) * HID + col0 + cbase;
+            const float sc = a.agg_scale;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(y[j * 8 + 0], y[j * 8 + 1]); o.y = pack_bf16x2(y[j * 8 + 2], y[j * 8 + 3]);
-              o.z = pack_bf16x2(y[j * 8 + 4], y[j * 8 + 5]); o.w = pack_bf16x2(y[j * 8 + 6], y[j * 8 + 7]);
-              *reinterpret_cast<uint4*>(dst + j * 8) = o;
+            for (int q = 0; q < CPT; ++q) y[q] *= sc;
+            if (ncol >= 8) {
+#pragma unroll
+              for (int j = 0; j < CPT / 8; ++j)
+                if (j < ncol / 8) *reinterpret_cast<uint4*>(dst + j * 8) = pack8f(y + j * 8);
+            } else if (ncol == 4) {
+              uint2 o;
+              o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+              *reinterpret_cast<uint2*>(dst) = o;
+            } else {
+              *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[0], y[1]);
             }
           }
         }
       } else if (orow >= 0) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
+        for (int q = 0; q < CPT; ++q) {
           const int c = col0 + q;
           if (c < OUT) {
             float v = y[q];
@@ -431,20 +468,33 @@ int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   a.agg_scale = agg_scale;
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  a.tile_rows = m->tile_rows > 0 ? m->tile_rows : TM;
+  if (aggr_out && a.tile_rows != TM) {
+    set_error("mlp_forward_aggregate: tile_rows must be 128 (or 0)");
+    return P4C_EINVAL;
+  }
   const long long total = static_cast<long long>(m->rows) * m->batch;
-  const long long ntiles = (total + TM - 1) / TM;
+  const long long ntiles = (total + a.tile_rows - 1) / a.tile_rows;
   const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
   const size_t smem = sizeof(FwdSmem) + 1024;
+  bool has_seg = false;
+  for (int s = 0; s < m->nsrc; ++s) has_seg |= m->src[s].seg_rowptr != nullptr;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp2_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mlp2_tc_fwd_kernel<512, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp2_tc_fwd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mlp_forward(tc): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return P4C_ECUDA;
     }
     configured = true;
   }
-  mlp2_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(a);
+  if (has_seg)
+    mlp2_tc_fwd_kernel<256, true><<<grid, 256, smem, st>>>(a);
+  else
+    mlp2_tc_fwd_kernel<512, false><<<grid, 512, smem, st>>>(a);
   P4C_CHECK_LAUNCH("mlp_forward(tc)");
   return P4C_OK;
 }

@@ -135,6 +135,7 @@ struct SegLinArgs {
   __nv_bfloat16* out;
   long long out_bs;
   int accumulate;
+  int tile_rows;  // valid rows per tile (16..128)
 };
 
 __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_constant__ SegLinArgs a) {
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
   const int quad = warp & 3, hsel = warp >> 2;
   const int row = quad * 32 + lane, col0 = hsel * 32;
   const long long total = static_cast<long long>(a.num_seg) * a.batch;
-  const long long ntiles = (total + 127) / 128;
+  const int TR = a.tile_rows;
+  const long long ntiles = (total + TR - 1) / TR;
 
   if (a.packed_block) {
     for (int i = tid; i < 512; i += 256) cp_async16(smem_u32(S.W) + i * 16, a.packed_block + i * 16, 16u);
@@ -172,11 +174,11 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
   uint32_t it = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     if (tid < 128) {
-      const long long g = tile * 128 + tid;
+      const long long g = tile * TR + tid;
       uint32_t lo = 0xFFFFFFFFu, hi = 0, sb = 0;
       float sc = 1.f;
       int32_t o = -1;
-      if (g < total) {
+      if (tid < TR && g < total) {
         const long long b = g / a.num_seg;
         const int rr = static_cast<int>(g - b * a.num_seg);
         lo = static_cast<uint32_t>(a.rowptr[rr]);
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
       S.lo[tid] = lo; S.hi[tid] = hi; S.sbase[tid] = sb; S.sc[tid] = sc; S.orow[tid] = o;
     }
     __syncthreads();
-    seg_sum_tile<256>(a.src, a.perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid);
+    seg_sum_tile<256>(a.src, a.perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
     cp_async_wait<0>();  // the weight block (first tile)
     fence_proxy_async();
     tc_fence_before();
@@ -258,7 +260,7 @@ extern "C" int p4c_wgrad_reduce_batched(const p4c_wgrad_t* table_dev, int32_t n,
 extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* rowptr, const int32_t* perm,
                               const float* scale, int32_t num_seg, int32_t batch, const float* w1, int32_t k1,
                               int32_t col0, const void* packed, int32_t kblock, void* out, int64_t out_bs,
-                              int accumulate, int dtype, void* stream) {
+                              int accumulate, int32_t tile_rows, int dtype, void* stream) {
   P4C_REQUIRE(src && rowptr && out && w1, "seg_linear: null pointer");
   P4C_REQUIRE(num_seg > 0 && batch > 0, "seg_linear: empty problem");
   P4C_REQUIRE(dtype == P4C_BF16, "seg_linear: tensor-core engine, bf16 storage only (dtype=%d)", dtype);
@@ -267,6 +269,9 @@ extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* ro
   P4C_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
               "seg_linear: src / out must be 16-byte aligned");
   P4C_REQUIRE(!packed || (kblock >= 0 && kblock < P4C_MAX_SRC), "seg_linear: bad kblock %d", kblock);
+  if (tile_rows == 0) tile_rows = 128;
+  P4C_REQUIRE(tile_rows == 16 || tile_rows == 32 || tile_rows == 64 || tile_rows == 128,
+              "seg_linear: tile_rows=%d not in {16,32,64,128}", tile_rows);
   using namespace tc;
   SegLinArgs a;
   a.src = static_cast<const __nv_bfloat16*>(src);
@@ -283,7 +288,8 @@ extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* ro
   a.out = static_cast<__nv_bfloat16*>(out);
   a.out_bs = out_bs;
   a.accumulate = accumulate;
-  const long long ntiles = (static_cast<long long>(num_seg) * batch + 127) / 128;
+  a.tile_rows = tile_rows;
+  const long long ntiles = (static_cast<long long>(num_seg) * batch + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
   const size_t smem = sizeof(SegLinSmem) + 1024;
   seg_linear_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);

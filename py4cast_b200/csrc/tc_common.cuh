@@ -92,6 +92,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- mbarrier ---------------------------------------------------------------------------------
@@ -106,18 +123,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
-    if ((spin & 1023u) == 1023u) {  // try_wait suspends in hardware; look at the clock rarely
+    if ((spin & 63u) == 63u) {  // each try_wait may suspend the thread in hardware for up to ~20 us
       if (t0 == 0) t0 = clock64();
       else if (clock64() - t0 > 4000000000ll) __trap();
     }
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
   }
 }
@@ -159,64 +176,105 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 
 // ---- segment sum of 64-wide bf16 rows into one 128-row swizzled smem tile ------------------------
 // Row r of the tile = sc[r] * sum_{e in [lo[r], hi[r])} src[sbase[r]*8 + (perm ? perm[e] : e) * 64 ..]
-// (lo[r] == ~0u: zero row).  One warp per row at a time: lane = 8 * g + j sums the edges
-// lo+g, lo+g+4, ... of 16-byte chunk j (two interleaved partial sums), the 4 edge groups are then
-// combined with two shuffles: a fixed order, so the result is bit-reproducible.  fp32 accumulation,
-// one rounding to bf16.  Optionally also stores the rows to out_rows[orow[r]] (global).
+// (lo[r] == ~0u: zero row).  One warp per row: lane = 8 * g + j sums the edges lo+g, lo+g+4, ... of
+// 16-byte chunk j into two interleaved partial sums (s0: edges lo+g+8i, s1: lo+g+4+8i), the 4 edge
+// groups are then combined with two shuffles: a fixed order, so the result is bit-reproducible.
+// Memory-level parallelism: a warp works on RB rows at once (index loads of all rows in flight,
+// then the row loads), and long segments are walked 4 edges per lane per iteration.
+// fp32 accumulation, one rounding to bf16.  Optionally also stores the rows to out_rows[orow[r]].
+__device__ __forceinline__ void seg_add8(float* s, const uint4& u) {
+  float2 t;
+  t = unpack_bf16x2(u.x); s[0] += t.x; s[1] += t.y;
+  t = unpack_bf16x2(u.y); s[2] += t.x; s[3] += t.y;
+  t = unpack_bf16x2(u.z); s[4] += t.x; s[5] += t.y;
+  t = unpack_bf16x2(u.w); s[6] += t.x; s[7] += t.y;
+}
+
 template <int NTHREADS>
 __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ perm,
                                              const uint32_t* lo, const uint32_t* hi, const uint32_t* sbase,
                                              const float* sc, const int32_t* orow, uint8_t* X,
-                                             __nv_bfloat16* out_rows, int tid) {
+                                             __nv_bfloat16* __restrict__ out_rows, int tid, int nrows = 128) {
+  constexpr int RB = 4;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, j = lane & 7;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-  for (int r = warp; r < 128; r += NTHREADS / 32) {
-    const uint32_t l = lo[r];
-    float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (l != 0xFFFFFFFFu) {
-      const uint32_t h = hi[r];
-      const __nv_bfloat16* sb = src + (static_cast<long long>(sbase[r]) << 3) + j * 8;
-      uint32_t e = l + g;
-      for (; e + 4 < h; e += 8) {
-        const long long e0 = perm ? perm[e] : e;
-        const long long e1 = perm ? perm[e + 4] : e + 4;
-        const uint4 u0 = *reinterpret_cast<const uint4*>(sb + e0 * 64);
-        const uint4 u1 = *reinterpret_cast<const uint4*>(sb + e1 * 64);
-        float2 t;
-        t = unpack_bf16x2(u0.x); s0[0] += t.x; s0[1] += t.y;
-        t = unpack_bf16x2(u0.y); s0[2] += t.x; s0[3] += t.y;
-        t = unpack_bf16x2(u0.z); s0[4] += t.x; s0[5] += t.y;
-        t = unpack_bf16x2(u0.w); s0[6] += t.x; s0[7] += t.y;
-        t = unpack_bf16x2(u1.x); s1[0] += t.x; s1[1] += t.y;
-        t = unpack_bf16x2(u1.y); s1[2] += t.x; s1[3] += t.y;
-        t = unpack_bf16x2(u1.z); s1[4] += t.x; s1[5] += t.y;
-        t = unpack_bf16x2(u1.w); s1[6] += t.x; s1[7] += t.y;
-      }
-      if (e < h) {
-        const long long e0 = perm ? perm[e] : e;
-        const uint4 u0 = *reinterpret_cast<const uint4*>(sb + e0 * 64);
-        float2 t;
-        t = unpack_bf16x2(u0.x); s0[0] += t.x; s0[1] += t.y;
-        t = unpack_bf16x2(u0.y); s0[2] += t.x; s0[3] += t.y;
-        t = unpack_bf16x2(u0.z); s0[4] += t.x; s0[5] += t.y;
-        t = unpack_bf16x2(u0.w); s0[6] += t.x; s0[7] += t.y;
-      }
-    }
-    const float scale = sc[r];
+  for (int r0 = warp * RB; r0 < nrows; r0 += (NTHREADS / 32) * RB) {
+    float s0[RB][8], s1[RB][8];
+    uint32_t l[RB], h[RB];
+    const __nv_bfloat16* sb[RB];
+    long long ea[RB], eb[RB];
+    bool va[RB], vb[RB];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float v = s0[q] + s1[q];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      s0[q] = v * scale;
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;
+      l[i] = r < nrows ? lo[r] : 0xFFFFFFFFu;
+      h[i] = l[i] != 0xFFFFFFFFu ? hi[r] : 0u;
+      sb[i] = src + (l[i] != 0xFFFFFFFFu ? (static_cast<long long>(sbase[r]) << 3) : 0ll) + j * 8;
+      const uint32_t pa = l[i] + g, pb = pa + 4;
+      va[i] = l[i] != 0xFFFFFFFFu && pa < h[i];
+      vb[i] = l[i] != 0xFFFFFFFFu && pb < h[i];
+      ea[i] = va[i] ? (perm ? static_cast<long long>(perm[pa]) : static_cast<long long>(pa)) : 0ll;
+      eb[i] = vb[i] ? (perm ? static_cast<long long>(perm[pb]) : static_cast<long long>(pb)) : 0ll;
     }
-    if (g == 0) {
-      uint4 o;
-      o.x = pack_bf16x2(s0[0], s0[1]); o.y = pack_bf16x2(s0[2], s0[3]);
-      o.z = pack_bf16x2(s0[4], s0[5]); o.w = pack_bf16x2(s0[6], s0[7]);
-      *reinterpret_cast<uint4*>(X + sw128_offset(r, j)) = o;
-      if (out_rows && l != 0xFFFFFFFFu)
-        *reinterpret_cast<uint4*>(out_rows + static_cast<long long>(orow[r]) * 64 + j * 8) = o;
+    uint4 ua[RB], ub[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      ua[i] = va[i] ? *reinterpret_cast<const uint4*>(sb[i] + ea[i] * 64) : zero4;
+      ub[i] = vb[i] ? *reinterpret_cast<const uint4*>(sb[i] + eb[i] * 64) : zero4;
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s0[i][q] = s1[i][q] = 0.f;
+      seg_add8(s0[i], ua[i]);
+      seg_add8(s1[i], ub[i]);
+    }
+    // long segments: 4 more edges per lane per iteration (positions +8, +12, +16, +20 ...)
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      if (l[i] == 0xFFFFFFFFu) continue;
+      uint32_t e = l[i] + g + 8;
+      for (; e + 12 < h[i]; e += 16) {
+        const long long e0 = perm ? perm[e] : e, e1 = perm ? perm[e + 4] : e + 4;
+        const long long e2 = perm ? perm[e + 8] : e + 8, e3 = perm ? perm[e + 12] : e + 12;
+        const uint4 u0 = *reinterpret_cast<const uint4*>(sb[i] + e0 * 64);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(sb[i] + e1 * 64);
+        const uint4 u2 = *reinterpret_cast<const uint4*>(sb[i] + e2 * 64);
+        const uint4 u3 = *reinterpret_cast<const uint4*>(sb[i] + e3 * 64);
+        seg_add8(s0[i], u0);
+        seg_add8(s1[i], u1);
+        seg_add8(s0[i], u2);
+        seg_add8(s1[i], u3);
+      }
+      for (; e < h[i]; e += 8) {
+        const long long e0 = perm ? perm[e] : e;
+        seg_add8(s0[i], *reinterpret_cast<const uint4*>(sb[i] + e0 * 64));
+        if (e + 4 < h[i]) {
+          const long long e1 = perm ? perm[e + 4] : e + 4;
+          seg_add8(s1[i], *reinterpret_cast<const uint4*>(sb[i] + e1 * 64));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int r = r0 + i;
+      const float scale = r < nrows ? sc[r] : 1.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v = s0[i][q] + s1[i][q];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        s0[i][q] = v * scale;
+      }
+      if (g == 0 && r < nrows) {
+        uint4 o;
+        o.x = pack_bf16x2(s0[i][0], s0[i][1]); o.y = pack_bf16x2(s0[i][2], s0[i][3]);
+        o.z = pack_bf16x2(s0[i][4], s0[i][5]); o.w = pack_bf16x2(s0[i][6], s0[i][7]);
+        *reinterpret_cast<uint4*>(X + sw128_offset(r, j)) = o;
+        if (out_rows && l[i] != 0xFFFFFFFFu)
+          *reinterpret_cast<uint4*>(out_rows + static_cast<long long>(orow[r]) * 64 + j * 8) = o;
+      }
     }
   }
 }

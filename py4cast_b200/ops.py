@@ -236,8 +236,8 @@ class GraphIndex:
     by_rec: Csr  # all edges keyed by receiver
     groups: List[EdgeGroup] = field(default_factory=list)
     node_chunks: Optional[List[Tuple[int, int]]] = None  # receiver ranges with own node-MLP weights
-    # > 0: edges are sorted by receiver and every receiver has exactly this many (a power of two
-    # <= 32): edge e belongs to receiver e // uniform_deg, so the aggregation can run in the
+    # > 0: edges are sorted by receiver and every receiver has exactly this many (1, 2, 4 or 8):
+    # edge e belongs to receiver e // uniform_deg, so the aggregation can run in the
     # epilogue of the edge kernel (m2g: 4 nearest mesh nodes; up / down edges: 1)
     uniform_deg: int = 0
 
@@ -280,7 +280,7 @@ class GraphIndex:
         uniform = 0
         if edge_chunk_sizes is None and by_rec.perm is None and num_rec > 0 and E % num_rec == 0:
             d = E // num_rec
-            if d in (1, 2, 4, 8, 16, 32):
+            if d in (1, 2, 4, 8):
                 expect = torch.arange(num_rec + 1, dtype=torch.int32, device=rec.device) * d
                 if bool(torch.equal(by_rec.rowptr, expect)):
                     uniform = d
@@ -430,9 +430,23 @@ def _fill_mlp(desc: Mlp, rows: int, batch: int, full_rows: int, srcs: Sequence[_
     desc.gamma, desc.beta = ptr(gamma), ptr(beta)
     desc.ln_eps = 1e-5
     desc.packed = None
+    desc.tile_rows = 0
+    for sp in srcs:
+        if sp.seg is not None:
+            desc.tile_rows = _seg_tile_rows(sp.tensor.shape[-2], sp.seg.num_seg)
     if meta is not None:
         assert meta.widths == tuple(s.tensor.shape[-1] for s in srcs), "weight image packed for other source widths"
         desc.packed = meta.image_ptr(dtype)
+
+
+def _seg_tile_rows(num_edges: int, num_seg: int) -> int:
+    """Valid rows per CTA tile of a segment-sum prologue: ~1k edges per CTA, so that long segments
+    (g2m: ~70 edges per mesh node, m2g by sender: ~200) are spread over many CTAs."""
+    avg = max(1.0, num_edges / max(1, num_seg))
+    rows = 128
+    while rows > 16 and rows * avg > 1024:
+        rows //= 2
+    return rows
 
 
 def _grad_target(p: Optional[torch.Tensor], needed: bool):
@@ -581,7 +595,8 @@ def seg_linear(src: torch.Tensor, csr: Csr, batch: int, w1: torch.Tensor, col0: 
         _lib.load().p4c_seg_linear(
             ptr(src), src.shape[1] * HIDDEN, ptr(csr.rowptr), ptr(csr.perm), ptr(csr.inv_deg) if mean else None,
             csr.num_seg, batch, ptr(w1), w1.shape[1], col0, packed, col0 // HIDDEN, ptr(out),
-            out.shape[1] * HIDDEN, int(accumulate), dtype_code(src.dtype), stream(),
+            out.shape[1] * HIDDEN, int(accumulate), _seg_tile_rows(src.shape[1], csr.num_seg),
+            dtype_code(src.dtype), stream(),
         ),
         "p4c_seg_linear",
     )

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (LP64): see include/py4cast_b200.h
     assert ctypes.sizeof(_lib.Src) == 64
-    assert ctypes.sizeof(_lib.Mlp) == 8 * 4 + 3 * 64 + 6 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Mlp) == 8 * 4 + 3 * 64 + 6 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.AdamWState) == 24
     assert ctypes.sizeof(_lib.Pack) == 7 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.WGrad) == 7 * 8 + 4 * 4
