@@ -159,6 +159,9 @@ int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* stream);
  * allows (bf16 storage, 64-wide sources), 0 = CUDA-core fp32 FFMA everywhere.  The environment
  * variable P4C_ENGINE=simt sets the initial value to 0. */
 void p4c_set_engine(int tensor_cores);
+/* developer aid: when set (16 x int64 device buffer), CTA 0 of the tensor-core forward kernel stores
+ * the SM clock at the phases of its first tile (set-up, gather, GEMM 1, epilogue 1, ...). NULL = off. */
+void p4c_set_trace_buffer(void* device_buffer);
 int p4c_get_engine(void);
 
 int p4c_mlp_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2,

@@ -735,6 +735,7 @@ static int set_smem(size_t bytes, const char* name) {
 
 using namespace p4c;
 
+extern "C" void p4c_set_trace_buffer(void* device_buffer) { tc_set_trace(static_cast<long long*>(device_buffer)); }
 extern "C" void p4c_set_engine(int tensor_cores) { g_tc_enabled = tensor_cores ? 1 : 0; }
 extern "C" int p4c_get_engine(void) { return tc_engine_enabled() ? 1 : 0; }
 

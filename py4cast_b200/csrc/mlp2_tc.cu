@@ -64,7 +64,14 @@ struct FwdArgs {
   float agg_scale;
   int zero_x;  // some block fetches fewer than 8 chunks per row: clear the tiles once
   int tile_rows;  // valid rows per 128-row tile (16..128)
+  long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's first tile
 };
+
+static long long* g_trace = nullptr;
+#define P4C_TRACE(i)                                   \
+  do {                                                 \
+    if (a.trace && blockIdx.x == 0 && tid == 0 && it == 0) a.trace[i] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, long long total_rows,
                                          FwdSmem& S, int p, int tid) {
@@ -113,7 +120,8 @@ __device__ __forceinline__ void issue_gather(const FwdArgs& a, FwdSmem& S, int p
     if (SEG && src.seg_rowptr) {
       // InteractionNet.aggregate fused into the prologue (fixed summation order)
       seg_sum_tile<NT>(base, src.seg_perm, S.row_off[p][k], S.seg_hi[p], S.seg_base[p], S.seg_sc[p],
-                       S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid, a.tile_rows);
+                       S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid, a.tile_rows,
+                       (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace : nullptr);
       continue;
     }
     const int nch = a.kb.nchunks[k];
@@ -170,6 +178,10 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
   const __nv_bfloat16* const residual = a.residual;
 
   // ---- one-time set-up: weights (image: 16-byte async copies), barriers, TMEM
+  {
+    const int it = 0;
+    P4C_TRACE(0);
+  }
   if (a.zero_x) {
     uint4* xz = reinterpret_cast<uint4*>(S.X);
     for (int i = tid; i < nblk * XBLK / 16; i += NT) xz[i] = make_uint4(0, 0, 0, 0);
@@ -221,12 +233,24 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
   const float* const beta = S.vec[3] + col0;
 
   long long tile = blockIdx.x;
+  {
+    const int it = 0;
+    P4C_TRACE(1);
+  }
   if (tile < ntiles) {
     row_info(a, tile * TR, total_rows, S, 0, tid);
     __syncthreads();
+    {
+      const int it = 0;
+      P4C_TRACE(2);
+    }
     issue_gather<NT, SEG>(a, S, 0, tid);
   }
   cp_async_commit();
+  {
+    const int it = 0;
+    P4C_TRACE(3);
+  }
 
   for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
     const int p = it & 1;
@@ -234,6 +258,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();  // X(tile) (and, first time, the weights) complete and visible to the tensor core
+    P4C_TRACE(4);
 
     // ---- GEMM 1: D1[128x64] = X[128 x 64*nblk] * W1^T
     if (tid == 0) {
@@ -253,6 +278,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     mbar_wait(&S.mbar[0], parity);
     tc_fence_after();
     __syncthreads();  // row_off[p^1] visible; X is free again
+    P4C_TRACE(5);
     if (next < ntiles) issue_gather<NT, SEG>(a, S, p ^ 1, tid);
     cp_async_commit();
 
@@ -280,6 +306,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    P4C_TRACE(6);
 
     // ---- GEMM 2: D2[128x64] = A2[128x64] * W2^T
     if (tid == 0) {
@@ -293,6 +320,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     }
     mbar_wait(&S.mbar[1], parity);
     tc_fence_after();
+    P4C_TRACE(7);
 
     // ---- epilogue 2: y = D2 + b2, LayerNorm (NCG threads per row), residual, stores
     {
@@ -415,11 +443,16 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
       }
     }
     tc_fence_before();
+    P4C_TRACE(8);
   }
 
   cp_async_wait<0>();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  {
+    const int it = 0;
+    P4C_TRACE(9);
+  }
 }
 
 }  // namespace tc
@@ -437,6 +470,8 @@ bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb) {
   for (int s = 0; s < m->nsrc; ++s) widths[s] = m->src[s].width;
   return tc::make_kblocks(m->nsrc, widths, kb);
 }
+
+void tc_set_trace(long long* buf) { tc::g_trace = buf; }
 
 bool tc_forward_supported(const p4c_mlp_t* m) {
   if (m->dtype != P4C_BF16) return false;
@@ -469,6 +504,7 @@ int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
   a.tile_rows = m->tile_rows > 0 ? m->tile_rows : TM;
+  a.trace = g_trace;
   if (aggr_out && a.tile_rows != TM) {
     set_error("mlp_forward_aggregate: tile_rows must be 128 (or 0)");
     return P4C_EINVAL;

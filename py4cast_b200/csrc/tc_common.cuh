@@ -175,13 +175,14 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ---- segment sum of 64-wide bf16 rows into one 128-row swizzled smem tile ------------------------
-// Row r of the tile = sc[r] * sum_{e in [lo[r], hi[r])} src[sbase[r]*8 + (perm ? perm[e] : e) * 64 ..]
-// (lo[r] == ~0u: zero row).  One warp per row: lane = 8 * g + j sums the edges lo+g, lo+g+4, ... of
-// 16-byte chunk j into two interleaved partial sums (s0: edges lo+g+8i, s1: lo+g+4+8i), the 4 edge
-// groups are then combined with two shuffles: a fixed order, so the result is bit-reproducible.
-// Memory-level parallelism: a warp works on RB rows at once (index loads of all rows in flight,
-// then the row loads), and long segments are walked 4 edges per lane per iteration.
-// fp32 accumulation, one rounding to bf16.  Optionally also stores the rows to out_rows[orow[r]].
+// Row r (< nrows) of the tile = sc[r] * sum_{e in [lo[r], hi[r])} src[sbase[r]*8 + (perm ? perm[e] : e)*64 ..]
+// (lo[r] == ~0u: zero row).  Work items = (row, edge group g < G, 16-byte chunk j < 8) with
+// G = 128 / nrows (1, 2 or 4): short tiles of long segments split every segment over G lanes.  A
+// thread owns 1024 / NTHREADS items (one per pass) and walks them TOGETHER, two edges per item per
+// iteration, so 2 * passes independent row loads are in flight per thread.  Each (row, g) sum is one
+// chain in ascending edge order; the G partial sums of a row are combined with a fixed shuffle tree:
+// bit-reproducible.  fp32 accumulation, one rounding to bf16.  Optionally also stores the rows to
+// out_rows[orow[r]] (global).
 __device__ __forceinline__ void seg_add8(float* s, const uint4& u) {
   float2 t;
   t = unpack_bf16x2(u.x); s[0] += t.x; s[1] += t.y;
@@ -194,89 +195,82 @@ template <int NTHREADS>
 __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ perm,
                                              const uint32_t* lo, const uint32_t* hi, const uint32_t* sbase,
                                              const float* sc, const int32_t* orow, uint8_t* X,
-                                             __nv_bfloat16* __restrict__ out_rows, int tid, int nrows = 128) {
-  constexpr int RB = 4;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, j = lane & 7;
+                                             __nv_bfloat16* __restrict__ out_rows, int tid, int nrows = 128,
+                                             long long* trace = nullptr) {
+  constexpr int P = 1024 / NTHREADS;  // items (passes) per thread
+  if (trace) trace[10] = clock64();
+  const int lg = nrows >= 128 ? 0 : (nrows >= 64 ? 1 : 2);  // log2(G); nrows < 32 still uses G = 4
+  const uint32_t G = 1u << lg;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-  for (int r0 = warp * RB; r0 < nrows; r0 += (NTHREADS / 32) * RB) {
-    float s0[RB][8], s1[RB][8];
-    uint32_t l[RB], h[RB];
-    const __nv_bfloat16* sb[RB];
-    long long ea[RB], eb[RB];
-    bool va[RB], vb[RB];
+  float acc[P][8];
+  uint32_t e[P], h[P];
+  const __nv_bfloat16* sb[P];
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = r0 + i;
-      l[i] = r < nrows ? lo[r] : 0xFFFFFFFFu;
-      h[i] = l[i] != 0xFFFFFFFFu ? hi[r] : 0u;
-      sb[i] = src + (l[i] != 0xFFFFFFFFu ? (static_cast<long long>(sbase[r]) << 3) : 0ll) + j * 8;
-      const uint32_t pa = l[i] + g, pb = pa + 4;
-      va[i] = l[i] != 0xFFFFFFFFu && pa < h[i];
-      vb[i] = l[i] != 0xFFFFFFFFu && pb < h[i];
-      ea[i] = va[i] ? (perm ? static_cast<long long>(perm[pa]) : static_cast<long long>(pa)) : 0ll;
-      eb[i] = vb[i] ? (perm ? static_cast<long long>(perm[pb]) : static_cast<long long>(pb)) : 0ll;
+  for (int p = 0; p < P; ++p) {
+    const int item = p * NTHREADS + tid;
+    const int j = item & 7, g = (item >> 3) & (G - 1), r = item >> (3 + lg);
+    const uint32_t l = r < nrows ? lo[r] : 0xFFFFFFFFu;
+    const bool valid = l != 0xFFFFFFFFu;
+    e[p] = valid ? l + g : 0u;
+    h[p] = valid ? hi[r] : 0u;
+    sb[p] = src + (valid ? (static_cast<long long>(sbase[r]) << 3) : 0ll) + j * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
+  }
+  if (trace) trace[11] = clock64();
+  int iters = 0;
+  while (true) {
+    ++iters;
+    long long i0[P], i1[P];
+    bool a0[P], a1[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      a0[p] = e[p] < h[p];
+      a1[p] = e[p] + G < h[p];
+      i0[p] = a0[p] ? (perm ? static_cast<long long>(perm[e[p]]) : static_cast<long long>(e[p])) : 0ll;
+      i1[p] = a1[p] ? (perm ? static_cast<long long>(perm[e[p] + G]) : static_cast<long long>(e[p] + G)) : 0ll;
     }
-    uint4 ua[RB], ub[RB];
+    uint4 u0[P], u1[P];
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      ua[i] = va[i] ? *reinterpret_cast<const uint4*>(sb[i] + ea[i] * 64) : zero4;
-      ub[i] = vb[i] ? *reinterpret_cast<const uint4*>(sb[i] + eb[i] * 64) : zero4;
+    for (int p = 0; p < P; ++p) {
+      u0[p] = a0[p] ? *reinterpret_cast<const uint4*>(sb[p] + i0[p] * 64) : zero4;
+      u1[p] = a1[p] ? *reinterpret_cast<const uint4*>(sb[p] + i1[p] * 64) : zero4;
     }
+    bool more = false;
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s0[i][q] = s1[i][q] = 0.f;
-      seg_add8(s0[i], ua[i]);
-      seg_add8(s1[i], ub[i]);
+    for (int p = 0; p < P; ++p) {
+      seg_add8(acc[p], u0[p]);
+      seg_add8(acc[p], u1[p]);
+      e[p] += 2 * G;
+      more |= e[p] < h[p];
     }
-    // long segments: 4 more edges per lane per iteration (positions +8, +12, +16, +20 ...)
+    if (!more) break;
+  }
+  if (trace) { trace[12] = clock64(); trace[15] = iters; }
+  __syncwarp();
+  if (trace) trace[13] = clock64();
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      if (l[i] == 0xFFFFFFFFu) continue;
-      uint32_t e = l[i] + g + 8;
-      for (; e + 12 < h[i]; e += 16) {
-        const long long e0 = perm ? perm[e] : e, e1 = perm ? perm[e + 4] : e + 4;
-        const long long e2 = perm ? perm[e + 8] : e + 8, e3 = perm ? perm[e + 12] : e + 12;
-        const uint4 u0 = *reinterpret_cast<const uint4*>(sb[i] + e0 * 64);
-        const uint4 u1 = *reinterpret_cast<const uint4*>(sb[i] + e1 * 64);
-        const uint4 u2 = *reinterpret_cast<const uint4*>(sb[i] + e2 * 64);
-        const uint4 u3 = *reinterpret_cast<const uint4*>(sb[i] + e3 * 64);
-        seg_add8(s0[i], u0);
-        seg_add8(s1[i], u1);
-        seg_add8(s0[i], u2);
-        seg_add8(s1[i], u3);
-      }
-      for (; e < h[i]; e += 8) {
-        const long long e0 = perm ? perm[e] : e;
-        seg_add8(s0[i], *reinterpret_cast<const uint4*>(sb[i] + e0 * 64));
-        if (e + 4 < h[i]) {
-          const long long e1 = perm ? perm[e + 4] : e + 4;
-          seg_add8(s1[i], *reinterpret_cast<const uint4*>(sb[i] + e1 * 64));
-        }
-      }
+  for (int p = 0; p < P; ++p) {
+    const int item = p * NTHREADS + tid;
+    const int j = item & 7, g = (item >> 3) & (G - 1), r = item >> (3 + lg);
+    const float scale = r < nrows ? sc[r] : 1.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = acc[p][q];
+      if (lg >= 1) v += __shfl_xor_sync(0xffffffffu, v, 8);
+      if (lg >= 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[p][q] = v * scale;
     }
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = r0 + i;
-      const float scale = r < nrows ? sc[r] : 1.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float v = s0[i][q] + s1[i][q];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        s0[i][q] = v * scale;
-      }
-      if (g == 0 && r < nrows) {
-        uint4 o;
-        o.x = pack_bf16x2(s0[i][0], s0[i][1]); o.y = pack_bf16x2(s0[i][2], s0[i][3]);
-        o.z = pack_bf16x2(s0[i][4], s0[i][5]); o.w = pack_bf16x2(s0[i][6], s0[i][7]);
-        *reinterpret_cast<uint4*>(X + sw128_offset(r, j)) = o;
-        if (out_rows && l[i] != 0xFFFFFFFFu)
-          *reinterpret_cast<uint4*>(out_rows + static_cast<long long>(orow[r]) * 64 + j * 8) = o;
-      }
+    if (g == 0 && r < nrows) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[p][0], acc[p][1]); o.y = pack_bf16x2(acc[p][2], acc[p][3]);
+      o.z = pack_bf16x2(acc[p][4], acc[p][5]); o.w = pack_bf16x2(acc[p][6], acc[p][7]);
+      *reinterpret_cast<uint4*>(X + sw128_offset(r, j)) = o;
+      if (out_rows && lo[r] != 0xFFFFFFFFu)
+        *reinterpret_cast<uint4*>(out_rows + static_cast<long long>(orow[r]) * 64 + j * 8) = o;
     }
   }
+  if (trace) trace[14] = clock64();
 }
 
 // ---- K-blocks of the layer-1 input ----------------------------------------------------------------

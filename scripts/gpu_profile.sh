@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r01}; shift
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control ${NCU_CACHE:-all} --profile-from-start off --csv \
   --log-file gpurun_out/launches_$TAG.csv python bench.py --profile-step ${BENCH_ARGS:-} \
   > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "ncu launches exit=$?"
