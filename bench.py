@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (NCCL prints its version there)
+
 import torch  # noqa: E402
 
 METRIC = "hilam_ar_rollout_train_samples_per_s"

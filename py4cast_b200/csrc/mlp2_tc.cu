@@ -318,6 +318,15 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
                     IDESC, j ? 1u : 0u);
       mma_commit(&S.mbar[1]);
     }
+    // residual / edge rows of this tile: fetched while GEMM 2 runs (consumed at the very end)
+    uint4 res_pre[CPT / 8];
+    if (OUT == HID && orow >= 0 && (residual || out2)) {
+      const __nv_bfloat16* rp =
+          out2 ? reinterpret_cast<const __nv_bfloat16*>(m.src[0].ptr) + (static_cast<long long>(S.row_off[p][0][row]) << 3) + col0
+               : residual + orow * HID + col0;
+#pragma unroll
+      for (int j = 0; j < CPT / 8; ++j) res_pre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+    }
     mbar_wait(&S.mbar[1], parity);
     tc_fence_after();
     P4C_TRACE(7);
@@ -357,10 +366,8 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
       }
       if (OUT == HID) {
         if (orow >= 0 && (out || out2)) {
-          const __nv_bfloat16* e_row =
-              out2 ? reinterpret_cast<const __nv_bfloat16*>(m.src[0].ptr) +
-                         (static_cast<long long>(S.row_off[p][0][row]) << 3) + col0
-                   : nullptr;
+          // out2 = src0 row + y (edge update); out = y (+ residual).  One of residual / out2 per
+          // call site (InteractionNet: edge MLP has out2, node MLP has residual).
 #pragma unroll
           for (int j = 0; j < CPT / 8; ++j) {
             float yy[8];
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
             const int c0 = col0 + j * 8;
             if (out2) {
               float e[8];
-              unpack8f(*reinterpret_cast<const uint4*>(e_row + j * 8), e);
+              unpack8f(res_pre[j], e);
 #pragma unroll
               for (int q = 0; q < 8; ++q) e[q] += yy[q];
               *reinterpret_cast<uint4*>(out2 + orow * HID + c0) = pack8f(e);
@@ -377,7 +384,8 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
             if (out) {
               if (residual) {
                 float e[8];
-                unpack8f(*reinterpret_cast<const uint4*>(residual + orow * HID + c0), e);
+                if (out2) unpack8f(*reinterpret_cast<const uint4*>(residual + orow * HID + c0), e);
+                else unpack8f(res_pre[j], e);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) yy[q] += e[q];
               }

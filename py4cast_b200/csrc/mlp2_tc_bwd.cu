@@ -76,6 +76,10 @@ struct BwdArgs {
   int ndx;         // K-blocks whose input gradient is produced (<= 2)
   int dx_blk[2];   // their block ids
   int zero_x;      // some block fetches fewer than 8 chunks per row: clear the tiles once
+  // where a row of dy_a lives: 0 = generic (index / scale looked up per tile), 1 = same gather
+  // index and batch stride as K-block `dy_blk` (its row offset is reused: no index round trip),
+  // 2 = identity rows laid out like the outputs (dy_a + orow * out_features)
+  int dy_mode, dy_blk;
 };
 
 __device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
@@ -243,24 +247,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     }
     // dy half-row -> packed bf16 registers (dy_a gathered and scaled, + dy_b)
     uint4 dyr[4];
-    {
-      long long ia = -1, bb = 0;
-      float sc = 1.f;
-      if (orow >= 0) {
-        bb = grow / m.rows;
+    const __nv_bfloat16* dy_row = dya;  // first element of this row of dy_a
+    float dy_sc = 1.f;
+    if (orow >= 0) {
+      if (args.dy_mode == 1) {
+        dy_row = dya + (static_cast<long long>(C.row_off[p][args.dy_blk][row]) << 3);
+      } else if (args.dy_mode == 2) {
+        dy_row = dya + orow * OUT;
+      } else {
+        const long long bb = grow / m.rows;
         const int rr = static_cast<int>(grow - bb * m.rows);
-        ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
-        if (g.dy_a_scale) sc = g.dy_a_scale[ia];
+        const long long ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
+        if (g.dy_a_scale) dy_sc = g.dy_a_scale[ia];
+        dy_row = dya + bb * g.dy_a_batch_stride + ia * OUT;
       }
+    }
+    {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c0 = col0 + j * 8;
         float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (orow >= 0) {
           if (OUT == HID) {
-            unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + c0), d);
+            unpack8(*reinterpret_cast<const uint4*>(dy_row + c0), d);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) d[q] *= sc;
+            for (int q = 0; q < 8; ++q) d[q] *= dy_sc;
             if (dyb) {
               float e[8];
               unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
             for (int q = 0; q < 8; ++q) {
               const int c = c0 + q;
               if (c < OUT) {
-                float v = __bfloat162float(dya[bb * g.dy_a_batch_stride + ia * OUT + c]) * sc;
+                float v = __bfloat162float(dy_row[c]) * dy_sc;
                 if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
                 d[q] = v;
               }
@@ -481,13 +492,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
             // residual / edge-update pass-through: d src0 += dy (dy_b only when dx0_add_dy == 1)
             float e[8];
             if (g.dx0_add_dy == 2) {
-              const long long bb = grow / m.rows;
-              const int rr = static_cast<int>(grow - bb * m.rows);
-              const long long ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
-              unpack8(*reinterpret_cast<const uint4*>(dya + bb * g.dy_a_batch_stride + ia * HID + c0), e);
-              const float sc = g.dy_a_scale ? g.dy_a_scale[ia] : 1.f;
+              unpack8(*reinterpret_cast<const uint4*>(dy_row + c0), e);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] = fmaf(e[q], sc, o[q]);
+              for (int q = 0; q < 8; ++q) o[q] = fmaf(e[q], dy_sc, o[q]);
             }
             if (dyb) {
               unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
@@ -609,6 +616,25 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
   a.ndx = tc_bwd_dx_blocks(m, g, a.kb, a.dx_blk);
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  a.dy_mode = 0;
+  a.dy_blk = 0;
+  const long long full = m->full_rows > 0 ? m->full_rows : m->rows;
+  if (!g->dy_a_scale) {
+    if (!g->dy_a_index && (m->batch == 1 || g->dy_a_batch_stride == full * m->out_features)) {
+      // identity rows; with full_rows the caller pre-offsets dy_a like the other output-like arrays
+      a.dy_mode = 2;
+    } else if (g->dy_a_index && m->out_features == P4C_HIDDEN) {
+      for (int k = 0; k < a.kb.nblk; ++k) {
+        const p4c_src_t& sk = m->src[a.kb.src[k]];
+        if (sk.index == g->dy_a_index && sk.ld == P4C_HIDDEN && a.kb.col0[k] == 0 &&
+            sk.batch_stride == g->dy_a_batch_stride) {
+          a.dy_mode = 1;
+          a.dy_blk = k;
+          break;
+        }
+      }
+    }
+  }
   const size_t smem = bwd_smem_bytes(a.kb.nblk, a.ndx) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
