@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--grid", default="512x640")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
+                    help="2: the two halves of the per-GPU batch run concurrently on two CUDA streams")
+    ap.add_argument("--cta-reserve", type=int, default=56)
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop after warm-up and exit "
@@ -68,6 +71,7 @@ def workload_config(args, world):
         "model_name": args.model, "grid": [H, W], "pred_steps": args.pred_steps,
         "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
         "strategy": args.strategy, "precision": args.precision, "parallelism": f"dp{world}",
+        "streams_per_gpu": args.streams,
         "l2": "per-step working set (several GB of activations) >> 126 MB L2: no flush needed",
     }
 
@@ -285,7 +289,7 @@ def gpu_arm(args):
         training_strategy=args.strategy, learning_rate=1e-3, min_learning_rate=3e-7, num_warmup_steps=1000,
         betas=(0.9, 0.95), precision=args.precision,
     ).to(dev)
-    trainer = DataParallelTrainer(lm, total_steps=100000)
+    trainer = DataParallelTrainer(lm, total_steps=100000, num_streams=args.streams, cta_reserve=args.cta_reserve)
     B, T = args.batch_per_gpu, args.pred_steps
     dev_batch = synthetic_batch(info, B, 2, T, seed=100 + rank, device=dev)
     host_batches = [synthetic_batch(info, B, 2, T, seed=200 + rank + 10 * i, pin=True) for i in range(2)]

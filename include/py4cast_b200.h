@@ -159,6 +159,12 @@ int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* stream);
  * allows (bf16 storage, 64-wide sources), 0 = CUDA-core fp32 FFMA everywhere.  The environment
  * variable P4C_ENGINE=simt sets the initial value to 0. */
 void p4c_set_engine(int tensor_cores);
+/* The persistent tensor-core kernels launch at most 2*148 - n CTAs (default n = 0: two per SM).
+ * With n > 0 some SMs keep a free CTA slot, so that small kernels of ANOTHER stream (the mesh
+ * levels of a second sample) run beside a large kernel instead of queueing behind it.  Changes the
+ * number of weight-gradient partial blocks: set it before the first backward call. */
+void p4c_set_cta_reserve(int n);
+int p4c_get_cta_reserve(void);
 /* developer aid: when set (16 x int64 device buffer), CTA 0 of the tensor-core forward kernel stores
  * the SM clock at the phases of its first tile (set-up, gather, GEMM 1, epilogue 1, ...). NULL = off. */
 void p4c_set_trace_buffer(void* device_buffer);

@@ -146,6 +146,8 @@ SYMBOLS = {
     "p4c_segment_sum": (_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _int, _int, _int, _vp]),
     "p4c_set_engine": (None, [_int]),
     "p4c_set_trace_buffer": (None, [_vp]),
+    "p4c_set_cta_reserve": (None, [_int]),
+    "p4c_get_cta_reserve": (_int, []),
     "p4c_get_engine": (_int, []),
     "p4c_mlp_forward": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "p4c_mlp_forward_aggregate": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),

@@ -45,6 +45,8 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
 bool tc_engine_enabled();
 
 constexpr int kNumSMs = 148;  // B200
+// persistent tensor-core kernels use at most 2 * kNumSMs - reserve CTAs (p4c_set_cta_reserve)
+int tc_max_ctas();
 constexpr int HIDDEN_W = P4C_HIDDEN;
 
 // ---- storage <-> fp32 conversion -------------------------------------------------

@@ -735,6 +735,12 @@ static int set_smem(size_t bytes, const char* name) {
 
 using namespace p4c;
 
+static int g_cta_reserve = 0;
+namespace p4c {
+int tc_max_ctas() { return 2 * kNumSMs - g_cta_reserve; }
+}  // namespace p4c
+extern "C" void p4c_set_cta_reserve(int n) { g_cta_reserve = n < 0 ? 0 : (n > 2 * kNumSMs - 16 ? 2 * kNumSMs - 16 : n); }
+extern "C" int p4c_get_cta_reserve(void) { return g_cta_reserve; }
 extern "C" void p4c_set_trace_buffer(void* device_buffer) { tc_set_trace(static_cast<long long*>(device_buffer)); }
 extern "C" void p4c_set_engine(int tensor_cores) { g_tc_enabled = tensor_cores ? 1 : 0; }
 extern "C" int p4c_get_engine(void) { return tc_engine_enabled() ? 1 : 0; }

@@ -519,7 +519,7 @@ int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   }
   const long long total = static_cast<long long>(m->rows) * m->batch;
   const long long ntiles = (total + a.tile_rows - 1) / a.tile_rows;
-  const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+  const int grid = static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
   const size_t smem = sizeof(FwdSmem) + 1024;
   bool has_seg = false;
   for (int s = 0; s < m->nsrc; ++s) has_seg |= m->src[s].seg_rowptr != nullptr;

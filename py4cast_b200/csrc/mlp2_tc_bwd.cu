@@ -603,7 +603,7 @@ bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g) {
 int tc_backward_grid(const p4c_mlp_t* m) {
   const long long total = static_cast<long long>(m->rows) * m->batch;
   const long long ntiles = (total + tc::TM - 1) / tc::TM;
-  return static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+  return static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
 }
 
 int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st) {

@@ -290,7 +290,7 @@ extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* ro
   a.accumulate = accumulate;
   a.tile_rows = tile_rows;
   const long long ntiles = (static_cast<long long>(num_seg) * batch + tile_rows - 1) / tile_rows;
-  const int grid = static_cast<int>(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+  const int grid = static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
   const size_t smem = sizeof(SegLinSmem) + 1024;
   seg_linear_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   P4C_CHECK_LAUNCH("seg_linear");

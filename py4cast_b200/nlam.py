@@ -336,12 +336,33 @@ class BaseGraphModel(ModelABC, nn.Module):
         packer.pack()
 
     def begin_rollout(self, dtype: Optional[torch.dtype] = None) -> None:
+        """Re-entrant: an outer begin_rollout (the trainer, around several concurrent micro-batch
+        rollouts) keeps one cache / one weight packing for all inner ones."""
+        depth = getattr(self, "_rollout_depth", 0)
+        self._rollout_depth = depth + 1
+        if depth > 0:
+            return
         self._rollout_cache = {}
         if dtype is None or dtype == torch.bfloat16:
             self.pack_weights()
 
     def end_rollout(self) -> None:
-        self._rollout_cache = None
+        self._rollout_depth = max(0, getattr(self, "_rollout_depth", 1) - 1)
+        if self._rollout_depth == 0:
+            self._rollout_cache = None
+
+    def precompute_static(self, dt: torch.dtype) -> None:
+        """Fills the rollout cache with every batch-independent embedding (on the current stream),
+        so that rollouts running on other streams only read them."""
+        if getattr(self, "_rollout_cache", None) is None:
+            raise RuntimeError("precompute_static() needs begin_rollout() first")
+        self._static_embedding("g2m", self.g2m_embedder, "g2m_features", dt)
+        self._static_embedding("m2g", self.m2g_embedder, "m2g_features", dt)
+        self.embedd_mesh_nodes(dt)
+        self._static_mesh_embeddings(dt)
+
+    def _static_mesh_embeddings(self, dt: torch.dtype) -> None:
+        pass
 
     def _static_embedding(self, key: str, mlp: "FusedMLP", feats_name: str, dt: torch.dtype) -> torch.Tensor:
         cache = getattr(self, "_rollout_cache", None)
@@ -401,6 +422,9 @@ class GraphLAM(BaseGraphModel):
     def embedd_mesh_nodes(self, dt):
         return self._static_embedding("mesh", self.mesh_embedder, "mesh_static_features", dt)
 
+    def _static_mesh_embeddings(self, dt):
+        self._static_embedding("m2m", self.m2m_embedder, "m2m_features", dt)
+
     def process_step(self, mesh_rep, dt):
         edge_rep = self._static_embedding("m2m", self.m2m_embedder, "m2m_features", dt)
         for net in self.processor:
@@ -438,13 +462,19 @@ class BaseHiGraphModel(BaseGraphModel):
     def embedd_mesh_nodes(self, dt):
         return self._static_embedding("mesh0", self.mesh_embedders[0], "mesh_static_0", dt)
 
-    def process_step(self, mesh_rep, dt):
+    def _static_mesh_embeddings(self, dt):
         L = self.num_levels
         emb = self._static_embedding
-        rep = [mesh_rep] + [emb(f"mesh{l}", self.mesh_embedders[l], f"mesh_static_{l}", dt) for l in range(1, L)]
+        higher = [emb(f"mesh{l}", self.mesh_embedders[l], f"mesh_static_{l}", dt) for l in range(1, L)]
         same = [emb(f"same{l}", self.mesh_same_embedders[l], f"m2m_features_{l}", dt) for l in range(L)]
         up = [emb(f"up{l}", self.mesh_up_embedders[l], f"up_features_{l}", dt) for l in range(L - 1)]
         down = [emb(f"down{l}", self.mesh_down_embedders[l], f"down_features_{l}", dt) for l in range(L - 1)]
+        return higher, same, up, down
+
+    def process_step(self, mesh_rep, dt):
+        L = self.num_levels
+        higher, same, up, down = self._static_mesh_embeddings(dt)
+        rep = [mesh_rep] + higher
         for l in range(1, L):  # init sweep, upward
             rep[l], up[l - 1] = self.mesh_init_gnns[l - 1](rep[l - 1], rep[l], up[l - 1])
         rep, same, up, down = self.hi_processor_step(rep, same, up, down)

@@ -24,12 +24,13 @@ _WGRAD_WS: dict = {}
 _WGRAD_WS_FLOATS = 2 * 148 * (192 * 64 + 64 * 64 + 4 * 64)
 
 
-def _wgrad_workspace(device: torch.device, floats: int) -> torch.Tensor:
-    ws = _WGRAD_WS.get(device)
+def _wgrad_workspace(key, floats: int) -> torch.Tensor:
+    """Shared scratch for in-call weight-gradient reductions, per (device, execution branch)."""
+    ws = _WGRAD_WS.get(key)
     need = max(floats, _WGRAD_WS_FLOATS)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.float32, device=device)
-        _WGRAD_WS[device] = ws
+        ws = torch.empty(need, dtype=torch.float32, device=key[0])
+        _WGRAD_WS[key] = ws
     return ws
 
 
@@ -61,9 +62,10 @@ class MlpMeta:
         self.k1 = int(sum(self.widths))
         self.out_features = int(out_features)
         self.image: Optional[torch.Tensor] = None  # uint8 [PACK_BYTES] view, valid after pack()
-        self.partials: Optional[torch.Tensor] = None
-        self.partials_blocks = 0
-        self.partials_used = False
+        # deferred weight-gradient partials, one set per execution branch (stream): branch -> tensor
+        self.partials: dict = {}
+        self.partials_blocks: dict = {}
+        self.partials_used: dict = {}
 
     def image_ptr(self, dtype: torch.dtype) -> Optional[int]:
         if self.image is None or dtype != torch.bfloat16:
@@ -123,53 +125,69 @@ class WeightPacker:
         check(_lib.load().p4c_pack_weights(ptr(self._table), len(self.metas), stream()), "p4c_pack_weights")
 
 
-_DEFERRED: List[MlpMeta] = []
+_DEFERRED: List[Tuple[MlpMeta, int]] = []  # (meta, branch) touched since the last flush
 _DEFERRED_TABLES: dict = {}
+_BRANCH = 0
 
 
-def _deferred_mode(meta: Optional[MlpMeta], nblocks: int, partial_floats: int, device) -> int:
+def set_branch(i: int) -> None:
+    """Execution branch (one per concurrently running micro-batch / CUDA stream) of the autograd
+    nodes created from now on: each branch accumulates weight-gradient partials in its own buffers."""
+    global _BRANCH
+    _BRANCH = int(i)
+
+
+def current_branch() -> int:
+    return _BRANCH
+
+
+def _deferred_mode(meta: Optional[MlpMeta], nblocks: int, partial_floats: int, device, branch: int = 0) -> int:
     """0 = reduce in the call; 1 / 2 = overwrite / accumulate this MLP's own partials (deferred)."""
     if meta is None or meta.sinks() is None:
         return 0
-    if meta.partials is None:
+    if branch not in meta.partials:
         if torch.cuda.is_current_stream_capturing():
             return 0
-        meta.partials = torch.empty(partial_floats, dtype=torch.float32, device=device)
-        meta.partials_blocks = nblocks
-    if meta.partials_blocks != nblocks or meta.partials.numel() < partial_floats:
+        meta.partials[branch] = torch.empty(partial_floats, dtype=torch.float32, device=device)
+        meta.partials_blocks[branch] = nblocks
+    if meta.partials_blocks[branch] != nblocks or meta.partials[branch].numel() < partial_floats:
         return 0  # same weights used with another problem size: keep that call self-contained
-    if not meta.partials_used:
-        meta.partials_used = True
-        _DEFERRED.append(meta)
+    if not meta.partials_used.get(branch, False):
+        meta.partials_used[branch] = True
+        _DEFERRED.append((meta, branch))
         return 1
     return 2
 
 
 def flush_wgrads() -> None:
     """Reduces the deferred weight-gradient partials of every MLP touched since the last flush
-    into the parameters' gradient sinks: ONE launch (the trainer calls it after backward)."""
+    into the parameters' gradient sinks: ONE launch per execution branch, branches in ascending
+    order (fixed summation order), issued on the current stream (the trainer calls it after
+    backward, when every branch has been joined)."""
     if not _DEFERRED:
         return
-    key = tuple(id(m) for m in _DEFERRED)
-    ent = _DEFERRED_TABLES.get(key)
-    if ent is None or ent[1] != tuple(m.partials.data_ptr() for m in _DEFERRED):
-        if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("flush_wgrads: run one eager step before CUDA-graph capture")
-        entries = []
-        for m in _DEFERRED:
-            e = WGrad()
-            e.partials = ptr(m.partials)
-            sinks = m.sinks()
-            for name, g in zip(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta"), sinks):
-                setattr(e, name, ptr(g))
-            e.nblocks, e.k1, e.out_features = m.partials_blocks, m.k1, m.out_features
-            entries.append(e)
-        dev = _DEFERRED[0].partials.device
-        ent = (_table_to_device(entries, dev), tuple(m.partials.data_ptr() for m in _DEFERRED), list(_DEFERRED))
-        _DEFERRED_TABLES[key] = ent
-    check(_lib.load().p4c_wgrad_reduce_batched(ptr(ent[0]), len(_DEFERRED), stream()), "p4c_wgrad_reduce_batched")
-    for m in _DEFERRED:
-        m.partials_used = False
+    for branch in sorted({b for _, b in _DEFERRED}):
+        metas = [m for m, b in _DEFERRED if b == branch]
+        sig = tuple((m.partials[branch].data_ptr(),) + tuple(g.data_ptr() for g in m.sinks() if g is not None)
+                    for m in metas)
+        key = (branch, tuple(id(m) for m in metas))
+        ent = _DEFERRED_TABLES.get(key)
+        if ent is None or ent[1] != sig:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("flush_wgrads: run one eager step before CUDA-graph capture")
+            entries = []
+            for m in metas:
+                e = WGrad()
+                e.partials = ptr(m.partials[branch])
+                for name, g in zip(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta"), m.sinks()):
+                    setattr(e, name, ptr(g))
+                e.nblocks, e.k1, e.out_features = m.partials_blocks[branch], m.k1, m.out_features
+                entries.append(e)
+            ent = (_table_to_device(entries, metas[0].partials[branch].device), sig, metas)
+            _DEFERRED_TABLES[key] = ent
+        check(_lib.load().p4c_wgrad_reduce_batched(ptr(ent[0]), len(metas), stream()), "p4c_wgrad_reduce_batched")
+        for m in metas:
+            m.partials_used[branch] = False
     _DEFERRED.clear()
 
 
@@ -461,7 +479,7 @@ def _grad_target(p: Optional[torch.Tensor], needed: bool):
 
 
 def _bind_wgrads(lib, desc: Mlp, g: MlpBwd, ws: Sequence[Optional[torch.Tensor]], needed: Sequence[bool],
-                 meta: Optional[MlpMeta], device) -> List[Optional[torch.Tensor]]:
+                 meta: Optional[MlpMeta], device, branch: int = 0) -> List[Optional[torch.Tensor]]:
     """Weight-gradient outputs of one backward call: deferred partials when the MLP has gradient
     sinks (trainer), otherwise the shared workspace + in-call reduction.  Returns the 6 values to
     hand back to autograd."""
@@ -469,16 +487,16 @@ def _bind_wgrads(lib, desc: Mlp, g: MlpBwd, ws: Sequence[Optional[torch.Tensor]]
     rets: List[Optional[torch.Tensor]] = [None] * 6
     mode = 0
     if desc.dtype == _lib.P4C_BF16 and all(needed[j] or ws[j] is None for j in range(6)):
-        mode = _deferred_mode(meta, lib.p4c_mlp_wgrad_blocks(C.byref(desc)), nfl, device)
+        mode = _deferred_mode(meta, lib.p4c_mlp_wgrad_blocks(C.byref(desc)), nfl, device, branch)
     g.partials_mode = mode
     if mode != 0:
-        g.wgrad_partials, g.wgrad_partials_floats = ptr(meta.partials), meta.partials.numel()
+        g.wgrad_partials, g.wgrad_partials_floats = ptr(meta.partials[branch]), meta.partials[branch].numel()
         return rets
     for j, slot in enumerate(("g_w1", "g_b1", "g_w2", "g_b2", "g_gamma", "g_beta")):
         buf, ret = _grad_target(ws[j], needed[j])
         setattr(g, slot, ptr(buf))
         rets[j] = ret
-    wsp = _wgrad_workspace(device, nfl)
+    wsp = _wgrad_workspace((device, branch), nfl)
     g.wgrad_partials, g.wgrad_partials_floats = ptr(wsp), wsp.numel()
     return rets
 
@@ -544,6 +562,7 @@ class _MLPFn(torch.autograd.Function):
         ctx.save_for_backward(x, w1, b1, w2, b2, gamma, beta, h1, stats)
         ctx.residual = residual
         ctx.meta = meta
+        ctx.branch = _BRANCH
         return out
 
     @staticmethod
@@ -571,7 +590,7 @@ class _MLPFn(torch.autograd.Function):
             g.dx0_add_dy = 2 if ctx.residual else 0
         elif ctx.residual:
             raise RuntimeError("residual MLP with a non-differentiable input is not supported")
-        rets = _bind_wgrads(lib, desc, g, ws, ctx.needs_input_grad[2:8], ctx.meta, x.device)
+        rets = _bind_wgrads(lib, desc, g, ws, ctx.needs_input_grad[2:8], ctx.meta, x.device, ctx.branch)
         check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward")
         return (None, dx, *rets, None)
 
@@ -711,6 +730,7 @@ class _InteractionNetFn(torch.autograd.Function):
         ctx.rec_shared = rec.dim() == 2
         ctx.same_nodes = same_nodes and rec.dim() == 3
         ctx.metas, ctx.tc = metas, tc
+        ctx.branch = _BRANCH
         ctx.save_for_backward(send, rec_b, edge, aggr, h1_e, st_e, h1_n, st_n, *weights)
         if update_edges:
             return rec_out, edge_out
@@ -763,7 +783,8 @@ class _InteractionNetFn(torch.autograd.Function):
             g.dx[1], g.dx_ld[1], g.dx_accumulate[1] = _off(d_aggr, o), HIDDEN, 0
             g.dx0_add_dy = 2
             base = 6 * (n_eg + ci)
-            wgrads[base: base + 6] = _bind_wgrads(lib, desc, g, w, wneed[base: base + 6], metas[n_eg + ci], dev)
+            wgrads[base: base + 6] = _bind_wgrads(lib, desc, g, w, wneed[base: base + 6], metas[n_eg + ci], dev,
+                                                  ctx.branch)
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(node)")
 
         # ---- edge MLP backward
@@ -800,7 +821,7 @@ class _InteractionNetFn(torch.autograd.Function):
                 g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_edge, o), HIDDEN, 0
                 g.dx0_add_dy = 1 if d_edge_out is not None else 0
             wgrads[6 * gidx: 6 * gidx + 6] = _bind_wgrads(lib, desc, g, w, wneed[6 * gidx: 6 * gidx + 6],
-                                                          metas[gidx], dev)
+                                                          metas[gidx], dev, ctx.branch)
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(edge)")
             # sender / receiver gradients by linearity: (segment-sum of dh1) x W1 slice
             if tc:

@@ -156,3 +156,44 @@ def test_launch_counter_counts_our_kernels(cuda, tmp_path):
     _lib.reset_launch_count()
     tr.train_step(b)
     assert _lib.launch_count() > 100
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_two_stream_half_batches_match_single_stream(cuda, tmp_path, use_graph):
+    """num_streams=2 (the two halves of the batch as concurrent rollouts on two CUDA streams, own
+    weight-gradient partial buffers per branch) gives the loss and the gradients of the plain step."""
+    from py4cast_b200 import _lib
+    from py4cast_b200.datasets import synthetic_batch
+    from py4cast_b200.trainer import DataParallelTrainer
+
+    res = []
+    try:
+        for streams in (1, 2):
+            lm, info = _lm(tmp_path, precision="bf16-true")
+            lm = lm.to(cuda)
+            tr = DataParallelTrainer(lm, total_steps=10, num_streams=streams, cta_reserve=56)
+            batch = synthetic_batch(info, 2, 2, 3, seed=5, device=cuda)
+            if use_graph:
+                w_init = tr.flat.flat.clone()
+                tr.capture(batch, warmup=1)  # the warm-up step updates the weights: restore them
+                tr.flat.flat.copy_(w_init)
+                w0 = tr.flat.flat.clone()
+                tr._graph.replay()
+                loss = tr._static_loss.clone()
+            else:
+                w0 = tr.flat.flat.clone()
+                loss = tr._forward_backward(_fresh_batch(batch)).clone()
+            torch.cuda.synchronize()
+            res.append((loss.float(), tr.flat.grad.clone(), w0))
+    finally:
+        _lib.load().p4c_set_cta_reserve(0)
+    if use_graph:
+        assert torch.equal(res[0][2], res[1][2])
+    assert_close(res[1][0], res[0][0], 2e-3, "loss, 2 streams vs 1")
+    assert_close(res[1][1], res[0][1], 2e-2, "flat gradient, 2 streams vs 1")
+
+
+def _fresh_batch(batch):
+    from py4cast_b200.trainer import _fresh
+
+    return _fresh(batch)
