@@ -139,6 +139,85 @@ ar_step_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x) {
   }
 }
 
+// Tiled variant of ar_concat / ar_step (the one used whenever the x tile fits shared memory):
+// one CTA = AR_TN consecutive nodes of one sample.  Every input array is contiguous over a node
+// range, so each is read with fully coalesced loads into an fp32 staging tile laid out exactly like
+// the x rows ([older states | new state | statics | forcing | zero padding]); the new state is
+// computed into its slot (and written to the prediction slab), then the tile is converted and
+// streamed out as one contiguous block.  No 64-bit divisions, no strided stores.
+constexpr int AR_TN = 64;
+
+template <typename T>
+__device__ __forceinline__ void ar_store_pair(T* p, float a, float b);
+template <>
+__device__ __forceinline__ void ar_store_pair<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <>
+__device__ __forceinline__ void ar_store_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256)
+ar_tile_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x, int has_update) {
+  extern __shared__ float S[];  // [AR_TN][ld]
+  const int F = a.f_state, T = a.num_prev, Fs = a.f_static, Ff = a.f_forcing;
+  const int f_in = T * F + Fs + Ff;
+  const int ld = a.x_ld > 0 ? a.x_ld : f_in;
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * AR_TN;
+  const int nn = min(AR_TN, a.nodes - n0);
+  const int tid = threadIdx.x;
+  const float invF = 1.0f / (float)F;
+  // older states (and, without update, the newest one too)
+  const int ncopy = has_update ? T - 1 : T;
+  for (int t = 0; t < ncopy; ++t) {
+    const float* src = a.prev[t] + (long long)b * a.prev_batch_stride[t] + (long long)n0 * F;
+    for (int i = tid; i < nn * F; i += 256) {
+      const int n = (int)(((float)i + 0.5f) * invF), f = i - n * F;
+      S[n * ld + t * F + f] = src[i];
+    }
+  }
+  if (Fs > 0) {
+    const float* src = a.stat + (long long)b * a.stat_batch_stride + (long long)n0 * Fs;
+    const float inv = 1.0f / (float)Fs;
+    for (int i = tid; i < nn * Fs; i += 256) {
+      const int n = (int)(((float)i + 0.5f) * inv), f = i - n * Fs;
+      S[n * ld + T * F + f] = src[i];
+    }
+  }
+  if (Ff > 0) {
+    const float* src = a.forcing + (long long)b * a.forcing_batch_stride + (long long)n0 * Ff;
+    const float inv = 1.0f / (float)Ff;
+    for (int i = tid; i < nn * Ff; i += 256) {
+      const int n = (int)(((float)i + 0.5f) * inv), f = i - n * Ff;
+      S[n * ld + T * F + Fs + f] = src[i];
+    }
+  }
+  const int npad = ld - f_in;
+  for (int i = tid; i < nn * npad; i += 256) {
+    const int n = i / npad, j = i - n * npad;
+    S[n * ld + f_in + j] = 0.f;
+  }
+  if (has_update) {
+    for (int i = tid; i < nn * F; i += 256) {
+      const int n = (int)(((float)i + 0.5f) * invF), f = i - n * F;
+      const float v = ar_new_state<TY>(s, b, n0 + n, f);
+      s.new_state[(long long)b * s.new_state_bs + (long long)n0 * F + i] = v;
+      S[n * ld + (T - 1) * F + f] = v;
+    }
+  }
+  __syncthreads();
+  TX* dst = x + ((long long)b * a.nodes + n0) * ld;
+  const int total = nn * ld;
+  if ((ld & 1) == 0) {
+    for (int i = tid; i < total / 2; i += 256) ar_store_pair<TX>(dst + 2 * i, S[2 * i], S[2 * i + 1]);
+  } else {
+    for (int i = tid; i < total; i += 256) dst[i] = from_f32<TX>(S[i]);
+  }
+}
+
 struct ArBwd {
   const float* g_new;
   long long g_new_bs;
@@ -395,12 +474,21 @@ extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* st
   const int f_in = a->num_prev * a->f_state + a->f_static + a->f_forcing;
   const long long total = (long long)a->batch * a->nodes * (a->x_ld > 0 ? a->x_ld : f_in);
   cudaStream_t st = (cudaStream_t)stream;
+  P4C_REQUIRE(x_dtype == P4C_F32 || x_dtype == P4C_BF16, "ar_concat: bad dtype %d", x_dtype);
+  const int ld = a->x_ld > 0 ? a->x_ld : f_in;
+  const size_t tile_smem = (size_t)AR_TN * ld * sizeof(float);
+  if (tile_smem <= 48 * 1024 && a->batch <= 65535) {
+    const dim3 grid((a->nodes + AR_TN - 1) / AR_TN, a->batch);
+    ArStep none{};
+    if (x_dtype == P4C_F32) ar_tile_kernel<float, float><<<grid, 256, tile_smem, st>>>(none, *a, (float*)x, 0);
+    else ar_tile_kernel<float, __nv_bfloat16><<<grid, 256, tile_smem, st>>>(none, *a, (__nv_bfloat16*)x, 0);
+    P4C_CHECK_LAUNCH("ar_concat(tile)");
+    return P4C_OK;
+  }
   if (x_dtype == P4C_F32)
     ar_concat_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(*a, (float*)x);
-  else if (x_dtype == P4C_BF16)
-    ar_concat_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(*a, (__nv_bfloat16*)x);
   else
-    P4C_REQUIRE(false, "ar_concat: bad dtype %d", x_dtype);
+    ar_concat_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(*a, (__nv_bfloat16*)x);
   P4C_CHECK_LAUNCH("ar_concat");
   return P4C_OK;
 }
@@ -436,6 +524,21 @@ extern "C" int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev
   const int f_in = next->num_prev * f_state + next->f_static + next->f_forcing;
   const long long total = (long long)batch * nodes * (next->x_ld > 0 ? next->x_ld : f_in);
   const int grid = grid_for(total, 256);
+  const int ld = next->x_ld > 0 ? next->x_ld : f_in;
+  const size_t tile_smem = (size_t)AR_TN * ld * sizeof(float);
+  if (tile_smem <= 48 * 1024 && batch <= 65535) {
+    const dim3 tg((nodes + AR_TN - 1) / AR_TN, batch);
+    if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
+      ar_tile_kernel<float, float><<<tg, 256, tile_smem, st>>>(s, *next, (float*)x_next, 1);
+    else if (y_dtype == P4C_F32 && x_dtype == P4C_BF16)
+      ar_tile_kernel<float, __nv_bfloat16><<<tg, 256, tile_smem, st>>>(s, *next, (__nv_bfloat16*)x_next, 1);
+    else if (y_dtype == P4C_BF16 && x_dtype == P4C_F32)
+      ar_tile_kernel<__nv_bfloat16, float><<<tg, 256, tile_smem, st>>>(s, *next, (float*)x_next, 1);
+    else
+      ar_tile_kernel<__nv_bfloat16, __nv_bfloat16><<<tg, 256, tile_smem, st>>>(s, *next, (__nv_bfloat16*)x_next, 1);
+    P4C_CHECK_LAUNCH("ar_step(tile)");
+    return P4C_OK;
+  }
   if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
     ar_step_kernel<float, float><<<grid, 256, 0, st>>>(s, *next, (float*)x_next);
   else if (y_dtype == P4C_F32 && x_dtype == P4C_BF16)
