@@ -348,9 +348,12 @@ def gpu_arm(args):
     h2d = sum(getattr(host_batches[0], n).tensor.numel() * 4 for n in ("inputs", "forcing", "outputs"))
 
     def step_e2e(i):
+        # every step: H2D of one pinned host batch (the NEXT step's, on the copy stream, overlapping
+        # this step's kernels - the input pipelining the reference gets from its pinned DataLoader)
+        # and a D2H read of this step's loss
         hb = host_batches[i % 2]
         if use_graph:
-            loss = trainer.replay(hb)
+            loss = trainer.replay(hb, prefetch=host_batches[(i + 1) % 2])
         else:
             gb = type(hb)(inputs=_to(hb.inputs, dev), forcing=_to(hb.forcing, dev), outputs=_to(hb.outputs, dev))
             loss = trainer.train_step(gb)

@@ -135,6 +135,9 @@ class DataParallelTrainer:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_batch: Optional[ItemBatch] = None
         self._static_loss: Optional[torch.Tensor] = None
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._staging: Optional[ItemBatch] = None
+        self._staged_for: Optional[ItemBatch] = None
 
     def sync_gradients(self) -> float:
         """ONE all-reduce (sum) of the flat gradient buffer; returns the scale that turns the sum
@@ -226,12 +229,46 @@ class DataParallelTrainer:
             src = getattr(batch, name).tensor
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
-    def replay(self, batch: Optional[ItemBatch] = None) -> torch.Tensor:
-        """One optimiser step: graph replay (fwd+bwd) + all-reduce + AdamW."""
+    def prefetch(self, batch: ItemBatch) -> None:
+        """Starts the host -> device copy of the NEXT step's batch on a dedicated copy stream into
+        a staging buffer, so that it overlaps the current step's kernels (what the reference gets
+        from DataLoader(pin_memory=True) + non_blocking transfers, lightning.py:572-579).  The
+        following `replay(batch)` with the same object moves it into the captured input buffers
+        with a device-to-device copy (~0.2 ms for the Titan batch instead of ~10 ms over PCIe)."""
+        if self._static_batch is None:
+            raise RuntimeError("call capture() first")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = _clone_batch(self._static_batch)
+            self._staged_ready = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._staging_free)  # the previous staged batch was consumed
+            for name in ("inputs", "forcing", "outputs"):
+                dst = getattr(self._staging, name).tensor
+                src = getattr(batch, name).tensor
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._staged_for = batch
+
+    def replay(self, batch: Optional[ItemBatch] = None, prefetch: Optional[ItemBatch] = None) -> torch.Tensor:
+        """One optimiser step: graph replay (fwd+bwd) + all-reduce + AdamW.  `batch` (host or
+        device) becomes the step's input — for free when it was announced with `prefetch()`;
+        `prefetch` announces the batch of the following step."""
         if self._graph is None:
             raise RuntimeError("call capture() first")
         if batch is not None:
-            self.load_inputs(batch)
+            if self._staged_for is batch:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(self._staged_ready)
+                self.load_inputs(self._staging)
+                self._staging_free.record(cur)
+                self._staged_for = None
+            else:
+                self.load_inputs(batch)
+        if prefetch is not None:
+            self.prefetch(prefetch)
         self._graph.replay()
         self.opt.step(grad_scale=self.sync_gradients())
         return self._static_loss

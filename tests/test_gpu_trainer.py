@@ -144,6 +144,32 @@ def test_cuda_graph_replay_equals_eager(cuda, tmp_path):
     assert eager.opt.host_state() == graph.opt.host_state()
 
 
+def test_prefetched_host_batches_equal_direct_loads(cuda, tmp_path):
+    """replay(batch, prefetch=next): the staged H2D copy on the copy stream + device-to-device move
+    feeds the captured step exactly the same bytes as a direct load of the pinned host batch."""
+    from py4cast_b200.datasets import synthetic_batch
+    from py4cast_b200.trainer import DataParallelTrainer
+
+    lm_a, info = _lm(tmp_path, precision="bf16-true")
+    lm_b, _ = _lm(tmp_path, precision="bf16-true")
+    lm_b.load_state_dict(lm_a.state_dict())
+    lm_a, lm_b = lm_a.to(cuda), lm_b.to(cuda)
+    host = [synthetic_batch(info, 2, 2, 3, seed=10 + s, pin=True) for s in range(4)]
+    direct = DataParallelTrainer(lm_a, total_steps=50)
+    staged = DataParallelTrainer(lm_b, total_steps=50)
+    example = synthetic_batch(info, 2, 2, 3, seed=0, device=cuda)
+    direct.capture(example, warmup=1)
+    staged.capture(example, warmup=1)
+    staged.prefetch(host[0])
+    for i, hb in enumerate(host):
+        ld = direct.replay(hb).clone()
+        ls = staged.replay(hb, prefetch=host[i + 1] if i + 1 < len(host) else None).clone()
+        assert torch.equal(ld, ls)
+    # a batch that was not announced is loaded directly
+    assert torch.equal(direct.replay(host[1]).clone(), staged.replay(host[1]).clone())
+    assert torch.equal(direct.flat.flat, staged.flat.flat)
+
+
 def test_launch_counter_counts_our_kernels(cuda, tmp_path):
     from py4cast_b200 import _lib
     from py4cast_b200.datasets import synthetic_batch
