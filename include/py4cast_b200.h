@@ -165,6 +165,15 @@ void p4c_set_engine(int tensor_cores);
  * number of weight-gradient partial blocks: set it before the first backward call. */
 void p4c_set_cta_reserve(int n);
 int p4c_get_cta_reserve(void);
+/* The tensor-core forward has two kernels: a warp-specialised, software-pipelined one (one CTA per
+ * SM: producer / MMA / epilogue warps, 3-stage gather ring) for calls of at least `n` 128-row tiles
+ * and the monolithic two-CTAs-per-SM kernel below that (and for segment-sum sources, out_features
+ * != 64).  Default n = 4 * 148 (environment variable P4C_WS_MIN_TILES); n <= 0 restores the default,
+ * a huge n disables the pipelined kernel.  Same results up to fp32 summation order. */
+void p4c_set_ws_min_tiles(int64_t n);
+int64_t p4c_get_ws_min_tiles(void);
+/* launches of the pipelined forward kernel so far (tests assert that it really ran) */
+int64_t p4c_ws_launch_count(void);
 /* developer aid: when set (16 x int64 device buffer), CTA 0 of the tensor-core forward kernel stores
  * the SM clock at the phases of its first tile (set-up, gather, GEMM 1, epilogue 1, ...). NULL = off. */
 void p4c_set_trace_buffer(void* device_buffer);

@@ -35,6 +35,11 @@ bool tc_forward_supported(const p4c_mlp_t* m);
 int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
                            float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st);
 void tc_set_trace(long long* buf);
+// warp-specialised pipelined forward for the large calls (mlp2_ws.cu)
+bool ws_forward_supported(const p4c_mlp_t* m, const void* residual, const void* out2, const void* aggr_out,
+                          int agg_group);
+int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
+                           float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st);
 // weight-gradient partial reduction of one MLP (pack.cu)
 int launch_wgrad_reduce_single(const p4c_wgrad_t* e, cudaStream_t st);
 bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g);

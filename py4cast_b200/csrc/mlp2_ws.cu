@@ -1,0 +1,580 @@
+// Warp-specialised, software-pipelined FORWARD of the fused 2-layer MLP for the large edge / grid
+// problems (bf16 storage): the same operator as mlp2_tc_fwd_kernel (mlp2_tc.cu), re-organised so
+// that gather, tensor-core work and the two epilogues of DIFFERENT tiles overlap inside one CTA.
+//
+// One persistent CTA per SM, 13 warps:
+//   warps 8-11  producer   cp.async gather of the up-to-three 64-column K-blocks of a 128-row tile into
+//                          a 3-stage ring of 128-byte-swizzled smem tiles; row offsets are computed
+//                          one per lane and handed out with shuffles so that every cp.async
+//                          instruction fetches four complete 128-byte rows (coalesced requests);
+//                          the gather indices of the next tile are loaded one iteration ahead.
+//   warp  12    MMA        one lane issues tcgen05.mma: G1(t) = X(t) W1^T -> D1[t&1],
+//                          G2(t-1) = A2(t-1) W2^T -> D2[(t-1)&1]; tcgen05.commit signals the
+//                          mbarriers (X stage free, D1 / D2 ready).
+//   warps 0-3 / 4-7        two epilogue groups, tile t belongs to group t & 1, thread = tile row
+//                          (TMEM lane), 64 columns per thread:
+//        epilogue 1: D1 + b1 -> bf16 h1, staged in the A2 tile; second pass (lanes re-mapped to
+//                    16-byte chunks of four consecutive rows): coalesced store of h1 (saved
+//                    activation) and SiLU in place -> A2 operand of G2.
+//        epilogue 2: D2 + b2, LayerNorm (thread-local statistics, no exchange), then
+//                    - fused aggregation over groups of consecutive rows (shuffle butterfly), or
+//                    - messages / residual output / edge update staged through the (free) A2 tile
+//                      and stored with coalesced 16-byte chunks.  The residual / edge row is the
+//                      tile's own K-block 0, read from shared memory instead of HBM.
+//   While group A waits for G2 of its tile, group B runs the epilogues of the next one; the
+//   producer runs two tiles ahead.  No thread spins hot: waits back off with nanosleep.
+//
+// TMEM: 256 columns (D1[2], D2[2], 64 fp32 columns each).  Shared memory: 3 x 48 KB X ring,
+// 2 x 16 KB A2, 32 KB weights (bf16 image of p4c_pack_weights), barriers  = ~209 KB.
+//
+// Reference semantics: mfai/neural-lam `make_mlp` (Linear, SiLU, Linear, LayerNorm) on
+// cat(edge, send[sender], rec[receiver]) and InteractionNet.aggregate.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace p4c {
+namespace tc {
+
+constexpr int WS_TM = 128;
+constexpr int WS_HID = P4C_HIDDEN;
+constexpr int WS_XBLK = WS_TM * 128;
+constexpr int WS_WBLK = WS_HID * 128;
+constexpr int WS_NS = 3;   // X ring stages
+constexpr int WS_LAG = 2;  // tiles the producer keeps in flight before it signals the oldest
+constexpr int WS_EPI_WARPS = 8, WS_PROD_WARPS = 4;
+constexpr int WS_THREADS = (WS_EPI_WARPS + WS_PROD_WARPS + 1) * 32;
+constexpr uint32_t WS_TMEM_COLS = 256;
+constexpr uint32_t kWsNoRow = 0xFFFFFFFFu;
+
+struct WsSmem {
+  uint8_t X[WS_NS][P4C_MAX_SRC][WS_XBLK];
+  uint8_t A2[2][WS_XBLK];
+  uint8_t W1[P4C_MAX_SRC][WS_WBLK];
+  uint8_t W2[WS_WBLK];
+  float vec[4][WS_HID];  // b1, b2, gamma, beta
+  uint64_t x_full[WS_NS], x_empty[WS_NS];
+  uint64_t d1_full[2], a2_full[2], d2_full[2], d2_empty[2];
+  uint32_t tmem_base;
+};
+
+struct WsArgs {
+  p4c_mlp_t m;
+  KBlocks kb;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out2;
+  __nv_bfloat16* save_h1;
+  float* save_stats;
+  __nv_bfloat16* aggr_out;
+  int agg_group;
+  float agg_scale;
+  int residual_x0;  // out = y + (row of K-block 0)
+  int zero_x;
+  unsigned long long div_magic;  // ceil(2^64 / rows): sample = umul64hi(global row, magic)
+  uint32_t total_rows, ntiles, full_rows;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" : : "r"(smem_u32(bar)) : "memory");
+}
+// wait with back-off (role warps wait for microseconds; a hot spin would steal issue slots from
+// the epilogue warps).  Traps after ~seconds instead of hanging the GPU on a protocol error.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(32);
+    if (spin > (1u << 25)) __trap();
+  }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 ws_pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+// bf16x2 -> two floats with integer ops (exact)
+__device__ __forceinline__ void ws_unpack2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xFFFF0000u);
+}
+__device__ __forceinline__ void ws_unpack8(const uint4& u, float* f) {
+  ws_unpack2(u.x, f[0], f[1]); ws_unpack2(u.y, f[2], f[3]);
+  ws_unpack2(u.z, f[4], f[5]); ws_unpack2(u.w, f[6], f[7]);
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid_constant__ WsArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const p4c_mlp_t& m = a.m;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = a.kb.nblk;
+  const uint32_t total_rows = a.total_rows;
+  const uint32_t rows = static_cast<uint32_t>(m.rows);
+  const bool need_x0 = a.residual_x0 || a.out2 != nullptr;
+
+  // ---- set-up: weight image, barriers, TMEM
+  if (a.zero_x) {
+    uint4* xz = reinterpret_cast<uint4*>(S.X);
+    for (int i = tid; i < WS_NS * P4C_MAX_SRC * WS_XBLK / 16; i += WS_THREADS) xz[i] = make_uint4(0, 0, 0, 0);
+  }
+  {
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(m.packed);
+    for (int i = tid; i < nblk * (WS_WBLK / 16); i += WS_THREADS)
+      cp_async16(smem_u32(S.W1) + i * 16, img + PK_W1 + i * 16, 16u);
+    for (int i = tid; i < WS_WBLK / 16; i += WS_THREADS) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
+    if (tid < 64) cp_async16(smem_u32(S.vec) + tid * 16, img + PK_VEC + tid * 16, 16u);
+    cp_async_commit();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < WS_NS; ++i) {
+      mbar_init(&S.x_full[i], WS_PROD_WARPS);
+      mbar_init(&S.x_empty[i], need_x0 ? 1 + 4 : 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&S.d1_full[i], 1);
+      mbar_init(&S.a2_full[i], 4);
+      mbar_init(&S.d2_full[i], 1);
+      mbar_init(&S.d2_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == WS_EPI_WARPS + WS_PROD_WARPS) tmem_alloc(&S.tmem_base, WS_TMEM_COLS);
+  cp_async_wait<0>();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const uint32_t ntl = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  pdl_launch_dependents();
+
+  if (warp >= WS_EPI_WARPS && warp < WS_EPI_WARPS + WS_PROD_WARPS) {
+    // =============================== producer ===============================
+    const int pw = warp - WS_EPI_WARPS;
+    const int sub = lane >> 3, j = lane & 7;  // lane -> (row within a group of 4, 16-byte chunk)
+    int32_t idx_next[P4C_MAX_SRC];
+    uint32_t b_next = 0, rr_next = 0;
+    bool valid_next = false;
+    auto load_indices = [&](uint32_t t) {  // gather indices of tile t (graph constants)
+      const uint32_t g = (blockIdx.x + t * gridDim.x) * WS_TM + pw * 32 + lane;
+      valid_next = t < ntl && g < total_rows;
+      b_next = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(g), a.div_magic));
+      rr_next = g - b_next * rows;
+#pragma unroll
+      for (int k = 0; k < P4C_MAX_SRC; ++k) {
+        idx_next[k] = static_cast<int32_t>(rr_next);
+        if (k < nblk && valid_next) {
+          const int32_t* ix = m.src[a.kb.src[k]].index;
+          if (ix) idx_next[k] = ix[rr_next];
+        }
+      }
+    };
+    load_indices(0);
+    pdl_wait();  // everything above reads only constants of the step (weights image, graph indices)
+    for (uint32_t t = 0; t < ntl; ++t) {
+      const uint32_t s = t % WS_NS, n = t / WS_NS;
+      uint32_t off[P4C_MAX_SRC];
+#pragma unroll
+      for (int k = 0; k < P4C_MAX_SRC; ++k) {
+        off[k] = kWsNoRow;
+        if (k < nblk && valid_next) {
+          const p4c_src_t& src = m.src[a.kb.src[k]];
+          off[k] = static_cast<uint32_t>(
+              (static_cast<long long>(b_next) * src.batch_stride + static_cast<long long>(idx_next[k]) * src.ld +
+               a.kb.col0[k]) >> 3);
+        }
+      }
+      load_indices(t + 1);
+      if (n > 0) mbar_wait_backoff(&S.x_empty[s], (n - 1) & 1u);
+#pragma unroll
+      for (int k = 0; k < P4C_MAX_SRC; ++k) {
+        if (k < nblk) {
+          const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[a.kb.src[k]].ptr);
+          const uint32_t xs = smem_u32(S.X[s][k]);
+          const bool fetch = j < a.kb.nchunks[k];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + sub;
+            const uint32_t o = __shfl_sync(0xffffffffu, off[k], r);
+            if (fetch) {
+              const bool ok = o != kWsNoRow;
+              cp_async16(xs + sw128_offset(pw * 32 + r, j), ok ? base + (static_cast<size_t>(o) << 3) + j * 8 : base,
+                         ok ? 16u : 0u);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      if (t >= WS_LAG) {
+        cp_async_wait<WS_LAG>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.x_full[(t - WS_LAG) % WS_NS]);
+      }
+    }
+    static_assert(WS_LAG == 2, "drain below is written for a lag of two tiles");
+    if (ntl >= 2) {
+      cp_async_wait<1>();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.x_full[(ntl - 2) % WS_NS]);
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.x_full[(ntl - 1) % WS_NS]);
+  } else if (warp == WS_EPI_WARPS + WS_PROD_WARPS) {
+    // ================================= MMA ==================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc_bf16(WS_TM, WS_HID, 0, 0);
+      for (uint32_t t = 0; t <= ntl; ++t) {
+        if (t < ntl) {
+          const uint32_t s = t % WS_NS, n = t / WS_NS, buf = t & 1u;
+          mbar_wait_backoff(&S.x_full[s], n & 1u);
+          tc_fence_after();
+          for (int k = 0; k < nblk; ++k) {
+            const uint32_t xa = smem_u32(S.X[s][k]), wa = smem_u32(S.W1[k]);
+            const int nk = (a.kb.kvalid[k] + 15) >> 4;
+            for (int q = 0; q < nk; ++q)
+              mma_bf16_ss(tmem + buf * WS_HID, make_desc_sw128(xa + q * 32, 16, 1024),
+                          make_desc_sw128(wa + q * 32, 16, 1024), IDESC, (k | q) ? 1u : 0u);
+          }
+          mma_commit(&S.x_empty[s]);
+          mma_commit(&S.d1_full[buf]);
+        }
+        if (t >= 1) {
+          const uint32_t u = t - 1, buf = u & 1u, nn = u >> 1;
+          mbar_wait_backoff(&S.a2_full[buf], nn & 1u);
+          if (nn > 0) mbar_wait_backoff(&S.d2_empty[buf], (nn - 1) & 1u);
+          tc_fence_after();
+          const uint32_t aa = smem_u32(S.A2[buf]), wa = smem_u32(S.W2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            mma_bf16_ss(tmem + 2 * WS_HID + buf * WS_HID, make_desc_sw128(aa + q * 32, 16, 1024),
+                        make_desc_sw128(wa + q * 32, 16, 1024), IDESC, q ? 1u : 0u);
+          mma_commit(&S.d2_full[buf]);
+        }
+      }
+    }
+  } else {
+    // =============================== epilogues ==============================
+    const int grp = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int sub = lane >> 3, j = lane & 7;
+    const uint32_t full = a.full_rows;
+    const uint32_t a2 = smem_u32(S.A2[grp]);
+    const uint32_t tm_d1 = tmem + (static_cast<uint32_t>(quad * 32) << 16) + grp * WS_HID;
+    const uint32_t tm_d2 = tm_d1 + 2 * WS_HID;
+    __nv_bfloat16* const save_h1 = a.save_h1;
+    __nv_bfloat16* const out = a.out;
+    __nv_bfloat16* const out2 = a.out2;
+    pdl_wait();
+    for (uint32_t t = grp; t < ntl; t += 2) {
+      const uint32_t s = t % WS_NS, nn = t >> 1;
+      const uint32_t grow = (blockIdx.x + t * gridDim.x) * WS_TM + row;
+      int32_t orow = -1;  // row in the output-like arrays
+      if (grow < total_rows) {
+        const uint32_t b = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(grow), a.div_magic));
+        orow = static_cast<int32_t>(b * full + (grow - b * rows));
+      }
+      mbar_wait_backoff(&S.d1_full[grp], nn & 1u);
+      tc_fence_after();
+      // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
+      uint4 res[8];
+      if (need_x0) {
+        const uint32_t x0 = smem_u32(S.X[s][0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) res[c] = lds128(x0 + sw128_offset(row, c));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.x_empty[s]);
+      }
+      // ---- epilogue 1, pass 1: h1 = D1 + b1 -> bf16 -> A2 (own row)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(tm_d1 + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 ba = *reinterpret_cast<const float4*>(&S.vec[0][half * 32 + c * 8]);
+          const float4 bb = *reinterpret_cast<const float4*>(&S.vec[0][half * 32 + c * 8 + 4]);
+          float h[8];
+          h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
+          h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
+          sts128(a2 + sw128_offset(row, half * 4 + c), ws_pack8(h));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      // ---- pass 2: coalesced h1 store, SiLU in place (lane -> chunk j of row 4 i + sub of this warp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + sub;
+        const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
+        const uint32_t addr = a2 + sw128_offset(quad * 32 + r, j);
+        const uint4 hb = lds128(addr);
+        if (save_h1 && orr >= 0) *reinterpret_cast<uint4*>(save_h1 + static_cast<long long>(orr) * WS_HID + j * 8) = hb;
+        float h[8];
+        ws_unpack8(hb, h);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+        sts128(addr, ws_pack8(h));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.a2_full[grp]);
+
+      // ---- epilogue 2
+      mbar_wait_backoff(&S.d2_full[grp], nn & 1u);
+      tc_fence_after();
+      float y[64];
+      {
+        float v0[32], v1[32];
+        tmem_ld32(tm_d2, v0);
+        tmem_ld32(tm_d2 + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          y[q] = v0[q];
+          y[32 + q] = v1[q];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.d2_empty[grp]);  // D2 is in registers: G2 of tile t + 2 may overwrite it
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 bv = *reinterpret_cast<const float4*>(&S.vec[1][c * 4]);
+        y[c * 4 + 0] += bv.x; y[c * 4 + 1] += bv.y; y[c * 4 + 2] += bv.z; y[c * 4 + 3] += bv.w;
+      }
+      if (m.layer_norm) {
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 64; ++q) {
+          ps[q & 3] += y[q];
+          pq[q & 3] = fmaf(y[q], y[q], pq[q & 3]);
+        }
+        const float sx = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        const float sq = (pq[0] + pq[1]) + (pq[2] + pq[3]);
+        const float mean = sx * (1.0f / WS_HID);
+        const float var = fmaxf(sq * (1.0f / WS_HID) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + m.ln_eps);
+        const float nm = -mean * rstd;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 gv = *reinterpret_cast<const float4*>(&S.vec[2][c * 4]);
+          const float4 bv = *reinterpret_cast<const float4*>(&S.vec[3][c * 4]);
+          y[c * 4 + 0] = fmaf(fmaf(y[c * 4 + 0], rstd, nm), gv.x, bv.x);
+          y[c * 4 + 1] = fmaf(fmaf(y[c * 4 + 1], rstd, nm), gv.y, bv.y);
+          y[c * 4 + 2] = fmaf(fmaf(y[c * 4 + 2], rstd, nm), gv.z, bv.z);
+          y[c * 4 + 3] = fmaf(fmaf(y[c * 4 + 3], rstd, nm), gv.w, bv.w);
+        }
+        if (a.save_stats && orow >= 0)
+          *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
+      }
+      // ---- outputs staged through the A2 tile (free: G2 of this tile is complete)
+      if (out2) {  // edge update: src0 row + y
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float e[8];
+          ws_unpack8(res[c], e);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) e[q] += y[c * 8 + q];
+          sts128(a2 + sw128_offset(row, c), ws_pack8(e));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + sub;
+          const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
+          const uint4 u = lds128(a2 + sw128_offset(quad * 32 + r, j));
+          if (orr >= 0) *reinterpret_cast<uint4*>(out2 + static_cast<long long>(orr) * WS_HID + j * 8) = u;
+        }
+        __syncwarp();
+      }
+      if (out) {  // messages, or y + residual
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float e[8];
+          if (a.residual_x0) {
+            ws_unpack8(res[c], e);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) e[q] += y[c * 8 + q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) e[q] = y[c * 8 + q];
+          }
+          sts128(a2 + sw128_offset(row, c), ws_pack8(e));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + sub;
+          const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
+          const uint4 u = lds128(a2 + sw128_offset(quad * 32 + r, j));
+          if (orr >= 0) *reinterpret_cast<uint4*>(out + static_cast<long long>(orr) * WS_HID + j * 8) = u;
+        }
+        __syncwarp();
+      }
+      if (a.aggr_out) {
+        // sum of the messages of `agg_group` consecutive rows (= lanes): transposing butterfly, at
+        // every step a lane hands one half of its columns to its partner and adds the partner's
+        // other half (fp32, fixed order; invalid rows add zero)
+        const int gsz = a.agg_group;
+        if (orow < 0) {
+#pragma unroll
+          for (int q = 0; q < 64; ++q) y[q] = 0.f;
+        }
+        int cbase = 0;
+#define P4C_WS_AGG_STEP(OFF, N)                                              \
+        if (gsz > OFF) {                                                     \
+          const bool up = (lane & OFF) != 0;                                 \
+          _Pragma("unroll") for (int i = 0; i < (N) / 2; ++i) {              \
+            const float send = up ? y[i] : y[i + (N) / 2];                   \
+            const float keep = up ? y[i + (N) / 2] : y[i];                   \
+            y[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);           \
+          }                                                                  \
+          if (up) cbase += (N) / 2;                                          \
+        }
+        P4C_WS_AGG_STEP(1, 64)
+        P4C_WS_AGG_STEP(2, 32)
+        P4C_WS_AGG_STEP(4, 16)
+        P4C_WS_AGG_STEP(8, 8)
+        P4C_WS_AGG_STEP(16, 4)
+#undef P4C_WS_AGG_STEP
+        if (orow >= 0) {
+          const int ncol = 64 / gsz;
+          __nv_bfloat16* dst = a.aggr_out + static_cast<long long>(orow / gsz) * WS_HID + cbase;
+          const float sc = a.agg_scale;
+          if (ncol >= 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c < ncol / 8) {
+                float e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = y[c * 8 + q] * sc;
+                *reinterpret_cast<uint4*>(dst + c * 8) = ws_pack8(e);
+              }
+            }
+          } else if (ncol == 4) {
+            uint2 o;
+            o.x = pack_bf16x2(y[0] * sc, y[1] * sc);
+            o.y = pack_bf16x2(y[2] * sc, y[3] * sc);
+            *reinterpret_cast<uint2*>(dst) = o;
+          } else {
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[0] * sc, y[1] * sc);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_EPI_WARPS + WS_PROD_WARPS) tmem_dealloc(tmem, WS_TMEM_COLS);
+}
+
+}  // namespace tc
+
+bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb);
+
+static long long g_ws_min_tiles = -1;
+static long long g_ws_launches = 0;
+static long long ws_min_tiles() {
+  if (g_ws_min_tiles < 0) {
+    const char* e = getenv("P4C_WS_MIN_TILES");
+    g_ws_min_tiles = (e && atoll(e) > 0) ? atoll(e) : 4ll * kNumSMs;
+  }
+  return g_ws_min_tiles;
+}
+
+// The warp-specialised kernel covers the large calls; everything else stays on mlp2_tc_fwd_kernel.
+bool ws_forward_supported(const p4c_mlp_t* m, const void* residual, const void* out2, const void* aggr_out,
+                          int agg_group) {
+  if (!m->packed || m->out_features != P4C_HIDDEN) return false;
+  if (m->tile_rows != 0 && m->tile_rows != 128) return false;
+  for (int s = 0; s < m->nsrc; ++s)
+    if (m->src[s].seg_rowptr) return false;
+  const long long full = m->full_rows > 0 ? m->full_rows : m->rows;
+  const long long total = static_cast<long long>(m->rows) * m->batch;
+  if (total >= (1ll << 31) - 256 * 1024 || full * m->batch >= (1ll << 31)) return false;
+  if ((total + 127) / 128 < ws_min_tiles()) return false;
+  if (residual) {
+    const p4c_src_t& s0 = m->src[0];
+    if (residual != s0.ptr || s0.index || s0.ld != P4C_HIDDEN || s0.width != P4C_HIDDEN) return false;
+    if (m->batch > 1 && s0.batch_stride != full * P4C_HIDDEN) return false;
+  }
+  if (aggr_out && (agg_group < 1 || agg_group > 32 || (agg_group & (agg_group - 1)))) return false;
+  return true;
+}
+
+int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
+                           float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st) {
+  using namespace tc;
+  WsArgs a;
+  a.m = *m;
+  tc_kblocks(m, &a.kb);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out2 = static_cast<__nv_bfloat16*>(out2);
+  a.save_h1 = static_cast<__nv_bfloat16*>(save_h1);
+  a.save_stats = save_stats;
+  a.aggr_out = static_cast<__nv_bfloat16*>(aggr_out);
+  a.agg_group = aggr_out ? agg_group : 1;
+  a.agg_scale = agg_scale;
+  a.residual_x0 = residual != nullptr;
+  a.zero_x = 0;
+  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  const unsigned long long rows = static_cast<unsigned long long>(m->rows);
+  a.div_magic = rows == 1 ? ~0ull : (~0ull / rows) + 1ull;  // ceil(2^64 / rows) for rows >= 2
+  const long long total = static_cast<long long>(m->rows) * m->batch;
+  a.total_rows = static_cast<uint32_t>(total);
+  a.ntiles = static_cast<uint32_t>((total + WS_TM - 1) / WS_TM);
+  a.full_rows = static_cast<uint32_t>(m->full_rows > 0 ? m->full_rows : m->rows);
+  int max_ctas = tc_max_ctas() / 2;
+  if (max_ctas < 1) max_ctas = 1;
+  const int grid = static_cast<int>(a.ntiles < static_cast<uint32_t>(max_ctas) ? a.ntiles : max_ctas);
+  const size_t smem = sizeof(WsSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("mlp_forward(ws): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return P4C_ECUDA;
+    }
+    configured = true;
+  }
+  mlp2_ws_fwd_kernel<<<grid, WS_THREADS, smem, st>>>(a);
+  P4C_CHECK_LAUNCH("mlp_forward(ws)");
+  ++g_ws_launches;
+  return P4C_OK;
+}
+
+}  // namespace p4c
+
+extern "C" void p4c_set_ws_min_tiles(int64_t n) { p4c::g_ws_min_tiles = n > 0 ? n : -1; }
+extern "C" int64_t p4c_get_ws_min_tiles(void) { return p4c::ws_min_tiles(); }
+extern "C" int64_t p4c_ws_launch_count(void) { return p4c::g_ws_launches; }
