@@ -49,6 +49,36 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
 // wherever the shape allows (bf16 storage, 64-wide sources)
 bool tc_engine_enabled();
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The tensor-core kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// kernel N+1 may start once every CTA of kernel N has executed griddepcontrol.launch_dependents
+// (placed after N's own set-up: TMEM allocated, barriers initialised), run ITS set-up (weight image
+// -> shared memory, TMEM allocation, graph-index loads: constants of the step) and then blocks in
+// griddepcontrol.wait until N has completed and its writes are visible.  Launch gaps and set-up
+// latency of the ~1200 launches of a HiLAM step overlap the previous kernel's tail.
+// P4C_PDL=0 disables the attribute (the device instructions are then no-ops).
+bool pdl_enabled();
+// the next PDL-capable launch must serialise fully (called after kernels whose output is read
+// BEFORE griddepcontrol.wait, i.e. p4c_pack_weights)
+void pdl_block_next();
+bool pdl_take_attr();  // true: launch with the attribute
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_take_attr() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kNumSMs = 148;  // B200
 // persistent tensor-core kernels use at most 2 * kNumSMs - reserve CTAs (p4c_set_cta_reserve)
 int tc_max_ctas();

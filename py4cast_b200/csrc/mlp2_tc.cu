@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     const int it = 0;
     P4C_TRACE(1);
   }
+  pdl_launch_dependents();
+  if (tile < ntiles) row_info(a, tile * TR, total_rows, S, 0, tid);  // graph constants only
+  pdl_wait();  // the previous kernel's outputs (this kernel's sources) are complete and visible
   if (tile < ntiles) {
-    row_info(a, tile * TR, total_rows, S, 0, tid);
     __syncthreads();
     {
       const int it = 0;
@@ -538,9 +540,9 @@ int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, 
     configured = true;
   }
   if (has_seg)
-    mlp2_tc_fwd_kernel<256, true><<<grid, 256, smem, st>>>(a);
+    launch_pdl(mlp2_tc_fwd_kernel<256, true>, dim3(grid), dim3(256), smem, st, a);
   else
-    mlp2_tc_fwd_kernel<512, false><<<grid, 512, smem, st>>>(a);
+    launch_pdl(mlp2_tc_fwd_kernel<512, false>, dim3(grid), dim3(512), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_forward(tc)");
   return P4C_OK;
 }

@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   float vacc[4] = {0.f, 0.f, 0.f, 0.f};
 
   long long tile = blockIdx.x;
+  pdl_launch_dependents();
+  if (tile < ntiles) bwd_row_info(m, kb, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);  // constants
+  pdl_wait();  // the previous kernel's outputs are complete and visible
   if (tile < ntiles) {
-    bwd_row_info(m, kb, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);
     __syncthreads();
     bwd_gather(m, kb, C.row_off[0], Xs, tid);
   }
@@ -645,7 +647,7 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
     }
     configured = smem;
   }
-  mlp2_tc_bwd_kernel<<<tc_backward_grid(m), NTHREADS, smem, st>>>(a);
+  launch_pdl(mlp2_tc_bwd_kernel, dim3(tc_backward_grid(m)), dim3(NTHREADS), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_backward(tc)");
   return P4C_OK;
 }

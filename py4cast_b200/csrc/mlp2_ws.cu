@@ -2,26 +2,28 @@
 // problems (bf16 storage): the same operator as mlp2_tc_fwd_kernel (mlp2_tc.cu), re-organised so
 // that gather, tensor-core work and the two epilogues of DIFFERENT tiles overlap inside one CTA.
 //
-// One persistent CTA per SM, 13 warps:
-//   warps 8-11  producer   cp.async gather of the up-to-three 64-column K-blocks of a 128-row tile into
+// One persistent CTA per SM, 21 warps:
+//   warps 16-19 producer   cp.async gather of the up-to-three 64-column K-blocks of a 128-row tile into
 //                          a 3-stage ring of 128-byte-swizzled smem tiles; row offsets are computed
 //                          one per lane and handed out with shuffles so that every cp.async
 //                          instruction fetches four complete 128-byte rows (coalesced requests);
 //                          the gather indices of the next tile are loaded one iteration ahead.
-//   warp  12    MMA        one lane issues tcgen05.mma: G1(t) = X(t) W1^T -> D1[t&1],
+//   warp  20    MMA        one lane issues tcgen05.mma: G1(t) = X(t) W1^T -> D1[t&1],
 //                          G2(t-1) = A2(t-1) W2^T -> D2[(t-1)&1]; tcgen05.commit signals the
 //                          mbarriers (X stage free, D1 / D2 ready).
-//   warps 0-3 / 4-7        two epilogue groups, tile t belongs to group t & 1, thread = tile row
-//                          (TMEM lane), 64 columns per thread:
+//   warps 0-7 / 8-15       two epilogue groups, tile t belongs to group t & 1; inside a group warp w
+//                          owns TMEM lane quadrant w % 4 (rows) and column half (w / 4) % 2: thread =
+//                          (tile row, 32 columns):
 //        epilogue 1: D1 + b1 -> bf16 h1, staged in the A2 tile; second pass (lanes re-mapped to
-//                    16-byte chunks of four consecutive rows): coalesced store of h1 (saved
+//                    16-byte chunks of eight consecutive rows): coalesced store of h1 (saved
 //                    activation) and SiLU in place -> A2 operand of G2.
-//        epilogue 2: D2 + b2, LayerNorm (thread-local statistics, no exchange), then
+//        epilogue 2: D2 + b2, LayerNorm (partial sums exchanged between the two threads of a row
+//                    through shared memory, one 64-thread named barrier), then
 //                    - fused aggregation over groups of consecutive rows (shuffle butterfly), or
 //                    - messages / residual output / edge update staged through the (free) A2 tile
 //                      and stored with coalesced 16-byte chunks.  The residual / edge row is the
 //                      tile's own K-block 0, read from shared memory instead of HBM.
-//   While group A waits for G2 of its tile, group B runs the epilogues of the next one; the
+//   While one group waits for G2 of its tile, the other runs the epilogues of the next one; the
 //   producer runs two tiles ahead.  No thread spins hot: waits back off with nanosleep.
 //
 // TMEM: 256 columns (D1[2], D2[2], 64 fp32 columns each).  Shared memory: 3 x 48 KB X ring,
@@ -41,7 +43,7 @@ constexpr int WS_XBLK = WS_TM * 128;
 constexpr int WS_WBLK = WS_HID * 128;
 constexpr int WS_NS = 3;   // X ring stages
 constexpr int WS_LAG = 2;  // tiles the producer keeps in flight before it signals the oldest
-constexpr int WS_EPI_WARPS = 8, WS_PROD_WARPS = 4;
+constexpr int WS_EPI_WARPS = 16, WS_PROD_WARPS = 4;
 constexpr int WS_THREADS = (WS_EPI_WARPS + WS_PROD_WARPS + 1) * 32;
 constexpr uint32_t WS_TMEM_COLS = 256;
 constexpr uint32_t kWsNoRow = 0xFFFFFFFFu;
@@ -52,6 +54,7 @@ struct WsSmem {
   uint8_t W1[P4C_MAX_SRC][WS_WBLK];
   uint8_t W2[WS_WBLK];
   float vec[4][WS_HID];  // b1, b2, gamma, beta
+  float2 ln_part[2][2][WS_TM];  // [group][column half][row]: LayerNorm partial (sum, sum of squares)
   uint64_t x_full[WS_NS], x_empty[WS_NS];
   uint64_t d1_full[2], a2_full[2], d2_full[2], d2_empty[2];
   uint32_t tmem_base;
@@ -78,6 +81,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // wait with back-off (role warps wait for microseconds; a hot spin would steal issue slots from
 // the epilogue warps).  Traps after ~seconds instead of hanging the GPU on a protocol error.
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0;; ++spin) {
@@ -92,8 +96,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    __nanosleep(32);
-    if (spin > (1u << 25)) __trap();
+    __nanosleep(SLEEP_NS);
+    if (spin > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -104,8 +108,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ws_pack8(const float* f) {
   uint4 u;
@@ -149,13 +151,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
   if (tid == 0) {
     for (int i = 0; i < WS_NS; ++i) {
       mbar_init(&S.x_full[i], WS_PROD_WARPS);
-      mbar_init(&S.x_empty[i], need_x0 ? 1 + 4 : 1);
+      mbar_init(&S.x_empty[i], need_x0 ? 1 + 8 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&S.d1_full[i], 1);
-      mbar_init(&S.a2_full[i], 4);
+      mbar_init(&S.a2_full[i], 8);
       mbar_init(&S.d2_full[i], 1);
-      mbar_init(&S.d2_empty[i], 4);
+      mbar_init(&S.d2_empty[i], 8);
     }
     mbar_fence_init();
   }
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         }
       }
       load_indices(t + 1);
-      if (n > 0) mbar_wait_backoff(&S.x_empty[s], (n - 1) & 1u);
+      if (n > 0) mbar_wait_backoff<96>(&S.x_empty[s], (n - 1) & 1u);
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
         if (k < nblk) {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       for (uint32_t t = 0; t <= ntl; ++t) {
         if (t < ntl) {
           const uint32_t s = t % WS_NS, n = t / WS_NS, buf = t & 1u;
-          mbar_wait_backoff(&S.x_full[s], n & 1u);
+          mbar_wait_backoff<20>(&S.x_full[s], n & 1u);
           tc_fence_after();
           for (int k = 0; k < nblk; ++k) {
             const uint32_t xa = smem_u32(S.X[s][k]), wa = smem_u32(S.W1[k]);
@@ -267,8 +269,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         }
         if (t >= 1) {
           const uint32_t u = t - 1, buf = u & 1u, nn = u >> 1;
-          mbar_wait_backoff(&S.a2_full[buf], nn & 1u);
-          if (nn > 0) mbar_wait_backoff(&S.d2_empty[buf], (nn - 1) & 1u);
+          mbar_wait_backoff<20>(&S.a2_full[buf], nn & 1u);
+          if (nn > 0) mbar_wait_backoff<20>(&S.d2_empty[buf], (nn - 1) & 1u);
           tc_fence_after();
           const uint32_t aa = smem_u32(S.A2[buf]), wa = smem_u32(S.W2);
 #pragma unroll
@@ -281,16 +283,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     }
   } else {
     // =============================== epilogues ==============================
-    const int grp = warp >> 2, quad = warp & 3;
+    // warp w < 16: group = w / 8 (tile parity), TMEM lane quadrant = w % 4, column half = (w / 4) % 2
+    const int grp = warp >> 3, quad = warp & 3, hsel = (warp >> 2) & 1;
     const int row = quad * 32 + lane;
-    const int sub = lane >> 3, j = lane & 7;
+    const int sub = lane >> 2, j = hsel * 4 + (lane & 3);  // pass-2 mapping: row 8 i + sub, chunk j
+    const int col0 = hsel * 32;
     const uint32_t full = a.full_rows;
     const uint32_t a2 = smem_u32(S.A2[grp]);
-    const uint32_t tm_d1 = tmem + (static_cast<uint32_t>(quad * 32) << 16) + grp * WS_HID;
+    const uint32_t tm_d1 = tmem + (static_cast<uint32_t>(quad * 32) << 16) + grp * WS_HID + col0;
     const uint32_t tm_d2 = tm_d1 + 2 * WS_HID;
+    const int pair_bar = 1 + grp * 4 + quad;  // named barrier of the two warps that share these rows
     __nv_bfloat16* const save_h1 = a.save_h1;
     __nv_bfloat16* const out = a.out;
     __nv_bfloat16* const out2 = a.out2;
+    const float* const b1 = S.vec[0] + col0;
+    const float* const b2 = S.vec[1] + col0;
+    const float* const gamma = S.vec[2] + col0;
+    const float* const beta = S.vec[3] + col0;
     pdl_wait();
     for (uint32_t t = grp; t < ntl; t += 2) {
       const uint32_t s = t % WS_NS, nn = t >> 1;
@@ -300,39 +309,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const uint32_t b = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(grow), a.div_magic));
         orow = static_cast<int32_t>(b * full + (grow - b * rows));
       }
-      mbar_wait_backoff(&S.d1_full[grp], nn & 1u);
+      mbar_wait_backoff<64>(&S.d1_full[grp], nn & 1u);
       tc_fence_after();
       // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
-      uint4 res[8];
+      uint4 res[4];
       if (need_x0) {
         const uint32_t x0 = smem_u32(S.X[s][0]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) res[c] = lds128(x0 + sw128_offset(row, c));
+        for (int c = 0; c < 4; ++c) res[c] = lds128(x0 + sw128_offset(row, hsel * 4 + c));
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.x_empty[s]);
       }
-      // ---- epilogue 1, pass 1: h1 = D1 + b1 -> bf16 -> A2 (own row)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      // ---- epilogue 1, pass 1: h1 = D1 + b1 -> bf16 -> A2 (own row, own column half)
+      {
         float v[32];
-        tmem_ld32(tm_d1 + half * 32, v);
+        tmem_ld32(tm_d1, v);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 ba = *reinterpret_cast<const float4*>(&S.vec[0][half * 32 + c * 8]);
-          const float4 bb = *reinterpret_cast<const float4*>(&S.vec[0][half * 32 + c * 8 + 4]);
+          const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           float h[8];
           h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
           h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
-          sts128(a2 + sw128_offset(row, half * 4 + c), ws_pack8(h));
+          sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
         }
       }
       tc_fence_before();
       __syncwarp();
-      // ---- pass 2: coalesced h1 store, SiLU in place (lane -> chunk j of row 4 i + sub of this warp)
+      // ---- pass 2: coalesced h1 store, SiLU in place (lane -> chunk j of row 8 i + sub of this warp)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = 4 * i + sub;
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + sub;
         const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
         const uint32_t addr = a2 + sw128_offset(quad * 32 + r, j);
         const uint4 hb = lds128(addr);
@@ -348,67 +356,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       if (lane == 0) mbar_arrive(&S.a2_full[grp]);
 
       // ---- epilogue 2
-      mbar_wait_backoff(&S.d2_full[grp], nn & 1u);
+      mbar_wait_backoff<64>(&S.d2_full[grp], nn & 1u);
       tc_fence_after();
-      float y[64];
-      {
-        float v0[32], v1[32];
-        tmem_ld32(tm_d2, v0);
-        tmem_ld32(tm_d2 + 32, v1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          y[q] = v0[q];
-          y[32 + q] = v1[q];
-        }
-      }
+      float y[32];
+      tmem_ld32(tm_d2, y);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.d2_empty[grp]);  // D2 is in registers: G2 of tile t + 2 may overwrite it
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float4 bv = *reinterpret_cast<const float4*>(&S.vec[1][c * 4]);
+      for (int c = 0; c < 8; ++c) {
+        const float4 bv = *reinterpret_cast<const float4*>(b2 + c * 4);
         y[c * 4 + 0] += bv.x; y[c * 4 + 1] += bv.y; y[c * 4 + 2] += bv.z; y[c * 4 + 3] += bv.w;
       }
       if (m.layer_norm) {
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < 64; ++q) {
+        for (int q = 0; q < 32; ++q) {
           ps[q & 3] += y[q];
           pq[q & 3] = fmaf(y[q], y[q], pq[q & 3]);
         }
-        const float sx = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-        const float sq = (pq[0] + pq[1]) + (pq[2] + pq[3]);
+        S.ln_part[grp][hsel][row] = make_float2((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]));
+        asm volatile("bar.sync %0, 64;" : : "r"(pair_bar) : "memory");
+        const float2 p0 = S.ln_part[grp][0][row], p1 = S.ln_part[grp][1][row];  // same order in both threads
+        const float sx = p0.x + p1.x, sq = p0.y + p1.y;
         const float mean = sx * (1.0f / WS_HID);
         const float var = fmaxf(sq * (1.0f / WS_HID) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + m.ln_eps);
         const float nm = -mean * rstd;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float4 gv = *reinterpret_cast<const float4*>(&S.vec[2][c * 4]);
-          const float4 bv = *reinterpret_cast<const float4*>(&S.vec[3][c * 4]);
+        for (int c = 0; c < 8; ++c) {
+          const float4 gv = *reinterpret_cast<const float4*>(gamma + c * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(beta + c * 4);
           y[c * 4 + 0] = fmaf(fmaf(y[c * 4 + 0], rstd, nm), gv.x, bv.x);
           y[c * 4 + 1] = fmaf(fmaf(y[c * 4 + 1], rstd, nm), gv.y, bv.y);
           y[c * 4 + 2] = fmaf(fmaf(y[c * 4 + 2], rstd, nm), gv.z, bv.z);
           y[c * 4 + 3] = fmaf(fmaf(y[c * 4 + 3], rstd, nm), gv.w, bv.w);
         }
-        if (a.save_stats && orow >= 0)
+        if (a.save_stats && orow >= 0 && hsel == 0)
           *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
       }
       // ---- outputs staged through the A2 tile (free: G2 of this tile is complete)
       if (out2) {  // edge update: src0 row + y
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           float e[8];
           ws_unpack8(res[c], e);
 #pragma unroll
           for (int q = 0; q < 8; ++q) e[q] += y[c * 8 + q];
-          sts128(a2 + sw128_offset(row, c), ws_pack8(e));
+          sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(e));
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + sub;
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + sub;
           const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
           const uint4 u = lds128(a2 + sw128_offset(quad * 32 + r, j));
           if (orr >= 0) *reinterpret_cast<uint4*>(out2 + static_cast<long long>(orr) * WS_HID + j * 8) = u;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       }
       if (out) {  // messages, or y + residual
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           float e[8];
           if (a.residual_x0) {
             ws_unpack8(res[c], e);
@@ -427,12 +428,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
 #pragma unroll
             for (int q = 0; q < 8; ++q) e[q] = y[c * 8 + q];
           }
-          sts128(a2 + sw128_offset(row, c), ws_pack8(e));
+          sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(e));
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + sub;
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + sub;
           const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
           const uint4 u = lds128(a2 + sw128_offset(quad * 32 + r, j));
           if (orr >= 0) *reinterpret_cast<uint4*>(out + static_cast<long long>(orr) * WS_HID + j * 8) = u;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const int gsz = a.agg_group;
         if (orow < 0) {
 #pragma unroll
-          for (int q = 0; q < 64; ++q) y[q] = 0.f;
+          for (int q = 0; q < 32; ++q) y[q] = 0.f;
         }
         int cbase = 0;
 #define P4C_WS_AGG_STEP(OFF, N)                                              \
@@ -459,19 +460,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           }                                                                  \
           if (up) cbase += (N) / 2;                                          \
         }
-        P4C_WS_AGG_STEP(1, 64)
-        P4C_WS_AGG_STEP(2, 32)
-        P4C_WS_AGG_STEP(4, 16)
-        P4C_WS_AGG_STEP(8, 8)
-        P4C_WS_AGG_STEP(16, 4)
+        P4C_WS_AGG_STEP(1, 32)
+        P4C_WS_AGG_STEP(2, 16)
+        P4C_WS_AGG_STEP(4, 8)
+        P4C_WS_AGG_STEP(8, 4)
 #undef P4C_WS_AGG_STEP
         if (orow >= 0) {
-          const int ncol = 64 / gsz;
-          __nv_bfloat16* dst = a.aggr_out + static_cast<long long>(orow / gsz) * WS_HID + cbase;
+          const int ncol = 32 / gsz;
+          __nv_bfloat16* dst = a.aggr_out + static_cast<long long>(orow / gsz) * WS_HID + col0 + cbase;
           const float sc = a.agg_scale;
           if (ncol >= 8) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               if (c < ncol / 8) {
                 float e[8];
 #pragma unroll
@@ -528,7 +528,7 @@ bool ws_forward_supported(const p4c_mlp_t* m, const void* residual, const void* 
     if (residual != s0.ptr || s0.index || s0.ld != P4C_HIDDEN || s0.width != P4C_HIDDEN) return false;
     if (m->batch > 1 && s0.batch_stride != full * P4C_HIDDEN) return false;
   }
-  if (aggr_out && (agg_group < 1 || agg_group > 32 || (agg_group & (agg_group - 1)))) return false;
+  if (aggr_out && (agg_group < 1 || agg_group > 16 || (agg_group & (agg_group - 1)))) return false;
   return true;
 }
 
@@ -567,7 +567,7 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
     }
     configured = true;
   }
-  mlp2_ws_fwd_kernel<<<grid, WS_THREADS, smem, st>>>(a);
+  launch_pdl(mlp2_ws_fwd_kernel, dim3(grid), dim3(WS_THREADS), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_forward(ws)");
   ++g_ws_launches;
   return P4C_OK;

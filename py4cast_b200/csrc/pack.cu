@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
   const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64, 0, 0);
 
+  pdl_launch_dependents();
+  pdl_wait();  // the previous kernel's outputs are complete and visible
   uint32_t it = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     if (tid < 128) {
@@ -245,6 +247,7 @@ extern "C" int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* st
   if (n == 0) return P4C_OK;
   pack_weights_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(table_dev);
   P4C_CHECK_LAUNCH("pack_weights");
+  pdl_block_next();  // the images are read before griddepcontrol.wait
   return P4C_OK;
 }
 
@@ -292,7 +295,7 @@ extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* ro
   const long long ntiles = (static_cast<long long>(num_seg) * batch + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
   const size_t smem = sizeof(SegLinSmem) + 1024;
-  seg_linear_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  launch_pdl(seg_linear_tc_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a);
   P4C_CHECK_LAUNCH("seg_linear");
   return P4C_OK;
 }

@@ -23,6 +23,22 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+static int g_pdl = -1;
+static bool g_pdl_block_next = false;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("P4C_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+void pdl_block_next() { g_pdl_block_next = true; }
+bool pdl_take_attr() {
+  const bool blocked = g_pdl_block_next;
+  g_pdl_block_next = false;
+  return pdl_enabled() && !blocked;
+}
+
 // ----------------------------------------------------------------------------- CSR
 __global__ void csr_hist_kernel(const long long* __restrict__ keys, long long E, int num_keys,
                                 int* __restrict__ counts, int* __restrict__ bad) {

@@ -26,6 +26,9 @@ def main():
     es = graph.m2g if args.which == "m2g" else graph.g2m
     torch.manual_seed(0)
     net = InteractionNet(es, 64, update_edges=False).to(dev)
+    from py4cast_b200 import ops
+    if dt == torch.bfloat16:  # weight images, as in a rollout (the pipelined forward needs them)
+        ops.WeightPacker([m.meta for m in net.modules() if hasattr(m, "meta")]).pack()
     B = args.batch
     g = torch.Generator(device="cuda").manual_seed(0)
     send = torch.randn(B, es.num_send, 64, device=dev, generator=g).to(dt).requires_grad_(True)
