@@ -35,6 +35,7 @@ bool tc_forward_supported(const p4c_mlp_t* m);
 int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
                            float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st);
 void tc_set_trace(long long* buf);
+long long* tc_get_trace();
 // warp-specialised pipelined forward for the large calls (mlp2_ws.cu)
 bool ws_forward_supported(const p4c_mlp_t* m, const void* residual, const void* out2, const void* aggr_out,
                           int agg_group);

@@ -482,6 +482,7 @@ bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb) {
 }
 
 void tc_set_trace(long long* buf) { tc::g_trace = buf; }
+long long* tc_get_trace() { return tc::g_trace; }
 
 bool tc_forward_supported(const p4c_mlp_t* m) {
   if (m->dtype != P4C_BF16) return false;

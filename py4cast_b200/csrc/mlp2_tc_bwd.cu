@@ -32,7 +32,7 @@ constexpr uint32_t COL_DW1A = 0, COL_DW1B = 64, COL_DW2 = 128, COL_SCRATCH = 192
 // small control block placed after the tiles (kept tiny: two CTAs must fit in one SM)
 struct BwdCtl {
   float b2[HID], gamma[HID];
-  uint32_t row_off[2][P4C_MAX_SRC][TM];  // source row offset in units of 8 elements; ~0u = invalid row
+  uint32_t row_off[P4C_MAX_SRC][TM];     // source row offset in units of 8 elements; ~0u = invalid row
   int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid row
   float2 ln_part[2][TM];                 // LayerNorm-backward row sums of each column half
   uint64_t mbar[4];
@@ -55,12 +55,14 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// bf16x2 -> two floats with integer ops (exact)
+__device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xFFFF0000u);
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  float2 t;
-  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+  unpack2(u.x, f[0], f[1]); unpack2(u.y, f[2], f[3]);
+  unpack2(u.z, f[4], f[5]); unpack2(u.w, f[6], f[7]);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 u;
@@ -80,32 +82,62 @@ struct BwdArgs {
   // index and batch stride as K-block `dy_blk` (its row offset is reused: no index round trip),
   // 2 = identity rows laid out like the outputs (dy_a + orow * out_features)
   int dy_mode, dy_blk;
+  long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's first tile, slots 16..31
 };
+#define P4C_BWD_TRACE(i)                                                             \
+  do {                                                                               \
+    if (args.trace && blockIdx.x == 0 && tid == 0 && (it == 0 || it == 2))           \
+      args.trace[16 + (it ? 16 : 0) + (i)] = clock64();                              \
+  } while (0)
 
-__device__ __forceinline__ void bwd_row_info(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
-                                             long long total_rows, uint32_t (*row_off)[TM], int32_t* orow,
-                                             int tid) {
-  if (tid >= TM) return;
+// Addressing of one tile row (thread tid < TM owns row tid): output row and, per K-block, the source
+// row offset.  The gather-index loads are issued here and consumed when the offsets are stored
+// (bwd_row_store), so their latency hides behind whatever runs in between.
+struct RowAddr {
+  int32_t orow;
+  uint32_t off[P4C_MAX_SRC];
+};
+__device__ __forceinline__ RowAddr bwd_row_addr(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
+                                                long long total_rows, int tid) {
+  RowAddr a;
+  a.orow = -1;
+#pragma unroll
+  for (int k = 0; k < P4C_MAX_SRC; ++k) a.off[k] = kNoRow;
   const long long g = tile_row0 + tid;
-  long long o = -1, b = 0;
-  int rr = 0;
-  if (g < total_rows) {
-    b = g / m.rows;
-    rr = static_cast<int>(g - b * m.rows);
-    o = b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr;
-  }
-  orow[tid] = static_cast<int32_t>(o);
-  for (int k = 0; k < kb.nblk; ++k) {
-    const p4c_src_t& src = m.src[kb.src[k]];
-    uint32_t off = kNoRow;
-    if (o >= 0) {
-      const long long idx = src.index ? static_cast<long long>(src.index[rr]) : static_cast<long long>(rr);
-      off = static_cast<uint32_t>((b * src.batch_stride + idx * src.ld + kb.col0[k]) >> 3);
+  if (tid < TM && g < total_rows) {
+    const long long b = g / m.rows;
+    const int rr = static_cast<int>(g - b * m.rows);
+    a.orow = static_cast<int32_t>(b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr);
+#pragma unroll
+    for (int k = 0; k < P4C_MAX_SRC; ++k) {
+      if (k < kb.nblk) {
+        const p4c_src_t& src = m.src[kb.src[k]];
+        const long long idx = src.index ? static_cast<long long>(src.index[rr]) : static_cast<long long>(rr);
+        a.off[k] = static_cast<uint32_t>((b * src.batch_stride + idx * src.ld + kb.col0[k]) >> 3);
+      }
     }
-    row_off[k][tid] = off;
   }
+  return a;
+}
+__device__ __forceinline__ void bwd_row_store(const RowAddr& a, int nblk, uint32_t (*row_off)[TM], int tid) {
+  if (tid >= TM) return;
+#pragma unroll
+  for (int k = 0; k < P4C_MAX_SRC; ++k)
+    if (k < nblk) row_off[k][tid] = a.off[k];
 }
 
+// next tile's saved pre-activation rows -> the (free) A1 tile, 16-byte chunks, coalesced
+__device__ __forceinline__ void bwd_h1_prefetch(const __nv_bfloat16* h1p, const int32_t* orow, uint8_t* A1, int tid) {
+  const uint32_t a1 = smem_u32(A1);
+#pragma unroll
+  for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
+    const int idx = i * NTHREADS + tid;
+    const int r = idx >> 3, j = idx & 7;
+    const long long o = orow[r];
+    cp_async16(a1 + sw128_offset(r, j), o >= 0 ? h1p + o * HID + j * 8 : h1p, o >= 0 ? 16u : 0u);
+  }
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" : : "l"(p)); }
 __device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const KBlocks& kb, const uint32_t (*row_off)[TM],
                                            uint8_t* xbase, int tid) {
   for (int k = 0; k < kb.nblk; ++k) {
@@ -126,9 +158,13 @@ __device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const KBlocks& kb
 }
 
 // shared-memory map (all tiles 1024-byte aligned):
-//   [X0 .. X(nblk-1)] [A1] [DH] [W2] [W2T] [W1T x ndx] [BwdCtl]
+//   [X0 .. X(nblk-1)] [A1] [DH] [W2] [W2T] [W1T x ndx] [ONES] [BwdCtl]
+// ONES: two 8-row swizzle atoms of bf16 1.0 -- the second 64-row half of an MN-major M=128 A operand
+// is pointed at it (leading-dimension offset of the descriptor), so that lanes 64..127 of the dW2 /
+// dW1B accumulators hold the column sums of dh2 / dh1 = the bias gradients, for free.
+constexpr int ONES_BYTES = 2048;
 __host__ __device__ inline size_t bwd_smem_bytes(int nblk, int ndx) {
-  return static_cast<size_t>(nblk + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + sizeof(BwdCtl);
+  return static_cast<size_t>(nblk + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + ONES_BYTES + sizeof(BwdCtl);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_constant__ BwdArgs args) {
@@ -145,7 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   uint8_t* W2s = DH + BLK;
   uint8_t* W2T = W2s + WBLK;
   uint8_t* W1T = W2T + WBLK;
-  BwdCtl& C = *reinterpret_cast<BwdCtl*>(W1T + ndx * WBLK);
+  uint8_t* ONES = W1T + ndx * WBLK;
+  BwdCtl& C = *reinterpret_cast<BwdCtl*>(ONES + ONES_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column half
@@ -158,6 +195,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   const bool need_w1 = need_w || g.g_w1 != nullptr, need_w2 = need_w || g.g_w2 != nullptr;
 
   // ---- one-time set-up
+  {
+    const int it = 0;
+    P4C_BWD_TRACE(0);
+  }
   if (args.zero_x) {
     uint4* xz = reinterpret_cast<uint4*>(Xs);
     for (int i = tid; i < nblk * BLK / 16; i += NTHREADS) xz[i] = make_uint4(0, 0, 0, 0);
@@ -191,6 +232,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       C.gamma[tid] = m.gamma ? m.gamma[tid] : 1.f;
     }
   }
+  if (tid < ONES_BYTES / 16)
+    reinterpret_cast<uint4*>(ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   cp_async_commit();  // group 0: the weight image (empty when converted in the kernel)
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&C.mbar[i], 1);
@@ -203,57 +246,82 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = C.tmem_base;
+  {
+    const int it = 0;
+    P4C_BWD_TRACE(1);
+  }
   const uint32_t tmem_row = tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0;
   constexpr uint32_t IDESC_KK = make_idesc_bf16(TM, HID, 0, 0);  // A, B K-major
   constexpr uint32_t IDESC_MM = make_idesc_bf16(TM, HID, 1, 1);  // A, B MN-major (transposed reads)
+
+  const int k1pad = (m.k1 + 31) / 32 * 32;
+  const long long pf = static_cast<long long>(k1pad) * HID + HID * HID + 4 * HID;
+  float* const part = g.wgrad_partials + static_cast<long long>(blockIdx.x) * pf;
+  float* const pvec = part + static_cast<long long>(k1pad) * HID + HID * HID;  // db1, db2, dgamma, dbeta
+  const bool padd = g.partials_mode == 2;  // add to what earlier calls left in this CTA's block
+  if (padd) {  // pull this CTA's block towards L2: it is read once, at the very end
+    for (long long o = static_cast<long long>(tid) * 32; o < pf; o += NTHREADS * 32) prefetch_l2(part + o);
+  }
 
   const __nv_bfloat16* h1p = reinterpret_cast<const __nv_bfloat16*>(g.h1);
   const __nv_bfloat16* dya = reinterpret_cast<const __nv_bfloat16*>(g.dy_a);
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(g.dy_b);
   __nv_bfloat16* dh1_out = reinterpret_cast<__nv_bfloat16*>(g.dh1_out);
 
-  // per-thread column-sum accumulators (column col0 + lane, rows of this warp): db1, db2, dgamma, dbeta
-  float vacc[4] = {0.f, 0.f, 0.f, 0.f};
+  // per-thread column-sum accumulators (column col0 + lane, rows of this warp): dgamma, dbeta
+  // (db1, db2 are accumulated by the tensor core: ONES lanes of dW1B / dW2)
+  float vacc[2] = {0.f, 0.f};
 
   long long tile = blockIdx.x;
   pdl_launch_dependents();
-  if (tile < ntiles) bwd_row_info(m, kb, tile * TM, total_rows, C.row_off[0], C.orow[0], tid);  // constants
-  pdl_wait();  // the previous kernel's outputs are complete and visible
-  if (tile < ntiles) {
-    __syncthreads();
-    bwd_gather(m, kb, C.row_off[0], Xs, tid);
+  {
+    const RowAddr ra = bwd_row_addr(m, kb, tile * TM, total_rows, tid);  // graph constants only
+    if (tid < TM) C.orow[0][tid] = ra.orow;
+    bwd_row_store(ra, nblk, C.row_off, tid);
   }
-  cp_async_commit();
+  pdl_wait();  // the previous kernel's outputs are complete and visible
+  __syncthreads();
+  {
+    const int it = 0;
+    P4C_BWD_TRACE(2);
+  }
+  bwd_h1_prefetch(h1p, C.orow[0], A1, tid);
+  cp_async_commit();  // group 1: h1 of the first tile
+  bwd_gather(m, kb, C.row_off, Xs, tid);
+  cp_async_commit();  // group 2: X of the first tile
+  // commit order from here on: ..., X(t), h1(t+1), X(t+1), ...: wait<1> at the top of tile t leaves
+  // X(t) in flight, wait<1> before G4 leaves h1(t+1) in flight.
 
   for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
     const int p = it & 1;
     const uint32_t parity = static_cast<uint32_t>(it & 1);
     const uint32_t acc = it ? 1u : 0u;  // weight-gradient accumulators: overwrite on the first tile
+    const long long next = tile + gridDim.x;
+
+    // weight image and h1(tile) have landed (X(tile) may still be in flight); the barrier makes
+    // the h1 chunks copied by other threads visible and ends the previous tile (A1 / DH / scratch
+    // are free)
+    cp_async_wait<1>();
+    tc_fence_before();
+    __syncthreads();
+    P4C_BWD_TRACE(3);
     const long long orow = C.orow[p][row];  // -1 = row beyond the problem
     const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
-    // the weight image (first commit group) must have landed before the first MMA; later on
-    // this only leaves the newest group (the next tile's gather) in flight
-    cp_async_wait<1>();
-    // ---- a. h1 half-row -> registers (packed bf16), a1 = SiLU(h1) -> A1 tile
-    uint4 h1r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c0 = col0 + j * 8;
-      h1r[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(h1p + orow * HID + c0) : make_uint4(0, 0, 0, 0);
-      float h[8];
-      unpack8(h1r[j], h);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
-      *reinterpret_cast<uint4*>(A1 + sw128_offset(row, c0 >> 3)) = pack8(h);
+    // addressing of the next tile: index loads issued now, consumed in phase f
+    RowAddr nra;
+    nra.orow = -1;
+    if (next < ntiles) {
+      nra = bwd_row_addr(m, kb, next * TM, total_rows, tid);
+      if (tid < TM) C.orow[p ^ 1][tid] = nra.orow;
     }
-    // dy half-row -> packed bf16 registers (dy_a gathered and scaled, + dy_b)
-    uint4 dyr[4];
+
+    // ---- a. issue every global load of the tile at once: dy_a (gathered, scaled), dy_b, LN stats
     const __nv_bfloat16* dy_row = dya;  // first element of this row of dy_a
     float dy_sc = 1.f;
     if (orow >= 0) {
       if (args.dy_mode == 1) {
-        dy_row = dya + (static_cast<long long>(C.row_off[p][args.dy_blk][row]) << 3);
+        dy_row = dya + (static_cast<long long>(C.row_off[args.dy_blk][row]) << 3);
       } else if (args.dy_mode == 2) {
         dy_row = dya + orow * OUT;
       } else {
@@ -264,31 +332,58 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         dy_row = dya + bb * g.dy_a_batch_stride + ia * OUT;
       }
     }
-    {
+    uint4 dyr[4];
+    uint4 dybr[4];
+    float2 lnst = make_float2(0.f, 0.f);  // (mean, rstd)
+    const bool wide = OUT == HID;
+    if (wide) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dyr[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(dy_row + col0 + j * 8) : make_uint4(0, 0, 0, 0);
+        dybr[j] = (orow >= 0 && dyb) ? *reinterpret_cast<const uint4*>(dyb + orow * HID + col0 + j * 8)
+                                     : make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (ln && orow >= 0) lnst = *reinterpret_cast<const float2*>(g.stats + 2 * orow);
+
+    // h1 half-row from the A1 tile -> registers (packed bf16); a1 = SiLU(h1) written back in place
+    uint4 h1r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4* slot = reinterpret_cast<uint4*>(A1 + sw128_offset(row, (col0 >> 3) + j));
+      h1r[j] = *slot;
+      float h[8];
+      unpack8(h1r[j], h);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+      *slot = pack8(h);
+    }
+    // dy half-row -> packed bf16 registers (dy_a scaled, + dy_b)
+    if (wide) {
+      if (dy_sc != 1.f || dyb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d[8], e[8];
+          unpack8(dyr[j], d);
+          unpack8(dybr[j], e);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = fmaf(d[q], dy_sc, e[q]);
+          dyr[j] = pack8(d);
+        }
+      }
+    } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c0 = col0 + j * 8;
         float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (orow >= 0) {
-          if (OUT == HID) {
-            unpack8(*reinterpret_cast<const uint4*>(dy_row + c0), d);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) d[q] *= dy_sc;
-            if (dyb) {
-              float e[8];
-              unpack8(*reinterpret_cast<const uint4*>(dyb + orow * HID + c0), e);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) d[q] += e[q];
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int c = c0 + q;
-              if (c < OUT) {
-                float v = __bfloat162float(dy_row[c]) * dy_sc;
-                if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
-                d[q] = v;
-              }
+          for (int q = 0; q < 8; ++q) {
+            const int c = c0 + q;
+            if (c < OUT) {
+              float v = __bfloat162float(dy_row[c]) * dy_sc;
+              if (dyb) v += __bfloat162float(dyb[orow * OUT + c]);
+              d[q] = v;
             }
           }
         }
@@ -297,12 +392,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     }
 
     if (ln) {
-      float mean = 0.f, rstd = 0.f;
-      if (orow >= 0) {
-        mean = g.stats[2 * orow];
-        rstd = g.stats[2 * orow + 1];
-      }
+      const float mean = lnst.x, rstd = lnst.y;
       // ---- b. G1: h2 = a1 W2^T -> scratch
+      P4C_BWD_TRACE(4);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -317,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
       mbar_wait(&C.mbar[0], parity);
       tc_fence_after();
+      P4C_BWD_TRACE(5);
       // ---- c. LayerNorm backward: xhat from the recomputed h2, row sums exchanged between the
       //         two threads of a row, then dh2 (kept in dyr), dgamma / dbeta column sums
       float xh[32];
@@ -359,24 +452,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         }
         dyr[j] = pack8(o);  // dyr now holds dh2
       }
-      vacc[2] += warp_colsum32(xh, lane);
-      vacc[3] += warp_colsum32(t1, lane);
+      vacc[0] += warp_colsum32(xh, lane);
+      vacc[1] += warp_colsum32(t1, lane);
     }
-    // db2 column sums + dh2 -> DH tile
-    {
-      float t[32];
+    // dh2 -> DH tile (db2 = its column sums: ONES lanes of G3)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unpack8(dyr[j], t + j * 8);
-        *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
-      }
-      vacc[1] += warp_colsum32(t, lane);
-    }
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
 
     // ---- d. G2: da1 = dh2 W2 -> scratch ;  G3: dW2 += a1^T dh2
+    P4C_BWD_TRACE(6);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), wt = smem_u32(W2T), a1 = smem_u32(A1);
@@ -384,16 +471,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       for (int j = 0; j < 4; ++j)
         mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
                     make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
-      if (need_w2) {
+      {
+        const uint32_t ones = smem_u32(ONES);
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // K = 128 rows, 16 per MMA = 2 groups of 8 rows = 2048 bytes
-          mma_bf16_ss(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, BLK, 1024),
+          mma_bf16_ss(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, ones - (a1 + j * 2048), 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
       }
       mma_commit(&C.mbar[1]);
     }
     mbar_wait(&C.mbar[1], parity);
     tc_fence_after();
+    P4C_BWD_TRACE(7);
+    // A1 is free (G1, G3 complete): the next tile's h1 rows start to stream in
+    if (next < ntiles) bwd_h1_prefetch(h1p, C.orow[p ^ 1], A1, tid);
+    cp_async_commit();
 
     // ---- e. dh1 = da1 * SiLU'(h1): db1 sums, global store, DH tile (overwrites dh2)
     {
@@ -410,27 +502,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = packed;
         if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + col0 + j * 8) = packed;
       }
-      vacc[0] += warp_colsum32(v, lane);
     }
-    cp_async_wait<0>();  // X(tile) landed (issued one tile ago)
+    P4C_BWD_TRACE(8);
+    cp_async_wait<1>();  // X(tile) landed (issued one tile ago); h1(next) stays in flight
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    P4C_BWD_TRACE(9);
 
     // ---- f. G4: dW1 += X^T dh1 ; G5(0): dX = dh1 W1[:, s0]
     if (tid == 0) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), xa = smem_u32(Xs);
-      if (need_w1) {
+      {
+        const uint32_t ones = smem_u32(ONES);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           mma_bf16_ss(tmem + COL_DW1A, make_desc_sw128(xa + j * 2048, BLK, 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
-        if (nblk == 3) {
+        // dW1B: lanes 0..63 = X2^T dh1 (three K-blocks) or ones; lanes 64..127 = 1^T dh1 = db1
+        const uint32_t x2 = nblk == 3 ? xa + 2 * BLK : ones;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            mma_bf16_ss(tmem + COL_DW1B, make_desc_sw128(xa + 2 * BLK + j * 2048, BLK, 1024),
-                        make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t ab = nblk == 3 ? x2 + j * 2048 : ones;
+          mma_bf16_ss(tmem + COL_DW1B, make_desc_sw128(ab, ones - ab, 1024),
+                      make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
         }
       }
       if (ndx > 0) {
@@ -442,13 +538,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
       mma_commit(&C.mbar[2]);
     }
-    // meanwhile: addressing of the next tile
-    const long long next = tile + gridDim.x;
-    if (next < ntiles) bwd_row_info(m, kb, next * TM, total_rows, C.row_off[p ^ 1], C.orow[p ^ 1], tid);
+    // meanwhile: next tile's source offsets (index loads issued at the top of this tile) and L2
+    // prefetch of its identity-indexed per-row inputs
+    if (next < ntiles) {
+      bwd_row_store(nra, nblk, C.row_off, tid);
+      const long long no = C.orow[p ^ 1][row];
+      if (no >= 0) {
+        if (args.dy_mode == 2) prefetch_l2(dya + no * OUT + col0);
+        if (dyb) prefetch_l2(dyb + no * OUT + col0);
+        if (ln && hsel == 0) prefetch_l2(g.stats + 2 * no);
+      }
+    }
     mbar_wait(&C.mbar[2], parity);
     tc_fence_after();
-    __syncthreads();  // next row_off visible; X, A1 are free (DH still feeds a possible second dX)
-    if (next < ntiles) bwd_gather(m, kb, C.row_off[p ^ 1], Xs, tid);
+    P4C_BWD_TRACE(10);
+    __syncthreads();  // next row_off visible; X is free (DH still feeds a possible second dX)
+    if (next < ntiles) bwd_gather(m, kb, C.row_off, Xs, tid);
     cp_async_commit();
 
     // ---- g. dX stores (one or two identity-indexed sources)
@@ -508,63 +613,81 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();  // tile done: A1 / DH / scratch may be overwritten
+    P4C_BWD_TRACE(11);
   }
+  tc_fence_before();
+  __syncthreads();  // last tile done (the loop's own end-of-tile barrier sits at the top of the next tile)
 
-  // ---- per-CTA partials: weight gradients from TMEM, vector gradients from the warp sums
+  // ---- per-CTA partials: weight and bias gradients from TMEM, LayerNorm-affine gradients from the
+  //      warp sums.  In accumulate mode the block's previous content is fetched with all loads in
+  //      flight at once (the lines were pulled into L2 when the kernel started).
   cp_async_wait<0>();
   tc_fence_after();
-  const int k1pad = (m.k1 + 31) / 32 * 32;
-  const long long pf = static_cast<long long>(k1pad) * HID + HID * HID + 4 * HID;
-  float* part = g.wgrad_partials + static_cast<long long>(blockIdx.x) * pf;
-  const bool padd = g.partials_mode == 2;  // add to what earlier calls left in this CTA's block
-  auto put32 = [&](float* dst, const float (&v)[32]) {
-#pragma unroll
-    for (int q = 0; q < 32; q += 4) {
-      float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-      if (padd) {
-        const float4 e = *reinterpret_cast<const float4*>(dst + q);
-        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-      }
-      *reinterpret_cast<float4*>(dst + q) = o;
-    }
-  };
   {
-    float v[32];
-    // dW1[k][c] for K-blocks 0,1 (TMEM lane = 64 * block + k)
-    tmem_ld32(tmem_row + COL_DW1A, v);
-    tmem_ld_wait();
+    // this thread's rows of the partial block: dW1 (blocks 0/1), dW1 (block 2), dW2, and for the
+    // thread that owns TMEM lane 64: db1, db2
+    float* dstA = nullptr;
+    float* dstB = nullptr;
+    float* dstC = nullptr;
     {
       const int blk = row >> 6, kk = row & 63;
-      if (need_w1 && blk < nblk && kk < kb.kvalid[blk])
-        put32(part + static_cast<long long>(kb.kstart[blk] + kk) * HID + col0, v);
+      if (need_w1 && blk < nblk && kk < kb.kvalid[blk]) dstA = part + static_cast<long long>(kb.kstart[blk] + kk) * HID + col0;
+      if (need_w1 && nblk == 3 && row < kb.kvalid[2]) dstB = part + static_cast<long long>(kb.kstart[2] + row) * HID + col0;
+      if (need_w2 && row < HID) dstC = part + static_cast<long long>(k1pad) * HID + static_cast<long long>(row) * HID + col0;
+      if (row == HID) {
+        dstB = pvec + col0;        // db1
+        dstC = pvec + HID + col0;  // db2
+      }
     }
+    float4 eA[8], eB[8], eC[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      eA[q] = (padd && dstA) ? *reinterpret_cast<const float4*>(dstA + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      eB[q] = (padd && dstB) ? *reinterpret_cast<const float4*>(dstB + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      eC[q] = (padd && dstC) ? *reinterpret_cast<const float4*>(dstC + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto put32 = [&](float* dst, const float (&v)[32], const float4 (&e)[8]) {
+      if (!dst) return;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) =
+            make_float4(v[4 * q] + e[q].x, v[4 * q + 1] + e[q].y, v[4 * q + 2] + e[q].z, v[4 * q + 3] + e[q].w);
+    };
+    float v[32];
+    tmem_ld32(tmem_row + COL_DW1A, v);  // dW1[k][c] for K-blocks 0,1 (TMEM lane = 64 * block + k)
+    tmem_ld_wait();
+    put32(dstA, v, eA);
     tmem_ld32(tmem_row + COL_DW1B, v);
     tmem_ld_wait();
-    if (need_w1 && nblk == 3 && row < kb.kvalid[2])
-      put32(part + static_cast<long long>(kb.kstart[2] + row) * HID + col0, v);
+    put32(dstB, v, eB);
     tmem_ld32(tmem_row + COL_DW2, v);
     tmem_ld_wait();
-    if (need_w2 && row < HID)
-      put32(part + static_cast<long long>(k1pad) * HID + static_cast<long long>(row) * HID + col0, v);
+    put32(dstC, v, eC);
+  }
+  {
+    const int it = 0;
+    P4C_BWD_TRACE(12);
   }
   // cross-warp sums in a fixed order; the A1 tile is free by now and serves as scratch
-  float (*red)[4][32] = reinterpret_cast<float (*)[4][32]>(A1);  // [warp][vector][lane]
+  float (*red)[2][32] = reinterpret_cast<float (*)[2][32]>(A1);  // [warp][vector][lane]
 #pragma unroll
-  for (int v = 0; v < 4; ++v) red[warp][v][lane] = vacc[v];
+  for (int v = 0; v < 2; ++v) red[warp][v][lane] = vacc[v];
   __syncthreads();
   if (tid < HID) {
-    float* pv = part + static_cast<long long>(k1pad) * HID + HID * HID;
     const int w0 = (tid >> 5) * 4, l = tid & 31;  // column tid lives in warps w0..w0+3 (same hsel)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < 2; ++v) {
       const float sum = (red[w0][v][l] + red[w0 + 1][v][l]) + (red[w0 + 2][v][l] + red[w0 + 3][v][l]);
-      pv[v * HID + tid] = padd ? pv[v * HID + tid] + sum : sum;
+      float* d = pvec + (2 + v) * HID + tid;  // dgamma, dbeta
+      *d = padd ? *d + sum : sum;
     }
   }
   tc_fence_before();
   __syncthreads();
+  {
+    const int it = 0;
+    P4C_BWD_TRACE(13);
+  }
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -620,6 +743,7 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
   a.dy_mode = 0;
   a.dy_blk = 0;
+  a.trace = tc_get_trace();
   const long long full = m->full_rows > 0 ? m->full_rows : m->rows;
   if (!g->dy_a_scale) {
     if (!g->dy_a_index && (m->batch == 1 || g->dy_a_batch_stride == full * m->out_features)) {

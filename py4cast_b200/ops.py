@@ -621,6 +621,23 @@ def seg_linear(src: torch.Tensor, csr: Csr, batch: int, w1: torch.Tensor, col0: 
     )
 
 
+def _batch_rows_csr(gi: GraphIndex, batch: int, device) -> Csr:
+    """Segments {b * E + e : b < batch} over the rows of a (B, E, 64) tensor viewed as (B * E, 64):
+    the batch sum of per-edge rows expressed as a segment sum (cached per edge set and batch)."""
+    cache = gi.__dict__.setdefault("_batch_csr", {})
+    key = (batch, str(device))
+    if key not in cache:
+        E = gi.num_edges
+        rowptr = torch.arange(0, (E + 1) * batch, batch, dtype=torch.int32, device=device)
+        perm = None
+        if batch > 1:
+            e = torch.arange(E, dtype=torch.int32, device=device)
+            perm = (e.unsqueeze(1) + E * torch.arange(batch, dtype=torch.int32, device=device).unsqueeze(0))
+            perm = perm.reshape(-1).contiguous()
+        cache[key] = Csr(rowptr, perm, E, None)
+    return cache[key]
+
+
 class _InteractionNetFn(torch.autograd.Function):
     """
     (send, rec, edge) -> (rec_out, edge_out):
@@ -789,7 +806,14 @@ class _InteractionNetFn(torch.autograd.Function):
 
         # ---- edge MLP backward
         dh1 = torch.empty(B, E, HIDDEN, dtype=dt, device=dev)
-        d_edge = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if need_edge else None
+        # Edge representation shared by the batch (static embeddings): its gradient is
+        # (sum_b dh1[b]) x W1[:, edge block] by linearity -> one fused segment-sum + GEMM over the
+        # batch instead of a (B, E, 64) input gradient from the edge kernel and a batch sum.
+        edge_by_linearity = need_edge and tc and edge.dim() == 2 and d_edge_out is None
+        d_edge = None
+        if need_edge:
+            d_edge = (torch.empty(E, HIDDEN, dtype=dt, device=dev) if edge_by_linearity
+                      else torch.empty(B, E, HIDDEN, dtype=dt, device=dev))
         d_send = None
         if need_send and not same_nodes:
             d_send = torch.empty(B, Ns, HIDDEN, dtype=dt, device=dev)
@@ -817,7 +841,7 @@ class _InteractionNetFn(torch.autograd.Function):
             g.dy_b = _off(d_edge_out, o) if d_edge_out is not None else None
             g.h1, g.stats = _off(h1_e, o), _off(st_e, grp.start * 2)
             g.dh1_out = _off(dh1, o)
-            if need_edge:
+            if need_edge and not edge_by_linearity:
                 g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_edge, o), HIDDEN, 0
                 g.dx0_add_dy = 1 if d_edge_out is not None else 0
             wgrads[6 * gidx: 6 * gidx + 6] = _bind_wgrads(lib, desc, g, w, wneed[6 * gidx: 6 * gidx + 6],
@@ -825,6 +849,10 @@ class _InteractionNetFn(torch.autograd.Function):
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(edge)")
             # sender / receiver gradients by linearity: (segment-sum of dh1) x W1 slice
             if tc:
+                if edge_by_linearity:
+                    bc = _batch_rows_csr(gi, B, dev)
+                    seg_linear(dh1.view(1, B * E, HIDDEN), Csr(bc.rowptr[grp.start: grp.stop + 1], bc.perm, n),
+                               1, w[0], 0, d_edge[grp.start: grp.stop].unsqueeze(0), False, meta=metas[gidx])
                 if need_rec:
                     seg_linear(dh1, grp.by_rec, B, w[0], 2 * HIDDEN, d_rec, True, meta=metas[gidx])
                 if need_send:
@@ -851,7 +879,10 @@ class _InteractionNetFn(torch.autograd.Function):
         if need_send and not same_nodes:
             g_send = batch_sum(d_send) if send.dim() == 2 else d_send
         g_rec = (batch_sum(d_rec) if ctx.rec_shared else d_rec) if need_rec else None
-        g_edge = (batch_sum(d_edge) if edge.dim() == 2 else d_edge) if need_edge else None
+        if edge_by_linearity:
+            g_edge = d_edge
+        else:
+            g_edge = (batch_sum(d_edge) if edge.dim() == 2 else d_edge) if need_edge else None
         return (None, None, None, None, g_send, g_rec, g_edge, *wgrads)
 
 
