@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--model", default="HiLAM", choices=["HiLAM", "GraphLAM", "HiLAMParallel"])
     ap.add_argument("--strategy", default="diff_ar", choices=["diff_ar", "scaled_ar"])
     ap.add_argument("--grid", default="512x640")
+    ap.add_argument("--processor-layers", type=int, default=4,
+                    help="mesh processor depth (reference hilam.yaml: 4); other values are for experiments only")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
@@ -251,9 +253,19 @@ def kernel_roofline(lm, info, cfg, dev):
         k["achieved_gbs"] = k["bytes"] / k["seconds"] / 1e9
         k["frac"] = k["achieved_gbs"] / peak
     dom = max(out, key=lambda k: k["seconds"])
+    # DRAM traffic per launch of the same kernel / shape from the committed ncu --set full capture
+    # (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the shape it was captured at
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if fused and os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B and (info.grid_shape if hasattr(info, "grid_shape") else None) in (None, (512, 640)) \
+                and E == 1310720:
+            traffic, traffic_src = tj.get("m2g_edge_fwd_dram_bytes_per_launch"), tj.get("source")
     roof = {
         "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-        "frac": dom["frac"], "traffic": None, "kernel": dom["kernel"], "peak_source": peak_src,
+        "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "kernel": dom["kernel"],
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom["bytes"], "avg_launch_ms": dom["seconds"] * 1e3,
         "kernels": [{"kernel": k["kernel"], "achieved_gbs": round(k["achieved_gbs"], 1),
                      "frac": round(k["frac"], 4), "ms": round(k["seconds"] * 1e3, 4)} for k in out],
@@ -282,6 +294,8 @@ def gpu_arm(args):
     settings = {"tmp_dir": tmp}
     if args.model != "GraphLAM":
         settings["n_max_levels"] = 3
+    if args.processor_layers != 4:
+        settings["processor_layers"] = args.processor_layers
     lm = AutoRegressiveLightning(
         settings_init_args=settings, dataset_info=info, num_input_steps=2,
         num_pred_steps_train=args.pred_steps, batch_size=args.batch_per_gpu, model_name=args.model,
