@@ -15,8 +15,14 @@ per AR step (`p4c_ar_step_forward`) writing the new state straight into its slot
 (B,T,N,F) prediction slab and producing the next model input in the same pass; diff stats are
 uploaded once, not every step.
 
+Validation / test (`validation_step`, `test_step`, reference lightning.py:864-917, 995-1063): the
+same rollout under `no_grad` on the same kernels, the per-timestep loss, the `ScaledLoss`
+MAE / RMSE per-feature metrics the reference computes inside `StateErrorPlot.update`
+(plots.py:510-533) and the `reduce_spatial_dim=False` loss map of `SpatialErrorPlot.update`
+(plots.py:598-614) — as device tensors kept on the module instead of figures / logger calls.
+
 Out of scope (raise NotImplementedError): `downscaling_only`, `mask_on_nan=True`,
-`mask_ratio != 0`, plotting / metrics / GRIB writing (validation, test, predict loops).
+`mask_ratio != 0`, figures / loggers / PSD-ACC metrics / GRIB writing.
 """
 
 from __future__ import annotations
@@ -456,3 +462,49 @@ class AutoRegressiveLightning(nn.Module):
         batch_loss = torch.mean(self.loss(prediction, target_masked, mask=mask))
         self.training_step_losses.append(batch_loss.detach())
         return batch_loss
+
+    # ------------------------------------------------------- validation / test
+    def _state_metrics(self, which: Tuple[Tuple[str, str], ...]) -> Dict[str, ScaledLoss]:
+        """`ScaledLoss` metrics by alias, prepared once (reference on_validation_start :864-869
+        builds {"mae": L1}, on_test_start :995-1001 builds {"mae": L1, "rmse": MSE})."""
+        cache = self.__dict__.setdefault("_metric_cache", {})
+        out = {}
+        for torch_loss, alias in which:
+            if alias not in cache:
+                m = ScaledLoss(torch_loss, reduction="none")
+                m.prepare(self, self.interior_mask, self.dataset_info)
+                cache[alias] = m
+            out[alias] = cache[alias]
+        return out
+
+    def _eval_step(self, batch: ItemBatch, batch_idx: int, metrics: Dict[str, ScaledLoss],
+                   spatial_map: bool) -> Dict[str, torch.Tensor]:
+        with torch.no_grad():
+            prediction, target = self.common_step(batch, batch_idx, phase="val_test")
+            mask, target_masked = self.get_mask_on_nan(target)
+            time_step_loss = torch.mean(self.loss(prediction, target_masked, mask), dim=0)
+            out = {"time_step_loss": time_step_loss, "mean_loss": torch.mean(time_step_loss)}
+            for alias, metric in metrics.items():
+                out[alias] = metric(prediction, target_masked, mask)  # (B, T, F)
+            if spatial_map:
+                spatial_loss = self.loss(prediction, target_masked, mask, reduce_spatial_dim=False)
+                if prediction.num_spatial_dims == 1:  # "b t (x y) -> b t x y" (plots.py:608-611)
+                    spatial_loss = spatial_loss.reshape(*spatial_loss.shape[:2], *self.grid_shape)
+                out["spatial_loss"] = spatial_loss
+        out["prediction"], out["target"] = prediction, target_masked
+        return out
+
+    def validation_step(self, batch: ItemBatch, batch_idx: int) -> Dict[str, torch.Tensor]:
+        """Runs validation on a single batch (reference lightning.py:887-917): rollout without
+        autograd, loss per timestep, MAE per feature.  Returns the tensors the reference hands
+        to its loggers / plotters; `val_mean_loss` and `validation_step_losses` are kept as there."""
+        out = self._eval_step(batch, batch_idx, self._state_metrics((("L1Loss", "mae"),)), spatial_map=False)
+        self.__dict__.setdefault("validation_step_losses", []).append(out["mean_loss"])
+        self.val_mean_loss = out["mean_loss"]
+        return out
+
+    def test_step(self, batch: ItemBatch, batch_idx: int) -> Dict[str, torch.Tensor]:
+        """Runs test on a single batch (reference lightning.py:1017-1042 + the plotters'
+        device-side work: MAE / RMSE per feature and the spatial loss map)."""
+        metrics = self._state_metrics((("L1Loss", "mae"), ("MSELoss", "rmse")))
+        return self._eval_step(batch, batch_idx, metrics, spatial_map=True)

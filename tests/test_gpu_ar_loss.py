@@ -244,3 +244,52 @@ def test_loss_properties_at_titan_size(cuda):
     sl.prepare(nn.Module(), interior, info)
     ref = ((a - b).abs() * interior).sum(2) / interior.sum() * sl.weights(tuple(fn), cuda)
     assert_close(sl(A, Bn), ref, FP32_TOL, "titan ScaledLoss(L1)")
+
+
+@pytest.mark.parametrize("name", ["graph_scaled_ar", "conv_diff_ar"])
+def test_validation_and_test_steps_vs_reference_golden(cuda, name):
+    """validation_step / test_step (reference lightning.py:887-917, 1017-1042 + the device-side
+    work of StateErrorPlot / SpatialErrorPlot): same rollout under no_grad, per-timestep loss,
+    ScaledLoss MAE / RMSE per feature, spatial loss map — against the verbatim-reference golden
+    vectors and the loss oracle."""
+    from oracle import ar_ref
+    from py4cast_b200.lightning import AutoRegressiveLightning
+
+    _register_linear_tanh()
+    case = load_golden("ar_rollout.pt")[name]
+    p, cfg, exp = case["problem"], case["config"], case["expected"]
+    s = p["shape"]
+    info = _dataset_info(p)
+    lm = AutoRegressiveLightning(
+        settings_init_args={}, dataset_info=info, num_input_steps=s["T_in"], num_pred_steps_train=s["T"],
+        num_pred_steps_val_test=s["T"], batch_size=s["B"],
+        model_name="GoldenGraphNet" if cfg["graph"] else "GoldenConvNet",
+        losses=[{"class": "WeightedLoss", "weight": 1.0, "params": {"loss": "MSELoss", "reduction": "none"}}],
+        training_strategy=cfg["strategy"],
+    )
+    with torch.no_grad():
+        lm.model.W.copy_(exp["model_W"])
+    lm = lm.to(cuda)
+
+    val = lm.validation_step(_batch(p, cuda), 0)
+    assert not val["prediction"].tensor.requires_grad
+    assert_close(val["time_step_loss"].cpu(), exp["weighted_mse_bt"].mean(0), FP32_TOL, f"{name} val time_step_loss")
+    assert_close(val["mean_loss"].cpu(), exp["batch_loss"], FP32_TOL, f"{name} val mean_loss")
+    assert lm.val_mean_loss is val["mean_loss"] and len(lm.validation_step_losses) == 1
+
+    tst = lm.test_step(_batch(p, cuda), 0)
+    assert_close(tst["rmse"].cpu(), exp["scaled_rmse_btf"], FP32_TOL, f"{name} test rmse")
+    # MAE and the spatial map: loss oracle (pinned against the verbatim reference in
+    # tests/test_oracle_pinning.py) on the golden prediction
+    pred, tgt = exp["pred"].flatten(2, 3), p["outputs"].flatten(2, 3)
+    interior1 = (1 - p["border_mask"]).flatten(0, 1)  # (N, 1)
+    interior = interior1.squeeze(-1)
+    ones = torch.ones_like(pred)
+    mae = ar_ref.scaled_loss(pred, tgt, ones, p["stat_std"], interior1, interior.sum().item(), kind="L1Loss")
+    assert tst["mae"].shape == (s["B"], s["T"], s["F"])
+    assert_close(tst["mae"].cpu(), mae, FP32_TOL, f"{name} test mae")
+    assert_close(val["mae"].cpu(), mae, FP32_TOL, f"{name} val mae")
+    w = p["state_weight"] / p["diff_std"] ** 2
+    smap = ar_ref.weighted_loss(pred, tgt, ones, w, interior, interior.sum().item(), reduce_spatial_dim=False)
+    assert tst["spatial_loss"].shape == (s["B"], s["T"], s["H"], s["W"])
+    assert_close(tst["spatial_loss"].cpu().flatten(2, 3), smap, FP32_TOL, f"{name} spatial loss map")
