@@ -1,7 +1,8 @@
 // Tensor-core engine of the fused 2-layer MLP — BACKWARD (bf16 storage, 64-wide sources).
 //
-// Per 128-row tile (256 threads: warp w owns TMEM lanes 32*(w%4).. = rows and columns 32*(w/4)..,
-// i.e. two threads per row with 32 columns each), five groups of tcgen05 MMAs with fp32 accumulators in
+// Per 128-row tile (TPR threads per row, TPR = 2 or 4: warp w owns TMEM lanes 32*(w%4).. = rows and the
+// 64/TPR columns starting at (64/TPR)*(w/4); TPR = 2 is the default, the 4-threads-per-row shape runs
+// 32 warps per SM at 64 registers and measured slower), five groups of tcgen05 MMAs with fp32 accumulators in
 // TMEM (256 columns per CTA: 192 persistent weight-gradient columns + one 64-column scratch):
 //   G1  h2   = a1 · W2^T                      (recomputed; LayerNorm input)      -> scratch
 //   G2  da1  = dh2 · W2                                                           -> scratch
@@ -22,7 +23,6 @@ namespace p4c {
 namespace tc {
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 256;
 constexpr int HID = P4C_HIDDEN;
 constexpr int BLK = TM * 128;    // 16 KB: one 128x64 bf16 tile
 constexpr int WBLK = HID * 128;  // 8 KB: one 64x64 bf16 tile
@@ -34,22 +34,34 @@ struct BwdCtl {
   float b2[HID], gamma[HID];
   uint32_t row_off[P4C_MAX_SRC][TM];     // source row offset in units of 8 elements; ~0u = invalid row
   int32_t orow[2][TM];                   // row in the output-like arrays; -1 = invalid row
-  float2 ln_part[2][TM];                 // LayerNorm-backward row sums of each column half
+  float2 ln_part[2][TM];                 // LayerNorm-backward row sums (exchange between the threads of a row)
   uint64_t mbar[4];
   uint32_t tmem_base;
 };
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
-// column sums over the 32 lanes of a warp: lane l ends with sum_lanes v[l] (fixed order)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+// column sums over the 32 lanes of a warp (fixed order): a transposing butterfly that halves the
+// columns a lane holds at every step.  N = 32: lane l ends with the sum of column l; N = 16: lanes
+// 2c and 2c+1 both end with the sum of column c.
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
+  int n = N;
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
+    if (n > 1) {
+      const int h = n / 2;
+      const bool hi = (lane & off) != 0;
 #pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = hi ? v[i] : v[i + off];
-      const float keep = hi ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < h) {
+          const float send = hi ? v[i] : v[i + h];
+          const float keep = hi ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
     }
   }
   return v[0];
@@ -91,53 +103,64 @@ struct BwdArgs {
   } while (0)
 
 // Addressing of one tile row (thread tid < TM owns row tid): output row and, per K-block, the source
-// row offset.  The gather-index loads are issued here and consumed when the offsets are stored
-// (bwd_row_store), so their latency hides behind whatever runs in between.
+// row.  The gather-index loads are issued here (bwd_row_addr) and their values are first touched
+// when the offsets are computed and stored (bwd_row_store, a phase later), so that the load
+// latency hides behind whatever runs in between instead of stalling the top of the tile.
 struct RowAddr {
   int32_t orow;
-  uint32_t off[P4C_MAX_SRC];
+  int32_t b;                   // sample of the row
+  int32_t idx[P4C_MAX_SRC];    // source row per K-block (gathered or identity)
 };
 __device__ __forceinline__ RowAddr bwd_row_addr(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
                                                 long long total_rows, int tid) {
   RowAddr a;
   a.orow = -1;
+  a.b = 0;
 #pragma unroll
-  for (int k = 0; k < P4C_MAX_SRC; ++k) a.off[k] = kNoRow;
+  for (int k = 0; k < P4C_MAX_SRC; ++k) a.idx[k] = 0;
   const long long g = tile_row0 + tid;
   if (tid < TM && g < total_rows) {
     const long long b = g / m.rows;
     const int rr = static_cast<int>(g - b * m.rows);
+    a.b = static_cast<int32_t>(b);
     a.orow = static_cast<int32_t>(b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr);
 #pragma unroll
     for (int k = 0; k < P4C_MAX_SRC; ++k) {
       if (k < kb.nblk) {
-        const p4c_src_t& src = m.src[kb.src[k]];
-        const long long idx = src.index ? static_cast<long long>(src.index[rr]) : static_cast<long long>(rr);
-        a.off[k] = static_cast<uint32_t>((b * src.batch_stride + idx * src.ld + kb.col0[k]) >> 3);
+        const int32_t* ix = m.src[kb.src[k]].index;
+        a.idx[k] = ix ? __ldg(ix + rr) : rr;
       }
     }
   }
   return a;
 }
-__device__ __forceinline__ void bwd_row_store(const RowAddr& a, int nblk, uint32_t (*row_off)[TM], int tid) {
+__device__ __forceinline__ void bwd_row_store(const RowAddr& a, const p4c_mlp_t& m, const KBlocks& kb,
+                                              uint32_t (*row_off)[TM], int tid) {
   if (tid >= TM) return;
 #pragma unroll
   for (int k = 0; k < P4C_MAX_SRC; ++k)
-    if (k < nblk) row_off[k][tid] = a.off[k];
+    if (k < kb.nblk) {
+      const p4c_src_t& src = m.src[kb.src[k]];
+      row_off[k][tid] = a.orow < 0 ? kNoRow
+                                   : static_cast<uint32_t>((static_cast<long long>(a.b) * src.batch_stride +
+                                                            static_cast<long long>(a.idx[k]) * src.ld + kb.col0[k]) >> 3);
+    }
 }
 
 // next tile's saved pre-activation rows -> the (free) A1 tile, 16-byte chunks, coalesced
+template <int NT>
 __device__ __forceinline__ void bwd_h1_prefetch(const __nv_bfloat16* h1p, const int32_t* orow, uint8_t* A1, int tid) {
   const uint32_t a1 = smem_u32(A1);
 #pragma unroll
-  for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
-    const int idx = i * NTHREADS + tid;
+  for (int i = 0; i < (TM * 8) / NT; ++i) {
+    const int idx = i * NT + tid;
     const int r = idx >> 3, j = idx & 7;
     const long long o = orow[r];
     cp_async16(a1 + sw128_offset(r, j), o >= 0 ? h1p + o * HID + j * 8 : h1p, o >= 0 ? 16u : 0u);
   }
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" : : "l"(p)); }
+template <int NT>
 __device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const KBlocks& kb, const uint32_t (*row_off)[TM],
                                            uint8_t* xbase, int tid) {
   for (int k = 0; k < kb.nblk; ++k) {
@@ -145,8 +168,8 @@ __device__ __forceinline__ void bwd_gather(const p4c_mlp_t& m, const KBlocks& kb
     const uint32_t xs = smem_u32(xbase + k * BLK);
     const int nch = kb.nchunks[k];
 #pragma unroll
-    for (int i = 0; i < (TM * 8) / NTHREADS; ++i) {
-      const int idx = i * NTHREADS + tid;
+    for (int i = 0; i < (TM * 8) / NT; ++i) {
+      const int idx = i * NT + tid;
       const int r = idx >> 3, j = idx & 7;
       if (j < nch) {
         const uint32_t off = row_off[k][r];
@@ -167,7 +190,11 @@ __host__ __device__ inline size_t bwd_smem_bytes(int nblk, int ndx) {
   return static_cast<size_t>(nblk + 2) * BLK + static_cast<size_t>(2 + ndx) * WBLK + ONES_BYTES + sizeof(BwdCtl);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_constant__ BwdArgs args) {
+template <int TPR>
+__global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_constant__ BwdArgs args) {
+  constexpr int NTHREADS = TM * TPR;  // TPR threads per tile row
+  constexpr int CPT = HID / TPR;      // columns per thread
+  constexpr int NJ = CPT / 8;         // 16-byte chunks per thread
   extern __shared__ unsigned char smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const p4c_mlp_t& m = args.m;
@@ -185,8 +212,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   BwdCtl& C = *reinterpret_cast<BwdCtl*>(ONES + ONES_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column half
-  const int row = quad * 32 + lane, col0 = hsel * 32;
+  const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column group
+  const int row = quad * 32 + lane, col0 = hsel * CPT;
+  const int quad_bar = 1 + quad;  // named barrier of the TPR warps that share these rows
   const long long total_rows = static_cast<long long>(m.rows) * m.batch;
   const long long ntiles = (total_rows + TM - 1) / TM;
   const int OUT = m.out_features;
@@ -277,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   {
     const RowAddr ra = bwd_row_addr(m, kb, tile * TM, total_rows, tid);  // graph constants only
     if (tid < TM) C.orow[0][tid] = ra.orow;
-    bwd_row_store(ra, nblk, C.row_off, tid);
+    bwd_row_store(ra, m, kb, C.row_off, tid);
   }
   pdl_wait();  // the previous kernel's outputs are complete and visible
   __syncthreads();
@@ -285,9 +313,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     const int it = 0;
     P4C_BWD_TRACE(2);
   }
-  bwd_h1_prefetch(h1p, C.orow[0], A1, tid);
+  bwd_h1_prefetch<NTHREADS>(h1p, C.orow[0], A1, tid);
   cp_async_commit();  // group 1: h1 of the first tile
-  bwd_gather(m, kb, C.row_off, Xs, tid);
+  bwd_gather<NTHREADS>(m, kb, C.row_off, Xs, tid);
   cp_async_commit();  // group 2: X of the first tile
   // commit order from here on: ..., X(t), h1(t+1), X(t+1), ...: wait<1> at the top of tile t leaves
   // X(t) in flight, wait<1> before G4 leaves h1(t+1) in flight.
@@ -309,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
     // addressing of the next tile: index loads issued now, consumed in phase f
-    RowAddr nra;
+    RowAddr nra = {};
     nra.orow = -1;
     if (next < ntiles) {
       nra = bwd_row_addr(m, kb, next * TM, total_rows, tid);
@@ -332,13 +360,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         dy_row = dya + bb * g.dy_a_batch_stride + ia * OUT;
       }
     }
-    uint4 dyr[4];
-    uint4 dybr[4];
+    uint4 dyr[NJ];
+    uint4 dybr[NJ];
     float2 lnst = make_float2(0.f, 0.f);  // (mean, rstd)
     const bool wide = OUT == HID;
     if (wide) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         dyr[j] = orow >= 0 ? *reinterpret_cast<const uint4*>(dy_row + col0 + j * 8) : make_uint4(0, 0, 0, 0);
         dybr[j] = (orow >= 0 && dyb) ? *reinterpret_cast<const uint4*>(dyb + orow * HID + col0 + j * 8)
                                      : make_uint4(0, 0, 0, 0);
@@ -346,23 +374,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     }
     if (ln && orow >= 0) lnst = *reinterpret_cast<const float2*>(g.stats + 2 * orow);
 
-    // h1 half-row from the A1 tile -> registers (packed bf16); a1 = SiLU(h1) written back in place
-    uint4 h1r[4];
+    // h1 part-row from the A1 tile: a1 = SiLU(h1) written back in place, SiLU'(h1) kept in
+    // registers (packed bf16) for phase e -- one sigmoid (one MUFU op) serves both
+    uint4 h1r[NJ];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       uint4* slot = reinterpret_cast<uint4*>(A1 + sw128_offset(row, (col0 >> 3) + j));
-      h1r[j] = *slot;
-      float h[8];
-      unpack8(h1r[j], h);
+      float h[8], gs[8];
+      unpack8(*slot, h);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+      for (int q = 0; q < 8; ++q) {
+        const float sg = fast_sigmoid(h[q]);
+        gs[q] = fmaf(sg, fmaf(-h[q], sg, h[q]), sg);  // s (1 + h (1 - s))
+        h[q] *= sg;
+      }
       *slot = pack8(h);
+      h1r[j] = pack8(gs);
     }
     // dy half-row -> packed bf16 registers (dy_a scaled, + dy_b)
     if (wide) {
       if (dy_sc != 1.f || dyb) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           float d[8], e[8];
           unpack8(dyr[j], d);
           unpack8(dybr[j], e);
@@ -373,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int c0 = col0 + j * 8;
         float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (orow >= 0) {
@@ -412,12 +445,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       P4C_BWD_TRACE(5);
       // ---- c. LayerNorm backward: xhat from the recomputed h2, row sums exchanged between the
       //         two threads of a row, then dh2 (kept in dyr), dgamma / dbeta column sums
-      float xh[32];
-      tmem_ld32(tmem_row + COL_SCRATCH, xh);
+      float xh[CPT];
+      tmem_ld<CPT>(tmem_row + COL_SCRATCH, xh);
       tmem_ld_wait();
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         float d[8];
         unpack8(dyr[j], d);
 #pragma unroll
@@ -429,16 +462,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
           s2 = fmaf(dxh, xh[j * 8 + q], s2);
         }
       }
-      C.ln_part[hsel][row] = make_float2(s1, s2);
-      __syncthreads();
+      // row sums over the TPR threads of a row (same association order in every thread); only the
+      // TPR warps that share the rows synchronise (named barrier)
+      if (TPR == 4) {
+        if (hsel >= 2) C.ln_part[hsel - 2][row] = make_float2(s1, s2);
+        asm volatile("bar.sync %0, %1;" : : "r"(quad_bar), "n"(32 * TPR) : "memory");
+        if (hsel < 2) {
+          const float2 o = C.ln_part[hsel][row];
+          C.ln_part[hsel][row] = make_float2(s1 + o.x, s2 + o.y);
+        }
+      } else {
+        C.ln_part[hsel][row] = make_float2(s1, s2);
+      }
+      asm volatile("bar.sync %0, %1;" : : "r"(quad_bar), "n"(32 * TPR) : "memory");
       {
         const float2 lo = C.ln_part[0][row], hi = C.ln_part[1][row];
         s1 = (lo.x + hi.x) * (1.0f / HID);
         s2 = (lo.y + hi.y) * (1.0f / HID);
       }
-      float t1[32];
+      {  // dbeta contribution: column sums of dy (before dyr is overwritten with dh2)
+        float t1[CPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) unpack8(dyr[j], t1 + j * 8);
+        vacc[1] += warp_colsum<CPT>(t1, lane);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
         float d[8], o[8];
         unpack8(dyr[j], d);
 #pragma unroll
@@ -448,16 +497,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
           const float dxh = d[q] * C.gamma[c];
           o[q] = rstd * (dxh - s1 - x * s2);
           xh[j * 8 + q] = d[q] * x;  // dgamma contribution
-          t1[j * 8 + q] = d[q];      // dbeta contribution
         }
         dyr[j] = pack8(o);  // dyr now holds dh2
       }
-      vacc[0] += warp_colsum32(xh, lane);
-      vacc[1] += warp_colsum32(t1, lane);
+      vacc[0] += warp_colsum<CPT>(xh, lane);
     }
     // dh2 -> DH tile (db2 = its column sums: ONES lanes of G3)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
+    for (int j = 0; j < NJ; ++j) *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -484,20 +531,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     tc_fence_after();
     P4C_BWD_TRACE(7);
     // A1 is free (G1, G3 complete): the next tile's h1 rows start to stream in
-    if (next < ntiles) bwd_h1_prefetch(h1p, C.orow[p ^ 1], A1, tid);
+    if (next < ntiles) bwd_h1_prefetch<NTHREADS>(h1p, C.orow[p ^ 1], A1, tid);
     cp_async_commit();
 
     // ---- e. dh1 = da1 * SiLU'(h1): db1 sums, global store, DH tile (overwrites dh2)
     {
-      float v[32];
-      tmem_ld32(tmem_row + COL_SCRATCH, v);
+      float v[CPT];
+      tmem_ld<CPT>(tmem_row + COL_SCRATCH, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         float h[8];
-        unpack8(h1r[j], h);
+        unpack8(h1r[j], h);  // SiLU'(h1)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * fast_silu_grad(h[q]) : 0.f;
+        for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * h[q] : 0.f;
         const uint4 packed = pack8(v + j * 8);
         *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = packed;
         if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + col0 + j * 8) = packed;
@@ -541,7 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     // meanwhile: next tile's source offsets (index loads issued at the top of this tile) and L2
     // prefetch of its identity-indexed per-row inputs
     if (next < ntiles) {
-      bwd_row_store(nra, nblk, C.row_off, tid);
+      bwd_row_store(nra, m, kb, C.row_off, tid);
       const long long no = C.orow[p ^ 1][row];
       if (no >= 0) {
         if (args.dy_mode == 2) prefetch_l2(dya + no * OUT + col0);
@@ -553,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
     tc_fence_after();
     P4C_BWD_TRACE(10);
     __syncthreads();  // next row_off visible; X is free (DH still feeds a possible second dX)
-    if (next < ntiles) bwd_gather(m, kb, C.row_off, Xs, tid);
+    if (next < ntiles) bwd_gather<NTHREADS>(m, kb, C.row_off, Xs, tid);
     cp_async_commit();
 
     // ---- g. dX stores (one or two identity-indexed sources)
@@ -579,12 +626,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
       const int ld = g.dx_ld[s];
       const int nch = kb.nchunks[blk];
       const bool add_dy = (blk == 0 && g.dx0_add_dy != 0);
-      float v[32];
-      tmem_ld32(tmem_row + COL_SCRATCH, v);
+      float v[CPT];
+      tmem_ld<CPT>(tmem_row + COL_SCRATCH, v);
       tmem_ld_wait();
       if (orow >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           float* o = v + j * 8;
           const int c0 = col0 + j * 8;
           if ((c0 >> 3) >= nch) continue;  // beyond the (padded) width of this block
@@ -639,28 +686,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
         dstC = pvec + HID + col0;  // db2
       }
     }
-    float4 eA[8], eB[8], eC[8];
+    constexpr int NQ = CPT / 4;
+    float4 eA[NQ], eB[NQ], eC[NQ];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       eA[q] = (padd && dstA) ? *reinterpret_cast<const float4*>(dstA + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
       eB[q] = (padd && dstB) ? *reinterpret_cast<const float4*>(dstB + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
       eC[q] = (padd && dstC) ? *reinterpret_cast<const float4*>(dstC + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    auto put32 = [&](float* dst, const float (&v)[32], const float4 (&e)[8]) {
+    auto put32 = [&](float* dst, const float (&v)[CPT], const float4 (&e)[NQ]) {
       if (!dst) return;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < NQ; ++q)
         *reinterpret_cast<float4*>(dst + 4 * q) =
             make_float4(v[4 * q] + e[q].x, v[4 * q + 1] + e[q].y, v[4 * q + 2] + e[q].z, v[4 * q + 3] + e[q].w);
     };
-    float v[32];
-    tmem_ld32(tmem_row + COL_DW1A, v);  // dW1[k][c] for K-blocks 0,1 (TMEM lane = 64 * block + k)
+    float v[CPT];
+    tmem_ld<CPT>(tmem_row + COL_DW1A, v);  // dW1[k][c] for K-blocks 0,1 (TMEM lane = 64 * block + k)
     tmem_ld_wait();
     put32(dstA, v, eA);
-    tmem_ld32(tmem_row + COL_DW1B, v);
+    tmem_ld<CPT>(tmem_row + COL_DW1B, v);
     tmem_ld_wait();
     put32(dstB, v, eB);
-    tmem_ld32(tmem_row + COL_DW2, v);
+    tmem_ld<CPT>(tmem_row + COL_DW2, v);
     tmem_ld_wait();
     put32(dstC, v, eC);
   }
@@ -674,7 +722,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) mlp2_tc_bwd_kernel(const __grid_c
   for (int v = 0; v < 2; ++v) red[warp][v][lane] = vacc[v];
   __syncthreads();
   if (tid < HID) {
-    const int w0 = (tid >> 5) * 4, l = tid & 31;  // column tid lives in warps w0..w0+3 (same hsel)
+    // column tid lives in the warps w0..w0+3 of its column group, lane l (see warp_colsum)
+    const int w0 = (tid / CPT) * 4, l = (tid % CPT) * (32 / CPT);
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const float sum = (red[w0][v][l] + red[w0 + 1][v][l]) + (red[w0 + 2][v][l] + red[w0 + 3][v][l]);
@@ -731,6 +780,19 @@ int tc_backward_grid(const p4c_mlp_t* m) {
   return static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
 }
 
+// threads per tile row of the backward kernel: 2 (default) or 4 (P4C_BWD_TPR / p4c_set_bwd_tpr).
+// Measured on B200 (profiles/r01h_bwd_shapes.txt): the 4-threads-per-row shape (32 warps per SM at 64
+// registers) is ~8 % SLOWER on the large calls -- the kernel is bound by its per-tile chain of
+// proxy fences (fence.proxy.async = MEMBAR.ALL.CTA in SASS) and LDGSTS issue, not by warp count.
+static int g_bwd_tpr = 0;
+static int bwd_threads_per_row() {
+  if (g_bwd_tpr == 0) {
+    const char* e = getenv("P4C_BWD_TPR");
+    g_bwd_tpr = (e && atoi(e) == 4) ? 4 : 2;
+  }
+  return g_bwd_tpr;
+}
+
 int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st) {
   using namespace tc;
   BwdArgs a;
@@ -762,18 +824,23 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
     }
   }
   const size_t smem = bwd_smem_bytes(a.kb.nblk, a.ndx) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp2_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int tpr = bwd_threads_per_row();
+  auto kernel = tpr == 4 ? mlp2_tc_bwd_kernel<4> : mlp2_tc_bwd_kernel<2>;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[tpr == 4]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mlp_backward(tc): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return P4C_ECUDA;
     }
-    configured = smem;
+    configured[tpr == 4] = smem;
   }
-  launch_pdl(mlp2_tc_bwd_kernel, dim3(tc_backward_grid(m)), dim3(NTHREADS), smem, st, a);
+  launch_pdl(kernel, dim3(tc_backward_grid(m)), dim3(TM * tpr), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_backward(tc)");
   return P4C_OK;
 }
 
 }  // namespace p4c
+
+extern "C" void p4c_set_bwd_tpr(int tpr) { p4c::g_bwd_tpr = tpr == 4 ? 4 : 2; }
+extern "C" int p4c_get_bwd_tpr(void) { return p4c::bwd_threads_per_row(); }

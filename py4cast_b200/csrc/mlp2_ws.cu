@@ -81,20 +81,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // wait with back-off (role warps wait for microseconds; a hot spin would steal issue slots from
 // the epilogue warps).  Traps after ~seconds instead of hanging the GPU on a protocol error.
-template <int SLEEP_NS>
+// RELAXED = true: no acquire fence (which would first drain the thread's outstanding global stores /
+// cp.async copies): for waits whose consumer is ordered by tcgen05.fence::after_thread_sync (TMEM
+// reads after a tcgen05.commit) or that only guard the re-use of a buffer (producer: stage free).
+template <int SLEEP_NS, bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
+    if (RELAXED) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    }
     if (done) return;
     __nanosleep(SLEEP_NS);
     if (spin > (1u << 24)) __trap();
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         }
       }
       load_indices(t + 1);
-      if (n > 0) mbar_wait_backoff<96>(&S.x_empty[s], (n - 1) & 1u);
+      if (n > 0) mbar_wait_backoff<96, true>(&S.x_empty[s], (n - 1) & 1u);
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
         if (k < nblk) {
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const uint32_t b = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(grow), a.div_magic));
         orow = static_cast<int32_t>(b * full + (grow - b * rows));
       }
-      mbar_wait_backoff<64>(&S.d1_full[grp], nn & 1u);
+      mbar_wait_backoff<64, true>(&S.d1_full[grp], nn & 1u);
       tc_fence_after();
       // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
       uint4 res[4];
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       if (lane == 0) mbar_arrive(&S.a2_full[grp]);
 
       // ---- epilogue 2
-      mbar_wait_backoff<64>(&S.d2_full[grp], nn & 1u);
+      mbar_wait_backoff<64, true>(&S.d2_full[grp], nn & 1u);
       tc_fence_after();
       float y[32];
       tmem_ld32(tm_d2, y);

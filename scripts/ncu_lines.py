@@ -51,7 +51,9 @@ for l in lines:
         try: agg[k] += int(l[5][k])
         except (ValueError, KeyError): pass
 print("stalls:", ", ".join(f"{k[6:]}={v*100//max(1,sum(agg.values()))}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
-for f, n, src, s, i, d in sorted(lines, key=lambda l: -l[4])[:top]:
+import os
+skey = 3 if os.environ.get("SORT") == "smp" else 4
+for f, n, src, s, i, d in sorted(lines, key=lambda l: -l[skey])[:top]:
     st = sorted(((int(d[k]) if d.get(k, "").isdigit() else 0, k[6:]) for k in stall_keys), reverse=True)[:3]
     print(f"{s*100/tot_s:5.1f}% smp {i*100/tot_i:5.1f}% ins  {f}:{n:<4d} {src[:64]:64s} {' '.join(f'{k}:{v}' for v,k in st if v)}")
 # ---- phase totals (file, first line, last line, label) given as extra args "file:lo-hi=label"
