@@ -246,7 +246,8 @@ def kernel_roofline(lm, info, cfg, dev):
     # activations written (h1: s*d*E, LN stats: 8*E) + index bytes (8*E) + the output: s*d*N_rec
     # aggregated rows (fused) or s*d*E messages (unfused)
     bytes_edge = B * (s * d * (Ns + Nr + E) + s * d * E + 8 * E + (s * d * Nr if fused else s * d * E)) + 8 * E
-    name = "mlp2_tc_fwd_kernel (m2g edge MLP: gather+MLP+LN" + ("+aggregate)" if fused else ")")
+    name = ("mlp2_ws_fwd_kernel" if fused else "mlp2_tc_fwd_kernel") + " (m2g edge MLP: gather+MLP+LN" + (
+        "+aggregate)" if fused else ")")
     out.append({"kernel": name, "bytes": bytes_edge, "seconds": t})
     if not fused:
         t = timeit(lambda: ops.segment_sum(msg, gi.by_rec, B))
@@ -261,9 +262,8 @@ def kernel_roofline(lm, info, cfg, dev):
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if fused and os.path.isfile(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("batch") == B and (info.grid_shape if hasattr(info, "grid_shape") else None) in (None, (512, 640)) \
-                and E == 1310720:
+        tj = json.load(open(tpath)).get("by_batch", {}).get(str(B))
+        if tj and (info.grid_shape if hasattr(info, "grid_shape") else None) in (None, (512, 640)) and E == 1310720:
             traffic, traffic_src = tj.get("m2g_edge_fwd_dram_bytes_per_launch"), tj.get("source")
     roof = {
         "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -94,6 +94,7 @@ struct BwdArgs {
   // index and batch stride as K-block `dy_blk` (its row offset is reused: no index round trip),
   // 2 = identity rows laid out like the outputs (dy_a + orow * out_features)
   int dy_mode, dy_blk;
+  int ablate;        // developer aid (P4C_BWD_ABLATE, timing experiments only: results are WRONG when non-zero)
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's first tile, slots 16..31
 };
 #define P4C_BWD_TRACE(i)                                                             \
@@ -120,7 +121,10 @@ __device__ __forceinline__ RowAddr bwd_row_addr(const p4c_mlp_t& m, const KBlock
   for (int k = 0; k < P4C_MAX_SRC; ++k) a.idx[k] = 0;
   const long long g = tile_row0 + tid;
   if (tid < TM && g < total_rows) {
-    const long long b = g / m.rows;
+    // 32-bit division whenever the row count allows it (the 64-bit one is a ~100-instruction routine)
+    const long long b = total_rows <= 0x7fffffffll
+                            ? static_cast<long long>(static_cast<uint32_t>(g) / static_cast<uint32_t>(m.rows))
+                            : g / m.rows;
     const int rr = static_cast<int>(g - b * m.rows);
     a.b = static_cast<int32_t>(b);
     a.orow = static_cast<int32_t>(b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr);
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
   bwd_gather<NTHREADS>(m, kb, C.row_off, Xs, tid);
   cp_async_commit();  // group 2: X of the first tile
   // commit order from here on: ..., X(t), h1(t+1), X(t+1), ...: wait<1> at the top of tile t leaves
-  // X(t) in flight, wait<1> before G4 leaves h1(t+1) in flight.
+  // X(t) in flight; before G4 of tile t only X(t) is outstanding (wait<0>), h1(t+1) is issued after it.
 
   for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
     const int p = it & 1;
@@ -333,7 +337,8 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     P4C_BWD_TRACE(3);
-    const long long orow = C.orow[p][row];  // -1 = row beyond the problem
+    const long long orow_true = C.orow[p][row];  // -1 = row beyond the problem
+    const long long orow = (args.ablate & 4) ? -1 : orow_true;  // (ablation: no per-row global reads / writes)
     const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
     // addressing of the next tile: index loads issued now, consumed in phase f
@@ -428,10 +433,10 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       const float mean = lnst.x, rstd = lnst.y;
       // ---- b. G1: h2 = a1 W2^T -> scratch
       P4C_BWD_TRACE(4);
-      fence_proxy_async();
+      if (!(args.ablate & 32)) fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 && !(args.ablate & 8)) {
         tc_fence_after();
         const uint32_t aa = smem_u32(A1), wa = smem_u32(W2s);
 #pragma unroll
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
                       make_desc_sw128(wa + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
         mma_commit(&C.mbar[0]);
       }
-      mbar_wait(&C.mbar[0], parity);
+      if (!(args.ablate & 8)) mbar_wait(&C.mbar[0], parity);
       tc_fence_after();
       P4C_BWD_TRACE(5);
       // ---- c. LayerNorm backward: xhat from the recomputed h2, row sums exchanged between the
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       tmem_ld<CPT>(tmem_row + COL_SCRATCH, xh);
       tmem_ld_wait();
       float s1 = 0.f, s2 = 0.f;
+      const float nmr = -mean * rstd;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         float d[8];
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int c = col0 + j * 8 + q;
-          xh[j * 8 + q] = (xh[j * 8 + q] + C.b2[c] - mean) * rstd;
+          xh[j * 8 + q] = fmaf(xh[j * 8 + q] + C.b2[c], rstd, nmr);  // (h2 - mean) * rstd
           const float dxh = d[q] * C.gamma[c];
           s1 += dxh;
           s2 = fmaf(dxh, xh[j * 8 + q], s2);
@@ -480,11 +486,12 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
         s1 = (lo.x + hi.x) * (1.0f / HID);
         s2 = (lo.y + hi.y) * (1.0f / HID);
       }
+      const float rs1 = -s1 * rstd, rs2 = -s2 * rstd;
       {  // dbeta contribution: column sums of dy (before dyr is overwritten with dh2)
         float t1[CPT];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) unpack8(dyr[j], t1 + j * 8);
-        vacc[1] += warp_colsum<CPT>(t1, lane);
+        if (!(args.ablate & 16)) vacc[1] += warp_colsum<CPT>(t1, lane);
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -495,23 +502,23 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
           const int c = col0 + j * 8 + q;
           const float x = xh[j * 8 + q];
           const float dxh = d[q] * C.gamma[c];
-          o[q] = rstd * (dxh - s1 - x * s2);
+          o[q] = fmaf(x, rs2, fmaf(dxh, rstd, rs1));  // rstd * (dxh - s1 - x * s2)
           xh[j * 8 + q] = d[q] * x;  // dgamma contribution
         }
         dyr[j] = pack8(o);  // dyr now holds dh2
       }
-      vacc[0] += warp_colsum<CPT>(xh, lane);
+      if (!(args.ablate & 16)) vacc[0] += warp_colsum<CPT>(xh, lane); else vacc[0] += xh[0] + xh[CPT - 1];
     }
     // dh2 -> DH tile (db2 = its column sums: ONES lanes of G3)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = dyr[j];
-    fence_proxy_async();
+    if (!(args.ablate & 32)) fence_proxy_async();
     tc_fence_before();
     __syncthreads();
 
     // ---- d. G2: da1 = dh2 W2 -> scratch ;  G3: dW2 += a1^T dh2
     P4C_BWD_TRACE(6);
-    if (tid == 0) {
+    if (tid == 0 && !(args.ablate & 8)) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), wt = smem_u32(W2T), a1 = smem_u32(A1);
 #pragma unroll
@@ -527,14 +534,10 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
       mma_commit(&C.mbar[1]);
     }
-    mbar_wait(&C.mbar[1], parity);
+    if (!(args.ablate & 8)) mbar_wait(&C.mbar[1], parity);
     tc_fence_after();
     P4C_BWD_TRACE(7);
-    // A1 is free (G1, G3 complete): the next tile's h1 rows start to stream in
-    if (next < ntiles) bwd_h1_prefetch<NTHREADS>(h1p, C.orow[p ^ 1], A1, tid);
-    cp_async_commit();
-
-    // ---- e. dh1 = da1 * SiLU'(h1): db1 sums, global store, DH tile (overwrites dh2)
+    // ---- e. dh1 = da1 * SiLU'(h1) -> DH tile (overwrites dh2; db1 = its column sums, ONES lanes of G4)
     {
       float v[CPT];
       tmem_ld<CPT>(tmem_row + COL_SCRATCH, v);
@@ -547,18 +550,20 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
         for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * h[q] : 0.f;
         const uint4 packed = pack8(v + j * 8);
         *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = packed;
-        if (dh1_out && orow >= 0) *reinterpret_cast<uint4*>(dh1_out + orow * HID + col0 + j * 8) = packed;
       }
     }
     P4C_BWD_TRACE(8);
-    cp_async_wait<1>();  // X(tile) landed (issued one tile ago); h1(next) stays in flight
-    fence_proxy_async();
+    // X(tile) landed (issued one tile ago).  Nothing else of this thread is in flight here: the
+    // proxy fence (MEMBAR.ALL.CTA in SASS) drains every outstanding global access of the thread, so
+    // the dh1 stores and the next tile's h1 prefetch are issued AFTER it, under the G4 / G5 MMAs.
+    cp_async_wait<0>();
+    if (!(args.ablate & 32)) fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     P4C_BWD_TRACE(9);
 
     // ---- f. G4: dW1 += X^T dh1 ; G5(0): dX = dh1 W1[:, s0]
-    if (tid == 0) {
+    if (tid == 0 && !(args.ablate & 8)) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), xa = smem_u32(Xs);
       {
@@ -585,8 +590,17 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
       mma_commit(&C.mbar[2]);
     }
-    // meanwhile: next tile's source offsets (index loads issued at the top of this tile) and L2
-    // prefetch of its identity-indexed per-row inputs
+    // meanwhile: dh1 to global memory (this thread's own chunks, read back from the DH tile), the
+    // next tile's h1 rows into the A1 tile (free: G1, G3 complete), its source offsets (index
+    // loads issued at the top of this tile) and L2 prefetch of its identity-indexed per-row inputs
+    if (dh1_out && orow >= 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        *reinterpret_cast<uint4*>(dh1_out + orow * HID + col0 + j * 8) =
+            *reinterpret_cast<const uint4*>(DH + sw128_offset(row, (col0 >> 3) + j));
+    }
+    if (next < ntiles && !(args.ablate & 2)) bwd_h1_prefetch<NTHREADS>(h1p, C.orow[p ^ 1], A1, tid);
+    cp_async_commit();
     if (next < ntiles) {
       bwd_row_store(nra, m, kb, C.row_off, tid);
       const long long no = C.orow[p ^ 1][row];
@@ -596,11 +610,11 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
         if (ln && hsel == 0) prefetch_l2(g.stats + 2 * no);
       }
     }
-    mbar_wait(&C.mbar[2], parity);
+    if (!(args.ablate & 8)) mbar_wait(&C.mbar[2], parity);
     tc_fence_after();
     P4C_BWD_TRACE(10);
     __syncthreads();  // next row_off visible; X is free (DH still feeds a possible second dX)
-    if (next < ntiles) bwd_gather<NTHREADS>(m, kb, C.row_off, Xs, tid);
+    if (next < ntiles && !(args.ablate & 1)) bwd_gather<NTHREADS>(m, kb, C.row_off, Xs, tid);
     cp_async_commit();
 
     // ---- g. dX stores (one or two identity-indexed sources)
@@ -806,6 +820,14 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
   a.dy_mode = 0;
   a.dy_blk = 0;
   a.trace = tc_get_trace();
+  {
+    static int ablate = -1;
+    if (ablate < 0) {
+      const char* e = getenv("P4C_BWD_ABLATE");
+      ablate = e ? atoi(e) : 0;
+    }
+    a.ablate = ablate;
+  }
   const long long full = m->full_rows > 0 ? m->full_rows : m->rows;
   if (!g->dy_a_scale) {
     if (!g->dy_a_index && (m->batch == 1 || g->dy_a_batch_stride == full * m->out_features)) {

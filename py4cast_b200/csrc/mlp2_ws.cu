@@ -352,16 +352,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      // ---- pass 2: coalesced h1 store, SiLU in place (lane -> chunk j of row 8 i + sub of this warp)
+      // ---- pass 2 (lane -> chunk j of row 8 i + sub of this warp): SiLU in place -> A2 operand of G2,
+      //      hand the tile to the MMA warp, THEN the coalesced store of h1 (saved activation): the
+      //      proxy fence (MEMBAR.ALL.CTA in SASS) would otherwise wait for the stores' acknowledgement
+      //      on the critical path to G2
+      uint4 hb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 8 * i + sub;
-        const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
         const uint32_t addr = a2 + sw128_offset(quad * 32 + r, j);
-        const uint4 hb = lds128(addr);
-        if (save_h1 && orr >= 0) *reinterpret_cast<uint4*>(save_h1 + static_cast<long long>(orr) * WS_HID + j * 8) = hb;
+        hb[i] = lds128(addr);
         float h[8];
-        ws_unpack8(hb, h);
+        ws_unpack8(hb[i], h);
 #pragma unroll
         for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
         sts128(addr, ws_pack8(h));
@@ -369,6 +371,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.a2_full[grp]);
+      if (save_h1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int32_t orr = __shfl_sync(0xffffffffu, orow, 8 * i + sub);
+          if (orr >= 0) *reinterpret_cast<uint4*>(save_h1 + static_cast<long long>(orr) * WS_HID + j * 8) = hb[i];
+        }
+      }
 
       // ---- epilogue 2
       mbar_wait_backoff<64, true>(&S.d2_full[grp], nn & 1u);

@@ -13,7 +13,7 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
     tail -3 gpurun_out/$f.log >> $OUT
   done
 fi
-for tpr in 2 4; do
+for tpr in ${TPRS:-2 4}; do
   echo "== P4C_BWD_TPR=$tpr" >> $OUT
   P4C_BWD_TPR=$tpr python scripts/kernel_micro.py --iters 4 --batch 2 2>&1 | tail -2 >> $OUT
   P4C_BWD_TPR=$tpr python scripts/kernel_micro.py --iters 4 --batch 2 --which g2m 2>&1 | tail -2 >> $OUT
