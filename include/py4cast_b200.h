@@ -168,7 +168,7 @@ int p4c_get_cta_reserve(void);
 /* The tensor-core forward has two kernels: a warp-specialised, software-pipelined one (one CTA per
  * SM: producer / MMA / epilogue warps, 3-stage gather ring) for calls of at least `n` 128-row tiles
  * and the monolithic two-CTAs-per-SM kernel below that (and for segment-sum sources, out_features
- * != 64).  Default n = 4 * 148 (environment variable P4C_WS_MIN_TILES); n <= 0 restores the default,
+ * != 64).  Default n = 2 * 148 (environment variable P4C_WS_MIN_TILES); n <= 0 restores the default,
  * a huge n disables the pipelined kernel.  Same results up to fp32 summation order. */
 void p4c_set_ws_min_tiles(int64_t n);
 int64_t p4c_get_ws_min_tiles(void);

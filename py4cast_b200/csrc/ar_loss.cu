@@ -287,11 +287,28 @@ loss_partial_kernel(const float* __restrict__ pred, const float* __restrict__ ta
   if (tid < active) {
     const int f = tid % F, no = tid / F;
     const long long base = bt * (long long)nodes * F;
-    for (int n = n0 + no; n < n1; n += npi) {
+    // four independent chains (fixed association order): four row loads in flight per thread
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    int n = n0 + no;
+    for (; n + 3 * npi < n1; n += 4 * npi) {
+      float pv[4], tv[4], mv[4], iv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long idx = base + (long long)(n + u * npi) * F + f;
+        pv[u] = pred[idx];
+        tv[u] = target[idx];
+        mv[u] = mask ? mask[idx] : 1.0f;
+        iv[u] = interior[n + u * npi];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] += iv[u] * loss_elem(pv[u], tv[u], mv[u], kind);
+    }
+    for (; n < n1; n += npi) {
       const long long idx = base + (long long)n * F + f;
       const float m = mask ? mask[idx] : 1.0f;
-      acc += interior[n] * loss_elem(pred[idx], target[idx], m, kind);
+      a4[0] += interior[n] * loss_elem(pred[idx], target[idx], m, kind);
     }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
   red[tid] = acc;
   __syncthreads();

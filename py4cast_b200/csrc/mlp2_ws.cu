@@ -531,7 +531,7 @@ static long long g_ws_launches = 0;
 static long long ws_min_tiles() {
   if (g_ws_min_tiles < 0) {
     const char* e = getenv("P4C_WS_MIN_TILES");
-    g_ws_min_tiles = (e && atoll(e) > 0) ? atoll(e) : 4ll * kNumSMs;
+    g_ws_min_tiles = (e && atoll(e) > 0) ? atoll(e) : 2ll * kNumSMs;
   }
   return g_ws_min_tiles;
 }
