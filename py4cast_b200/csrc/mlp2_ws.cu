@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         }
       }
       load_indices(t + 1);
-      if (n > 0) mbar_wait_backoff<96, true>(&S.x_empty[s], (n - 1) & 1u);
+      if (n > 0) mbar_wait_backoff<200, true>(&S.x_empty[s], (n - 1) & 1u);
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
         if (k < nblk) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const uint32_t b = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(grow), a.div_magic));
         orow = static_cast<int32_t>(b * full + (grow - b * rows));
       }
-      mbar_wait_backoff<64, true>(&S.d1_full[grp], nn & 1u);
+      mbar_wait_backoff<160, true>(&S.d1_full[grp], nn & 1u);
       tc_fence_after();
       // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
       uint4 res[4];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       }
 
       // ---- epilogue 2
-      mbar_wait_backoff<64, true>(&S.d2_full[grp], nn & 1u);
+      mbar_wait_backoff<160, true>(&S.d2_full[grp], nn & 1u);
       tc_fence_after();
       float y[32];
       tmem_ld32(tm_d2, y);
