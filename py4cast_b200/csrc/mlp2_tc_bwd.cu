@@ -112,22 +112,21 @@ struct RowAddr {
   int32_t b;                   // sample of the row
   int32_t idx[P4C_MAX_SRC];    // source row per K-block (gathered or identity)
 };
-__device__ __forceinline__ RowAddr bwd_row_addr(const p4c_mlp_t& m, const KBlocks& kb, long long tile_row0,
-                                                long long total_rows, int tid) {
+// Tile order: tile T = (row block T / batch, sample T % batch): the samples of one row block run
+// back to back on neighbouring CTAs, so a K-block shared by the batch (static edge embeddings,
+// batch_stride 0: 168 MB for m2g, more than L2) comes from HBM once per step instead of once per sample.
+__device__ __forceinline__ RowAddr bwd_row_addr(const p4c_mlp_t& m, const KBlocks& kb, long long tile, int tid) {
   RowAddr a;
   a.orow = -1;
   a.b = 0;
 #pragma unroll
   for (int k = 0; k < P4C_MAX_SRC; ++k) a.idx[k] = 0;
-  const long long g = tile_row0 + tid;
-  if (tid < TM && g < total_rows) {
-    // 32-bit division whenever the row count allows it (the 64-bit one is a ~100-instruction routine)
-    const long long b = total_rows <= 0x7fffffffll
-                            ? static_cast<long long>(static_cast<uint32_t>(g) / static_cast<uint32_t>(m.rows))
-                            : g / m.rows;
-    const int rr = static_cast<int>(g - b * m.rows);
-    a.b = static_cast<int32_t>(b);
-    a.orow = static_cast<int32_t>(b * (m.full_rows > 0 ? m.full_rows : m.rows) + rr);
+  const uint32_t blk = static_cast<uint32_t>(tile) / static_cast<uint32_t>(m.batch);
+  const int rr = static_cast<int>(blk) * TM + tid;
+  if (tid < TM && rr < m.rows) {
+    const int b = static_cast<int>(static_cast<uint32_t>(tile) - blk * static_cast<uint32_t>(m.batch));
+    a.b = b;
+    a.orow = static_cast<int32_t>(static_cast<long long>(b) * (m.full_rows > 0 ? m.full_rows : m.rows) + rr);
 #pragma unroll
     for (int k = 0; k < P4C_MAX_SRC; ++k) {
       if (k < kb.nblk) {
@@ -219,8 +218,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
   const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column group
   const int row = quad * 32 + lane, col0 = hsel * CPT;
   const int quad_bar = 1 + quad;  // named barrier of the TPR warps that share these rows
-  const long long total_rows = static_cast<long long>(m.rows) * m.batch;
-  const long long ntiles = (total_rows + TM - 1) / TM;
+  const long long ntiles = static_cast<long long>((m.rows + TM - 1) / TM) * m.batch;  // row blocks x samples
   const int OUT = m.out_features;
   const bool ln = m.layer_norm != 0;
   const bool need_w = g.partials_mode != 0;  // deferred reduction: every weight gradient is produced
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
   long long tile = blockIdx.x;
   pdl_launch_dependents();
   {
-    const RowAddr ra = bwd_row_addr(m, kb, tile * TM, total_rows, tid);  // graph constants only
+    const RowAddr ra = bwd_row_addr(m, kb, tile, tid);  // graph constants only
     if (tid < TM) C.orow[0][tid] = ra.orow;
     bwd_row_store(ra, m, kb, C.row_off, tid);
   }
@@ -339,13 +337,12 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
     P4C_BWD_TRACE(3);
     const long long orow_true = C.orow[p][row];  // -1 = row beyond the problem
     const long long orow = (args.ablate & 4) ? -1 : orow_true;  // (ablation: no per-row global reads / writes)
-    const long long grow = tile * TM + row;  // global row (for dy_a indexing)
 
     // addressing of the next tile: index loads issued now, consumed in phase f
     RowAddr nra = {};
     nra.orow = -1;
     if (next < ntiles) {
-      nra = bwd_row_addr(m, kb, next * TM, total_rows, tid);
+      nra = bwd_row_addr(m, kb, next, tid);
       if (tid < TM) C.orow[p ^ 1][tid] = nra.orow;
     }
 
@@ -358,8 +355,9 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       } else if (args.dy_mode == 2) {
         dy_row = dya + orow * OUT;
       } else {
-        const long long bb = grow / m.rows;
-        const int rr = static_cast<int>(grow - bb * m.rows);
+        const uint32_t blk = static_cast<uint32_t>(tile) / static_cast<uint32_t>(m.batch);
+        const long long bb = static_cast<uint32_t>(tile) - blk * static_cast<uint32_t>(m.batch);
+        const int rr = static_cast<int>(blk) * TM + row;
         const long long ia = g.dy_a_index ? static_cast<long long>(g.dy_a_index[rr]) : static_cast<long long>(rr);
         if (g.dy_a_scale) dy_sc = g.dy_a_scale[ia];
         dy_row = dya + bb * g.dy_a_batch_stride + ia * OUT;
@@ -790,7 +788,8 @@ bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g) {
 
 int tc_backward_grid(const p4c_mlp_t* m) {
   const long long total = static_cast<long long>(m->rows) * m->batch;
-  const long long ntiles = (total + tc::TM - 1) / tc::TM;
+  (void)total;
+  const long long ntiles = static_cast<long long>((m->rows + tc::TM - 1) / tc::TM) * m->batch;
   return static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
 }
 

@@ -72,8 +72,12 @@ struct WsArgs {
   float agg_scale;
   int residual_x0;  // out = y + (row of K-block 0)
   int zero_x;
-  unsigned long long div_magic;  // ceil(2^64 / rows): sample = umul64hi(global row, magic)
-  uint32_t total_rows, ntiles, full_rows;
+  // Tile order: tile T = (row block T / batch, sample T % batch), i.e. the samples of one row block are
+  // processed back to back (by neighbouring CTAs at the same time), so that a source shared by the
+  // batch (static edge / mesh embeddings: batch_stride 0) is fetched from HBM once and served to the
+  // other samples from L2 instead of being re-read per sample (m2g edge embedding: 168 MB > L2).
+  unsigned long long div_magic;  // ceil(2^64 / batch): row block = umul64hi(tile, magic)
+  uint32_t batch, ntiles, full_rows;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
   const p4c_mlp_t& m = a.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nblk = a.kb.nblk;
-  const uint32_t total_rows = a.total_rows;
+  const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
   const bool need_x0 = a.residual_x0 || a.out2 != nullptr;
 
@@ -196,10 +200,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     uint32_t b_next = 0, rr_next = 0;
     bool valid_next = false;
     auto load_indices = [&](uint32_t t) {  // gather indices of tile t (graph constants)
-      const uint32_t g = (blockIdx.x + t * gridDim.x) * WS_TM + pw * 32 + lane;
-      valid_next = t < ntl && g < total_rows;
-      b_next = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(g), a.div_magic));
-      rr_next = g - b_next * rows;
+      const uint32_t tile = blockIdx.x + t * gridDim.x;
+      const uint32_t blk = nbatch == 1 ? tile
+                                       : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
+      b_next = tile - blk * nbatch;
+      rr_next = blk * WS_TM + pw * 32 + lane;
+      valid_next = t < ntl && rr_next < rows;
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
         idx_next[k] = static_cast<int32_t>(rr_next);
@@ -318,12 +324,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     pdl_wait();
     for (uint32_t t = grp; t < ntl; t += 2) {
       const uint32_t s = t % WS_NS, nn = t >> 1;
-      const uint32_t grow = (blockIdx.x + t * gridDim.x) * WS_TM + row;
+      const uint32_t tile = blockIdx.x + t * gridDim.x;
+      const uint32_t blk = nbatch == 1 ? tile
+                                       : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
+      const uint32_t rr = blk * WS_TM + row;
       int32_t orow = -1;  // row in the output-like arrays
-      if (grow < total_rows) {
-        const uint32_t b = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(grow), a.div_magic));
-        orow = static_cast<int32_t>(b * full + (grow - b * rows));
-      }
+      if (rr < rows) orow = static_cast<int32_t>((tile - blk * nbatch) * full + rr);
       mbar_wait_backoff<160, true>(&S.d1_full[grp], nn & 1u);
       tc_fence_after();
       // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
@@ -573,10 +579,10 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
   const unsigned long long rows = static_cast<unsigned long long>(m->rows);
-  a.div_magic = rows == 1 ? ~0ull : (~0ull / rows) + 1ull;  // ceil(2^64 / rows) for rows >= 2
-  const long long total = static_cast<long long>(m->rows) * m->batch;
-  a.total_rows = static_cast<uint32_t>(total);
-  a.ntiles = static_cast<uint32_t>((total + WS_TM - 1) / WS_TM);
+  const unsigned long long nb = static_cast<unsigned long long>(m->batch);
+  a.div_magic = nb == 1 ? 0ull : (~0ull / nb) + 1ull;  // ceil(2^64 / batch) for batch >= 2 (batch 1: not used)
+  a.batch = static_cast<uint32_t>(m->batch);
+  a.ntiles = static_cast<uint32_t>((rows + WS_TM - 1) / WS_TM * nb);
   a.full_rows = static_cast<uint32_t>(m->full_rows > 0 ? m->full_rows : m->rows);
   int max_ctas = tc_max_ctas() / 2;
   if (max_ctas < 1) max_ctas = 1;
