@@ -83,6 +83,44 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// ---- packed bf16x2 activation math (two elements per instruction, one MUFU op per pair) -------------
+// P4C_BWD_PACKED_DH1 (default on): dh1 = da1 * SiLU'(h1) as one bf16x2 product per pair (da1 is
+// rounded to bf16 first; the result is bf16 storage anyway).
+// P4C_BWD_PACKED_SILU (default OFF): SiLU and SiLU' of the saved pre-activation evaluated in bf16x2
+// as well.  Measured on B200: another 0.8 % of the step, but the extra rounding of the recomputed a1
+// raises the worst parameter-gradient error of a model rollout from 1.3e-2 to 1.6e-2 (bar: 2e-2),
+// so it stays off.
+#ifndef P4C_BWD_PACKED_DH1
+#define P4C_BWD_PACKED_DH1 1
+#endif
+#ifndef P4C_BWD_PACKED_SILU
+#define P4C_BWD_PACKED_SILU 0
+#endif
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_tanh(uint32_t a) {
+  uint32_t d;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// h (bf16x2) -> a = h * sigmoid(h), g = sigmoid(h) * (1 + h * (1 - sigmoid(h)))
+__device__ __forceinline__ void bf2_silu_and_grad(uint32_t h, uint32_t& a, uint32_t& g) {
+  constexpr uint32_t HALF = 0x3F003F00u, NEG1 = 0xBF80BF80u;  // (0.5, 0.5), (-1, -1)
+  const uint32_t sg = bf2_fma(bf2_tanh(bf2_mul(h, HALF)), HALF, HALF);
+  a = bf2_mul(h, sg);
+  const uint32_t u = bf2_fma(a, NEG1, h);  // h - h * sg
+  g = bf2_fma(sg, u, sg);
+}
+__device__ __forceinline__ uint32_t bf2_from_floats(float lo, float hi) { return pack_bf16x2(lo, hi); }
+
 struct BwdArgs {
   p4c_mlp_t m;
   p4c_mlp_bwd_t g;
@@ -383,6 +421,15 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       uint4* slot = reinterpret_cast<uint4*>(A1 + sw128_offset(row, (col0 >> 3) + j));
+#if P4C_BWD_PACKED_SILU
+      const uint4 hv = *slot;
+      uint4 av;
+      bf2_silu_and_grad(hv.x, av.x, h1r[j].x);
+      bf2_silu_and_grad(hv.y, av.y, h1r[j].y);
+      bf2_silu_and_grad(hv.z, av.z, h1r[j].z);
+      bf2_silu_and_grad(hv.w, av.w, h1r[j].w);
+      *slot = av;
+#else
       float h[8], gs[8];
       unpack8(*slot, h);
 #pragma unroll
@@ -393,6 +440,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       }
       *slot = pack8(h);
       h1r[j] = pack8(gs);
+#endif
     }
     // dy half-row -> packed bf16 registers (dy_a scaled, + dy_b)
     if (wide) {
@@ -542,11 +590,20 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
+#if P4C_BWD_PACKED_DH1
+        uint4 packed = pack8(v + j * 8);  // da1 -> bf16, times SiLU'(h1) in bf16x2
+        packed.x = bf2_mul(packed.x, h1r[j].x);
+        packed.y = bf2_mul(packed.y, h1r[j].y);
+        packed.z = bf2_mul(packed.z, h1r[j].z);
+        packed.w = bf2_mul(packed.w, h1r[j].w);
+        if (orow < 0) packed = make_uint4(0, 0, 0, 0);
+#else
         float h[8];
         unpack8(h1r[j], h);  // SiLU'(h1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[j * 8 + q] = orow >= 0 ? v[j * 8 + q] * h[q] : 0.f;
         const uint4 packed = pack8(v + j * 8);
+#endif
         *reinterpret_cast<uint4*>(DH + sw128_offset(row, (col0 >> 3) + j)) = packed;
       }
     }
