@@ -355,6 +355,21 @@ int p4c_loss_backward(const float* pred, const float* target, const float* mask,
                       int32_t f, int kind, int form, float* dpred, float* dtarget,
                       void* stream);
 
+/* -------------------------------------------------------------------------
+ * External forcings of a sample window (input pipeline).
+ * Replaces reference py4cast/forcingutils.py:61-90 (get_year_hour_forcing) + :93-132
+ * (generate_toa_radiation_forcing) as assembled by datasets/base.py:233-274 (generate_forcings)
+ * and broadcast / concatenated at base.py:509-515: writes channels ch0.. of the
+ * (slots, nodes, ld) fp32 forcing tensor in one pass.
+ *   lat, lon [nodes] degrees; hour [slots] = UTC hour of day of each time slot;
+ *   sin_dec, cos_dec [slots] = sin / cos of the solar declination (radians) of each slot;
+ *   datetime4 [slots][4] = (cos_hour, sin_hour, cos_doy, sin_doy) columns of get_year_hour_forcing,
+ *   or NULL: then only the top-of-atmosphere radiation is written (1 channel instead of 5).
+ * ---------------------------------------------------------------------- */
+int p4c_forcing_fill(const float* lat, const float* lon, const float* hour, const float* sin_dec,
+                     const float* cos_dec, const float* datetime4, int32_t slots, int32_t nodes,
+                     float* out, int32_t ld, int32_t ch0, void* stream);
+
 /* ------------------------------------------------------------------------
  * Optimiser: AdamW on one flat fp32 buffer (reference lightning.py:442-467:
  * torch.optim.AdamW + cosine-with-min-lr schedule with warm-up).

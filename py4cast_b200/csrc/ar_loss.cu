@@ -463,6 +463,34 @@ __global__ void loss_denom_kernel(float num_interior, const int* __restrict__ co
   *denom = num_interior - (count ? (float)*count : 0.f);
 }
 
+// --------------------------------------------------------------------- external forcings
+// The five generated forcing channels of one sample window (reference py4cast/forcingutils.py:61-132,
+// assembled by datasets/base.py:233-274 `generate_forcings` and broadcast over the grid at :509-511):
+// [cos_hour, sin_hour, cos_doy, sin_doy] (per time slot, the same for every pixel) and the
+// top-of-atmosphere solar irradiation max(0, E0 cos(zenith)) with
+//   cos(zenith) = sin(phi) sin(dec) + cos(phi) cos(dec) cos(omega),  omega = 15 (hour + lon/15 - 12) deg,
+// written straight into channels ch0.. of the (slots, nodes, ld) forcing tensor (no per-channel
+// tensors, no expand + cat).  fp32 throughout, like the reference.
+__global__ void forcing_fill_kernel(const float* __restrict__ lat, const float* __restrict__ lon,
+                                    const float* __restrict__ hour, const float* __restrict__ sin_dec,
+                                    const float* __restrict__ cos_dec, const float* __restrict__ dt4,
+                                    int slots, int nodes, float* __restrict__ out, int ld, int ch0) {
+  const float kRad = 0.017453292519943295f;  // float32(pi / 180), what np.radians multiplies by
+  const int t = blockIdx.y;
+  const float hr = hour[t], sd = sin_dec[t], cd = cos_dec[t];
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  if (dt4) { d0 = dt4[4 * t]; d1 = dt4[4 * t + 1]; d2 = dt4[4 * t + 2]; d3 = dt4[4 * t + 3]; }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nodes; n += gridDim.x * blockDim.x) {
+    const float hours_lcl = hr + lon[n] / 15.f;
+    const float omega_rad = (15.f * (hours_lcl - 12.f)) * kRad;
+    const float phi_rad = lat[n] * kRad;
+    const float cos_sza = sinf(phi_rad) * sd + cosf(phi_rad) * cd * cosf(omega_rad);
+    float* o = out + ((long long)t * nodes + n) * ld + ch0;
+    if (dt4) { o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d3; o += 4; }
+    o[0] = fmaxf(0.f, 1366.f * cos_sza);
+  }
+}
+
 // ------------------------------------------------------------------------------- AdamW
 __global__ void adamw_advance_kernel(p4c_adamw_state_t* st, float base_lr, float min_lr,
                                      long long warmup, long long total_steps, float beta1,
@@ -748,5 +776,20 @@ extern "C" int p4c_adamw_step(float* param, const float* grad, float* exp_avg, f
   adamw_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, weight_decay, grad_scale);
   P4C_CHECK_LAUNCH("adamw_step");
+  return P4C_OK;
+}
+
+extern "C" int p4c_forcing_fill(const float* lat, const float* lon, const float* hour, const float* sin_dec,
+                                const float* cos_dec, const float* datetime4, int32_t slots, int32_t nodes,
+                                float* out, int32_t ld, int32_t ch0, void* stream) {
+  P4C_REQUIRE(lat && lon && hour && sin_dec && cos_dec && out, "forcing_fill: null pointer");
+  P4C_REQUIRE(slots > 0 && slots <= 65535 && nodes > 0, "forcing_fill: bad sizes (slots=%d nodes=%d)", slots, nodes);
+  P4C_REQUIRE(ch0 >= 0 && ch0 + (datetime4 ? 5 : 1) <= ld, "forcing_fill: channels %d.. do not fit ld=%d", ch0, ld);
+  int bx = (nodes + 255) / 256;
+  const int cap = (16 * kNumSMs + slots - 1) / slots;
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  forcing_fill_kernel<<<dim3(bx, slots), 256, 0, (cudaStream_t)stream>>>(lat, lon, hour, sin_dec, cos_dec, datetime4,
+                                                                         slots, nodes, out, ld, ch0);
+  P4C_CHECK_LAUNCH("forcing_fill");
   return P4C_OK;
 }

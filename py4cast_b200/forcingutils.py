@@ -1,0 +1,137 @@
+"""
+External forcings (date / hour features and top-of-atmosphere solar radiation) generated on the GPU.
+
+Mirrors reference py4cast/forcingutils.py — same function names, arguments and returned shapes:
+`compute_day_of_years` (:19-33), `compute_hours_of_day` (:36-46),
+`compute_seconds_from_start_of_year` (:49-58), `get_year_hour_forcing` (:61-90),
+`generate_toa_radiation_forcing` (:93-132) — and `generate_forcings` of datasets/base.py:233-274.
+The date arithmetic (a handful of scalars per sample) stays on the host exactly as in the
+reference; the per-pixel part runs in ONE kernel (`p4c_forcing_fill`), which can also write the
+five generated channels straight into their slots of a batch's forcing tensor
+(`fill_external_forcings`) instead of building per-channel tensors that are expanded and
+concatenated afterwards (base.py:509-515).  No CPU fallback: lat / lon must be CUDA tensors.
+"""
+
+from __future__ import annotations
+
+import datetime as dt
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+from .namedtensor import NamedTensor
+
+
+def compute_day_of_years(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
+    """Day of the year of each term (1st of January is 1)."""
+    days = []
+    for term in output_terms:
+        date_tmp = date + term
+        days.append((date_tmp - dt.datetime(date_tmp.year, 1, 1)).days + 1)
+    return np.asarray(days)
+
+
+def compute_hours_of_day(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
+    """Hour of the day (with minutes as a fraction) of each term."""
+    hours = []
+    for term in output_terms:
+        date_tmp = date + term
+        hours.append(date_tmp.hour + date_tmp.minute / 60)
+    return np.asarray(hours)
+
+
+def compute_seconds_from_start_of_year(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
+    """Seconds elapsed since the beginning of `date`'s year, per term."""
+    start_of_year = dt.datetime(date.year, 1, 1)
+    return np.asarray([(date + term - start_of_year).total_seconds() for term in output_terms])
+
+
+def get_year_hour_forcing(date: dt.datetime, output_terms: List[dt.timedelta]) -> torch.Tensor:
+    """(N_t, 4) = (sin, cos) of the hour angle and of the year angle, rescaled to [0, 1] (host tensor:
+    four numbers per time slot, same float32 operations as the reference)."""
+    hours_of_day = compute_hours_of_day(date, output_terms)
+    seconds_from_start_of_year = compute_seconds_from_start_of_year(date, output_terms)
+    days_in_year = 366 if date.year % 4 == 0 else 365
+    seconds_in_year = days_in_year * 24 * 60 * 60
+    hour_angle = (torch.Tensor(hours_of_day) / 12) * torch.pi
+    year_angle = (torch.Tensor(seconds_from_start_of_year) / seconds_in_year) * 2 * torch.pi
+    datetime_forcing = torch.stack(
+        (torch.sin(hour_angle), torch.cos(hour_angle), torch.sin(year_angle), torch.cos(year_angle)), dim=1
+    )
+    return (datetime_forcing + 1) / 2
+
+
+def _solar_scalars(date_utc: dt.datetime, output_terms: Sequence[dt.timedelta]):
+    """Per time slot: hour of day, sin / cos of the solar declination (float32, reference :101-117)."""
+    day_of_years = compute_day_of_years(date_utc, list(output_terms))
+    hours_of_day = compute_hours_of_day(date_utc, list(output_terms))
+    dec = 23.45 * torch.sin(2 * np.pi * (284 + torch.Tensor(day_of_years)) / 365)
+    dec_rad = dec * np.float32(np.pi / 180.0)
+    return torch.Tensor(hours_of_day), torch.sin(dec_rad), torch.cos(dec_rad)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.P4CError(f"py4cast_b200.forcingutils: {what} must be a CUDA tensor (no CPU fallback)")
+    return t.to(torch.float32).contiguous()
+
+
+def _fill(lat, lon, hour, sin_dec, cos_dec, dt4, out, ld: int, ch0: int) -> None:
+    dev = lat.device
+    hour, sin_dec, cos_dec = (v.to(dev, torch.float32).contiguous() for v in (hour, sin_dec, cos_dec))
+    dt4 = None if dt4 is None else dt4.to(dev, torch.float32).contiguous()
+    check(
+        _lib.load().p4c_forcing_fill(
+            ptr(lat), ptr(lon), ptr(hour), ptr(sin_dec), ptr(cos_dec), ptr(dt4), hour.numel(), lat.numel(),
+            ptr(out), ld, ch0, stream(),
+        ),
+        "p4c_forcing_fill",
+    )
+
+
+def generate_toa_radiation_forcing(lat: torch.Tensor, lon: torch.Tensor, date_utc: dt.datetime,
+                                   output_terms: List[dt.timedelta]) -> torch.Tensor:
+    """Solar irradiation at the top of the atmosphere, (N_t, lat, lon, 1) on lat's device."""
+    lat, lon = _require_cuda(lat, "lat"), _require_cuda(lon, "lon")
+    hour, sd, cd = _solar_scalars(date_utc, output_terms)
+    out = torch.empty(hour.numel(), *lat.shape, 1, dtype=torch.float32, device=lat.device)
+    _fill(lat, lon, hour, sd, cd, None, out, 1, 0)
+    return out
+
+
+def generate_forcings(date: dt.datetime, timedeltas: List[dt.timedelta], grid) -> List[NamedTensor]:
+    """The list of external-forcing NamedTensors of reference datasets/base.py:233-274
+    (`grid` needs `.lat` / `.lon`, CUDA tensors of shape (lat, lon))."""
+    datetime_forcing = get_year_hour_forcing(date, timedeltas).type(torch.float32).to(grid.lat.device)
+    solar_forcing = generate_toa_radiation_forcing(grid.lat, grid.lon, date, timedeltas)
+    return [
+        NamedTensor(feature_names=["cos_hour", "sin_hour"], tensor=datetime_forcing[:, :2],
+                    names=["timestep", "features"]),
+        NamedTensor(feature_names=["cos_doy", "sin_doy"], tensor=datetime_forcing[:, 2:],
+                    names=["timestep", "features"]),
+        NamedTensor(feature_names=["toa_radiation"], tensor=solar_forcing,
+                    names=["timestep", "lat", "lon", "features"]),
+    ]
+
+
+def fill_external_forcings(forcing: torch.Tensor, ch0: int, lat: torch.Tensor, lon: torch.Tensor,
+                           dates: Sequence[dt.datetime], timedeltas: Sequence[dt.timedelta]) -> None:
+    """Writes [cos_hour, sin_hour, cos_doy, sin_doy, toa_radiation] of every (sample, step) into
+    channels ch0..ch0+4 of a batch's forcing tensor (B, T, lat, lon, F_f) / (B, T, N, F_f) in ONE launch —
+    what `generate_forcings` + `unsqueeze_and_expand_from_` + `NamedTensor.concat` produce per item
+    in the reference (base.py:503-515), for a whole batch (`dates[b]` = reference date of sample b)."""
+    lat, lon = _require_cuda(lat, "lat"), _require_cuda(lon, "lon")
+    if not (forcing.is_cuda and forcing.dtype == torch.float32 and forcing.is_contiguous()):
+        raise _lib.P4CError("fill_external_forcings: forcing must be a contiguous fp32 CUDA tensor")
+    B, T, F = forcing.shape[0], forcing.shape[1], forcing.shape[-1]
+    if len(dates) != B or len(timedeltas) != T or forcing.numel() != B * T * lat.numel() * F:
+        raise ValueError("fill_external_forcings: shapes / dates / timedeltas do not match")
+    hours, sds, cds, dt4s = [], [], [], []
+    for d in dates:
+        h, sd, cd = _solar_scalars(d, timedeltas)
+        hours.append(h), sds.append(sd), cds.append(cd)
+        dt4s.append(get_year_hour_forcing(d, list(timedeltas)).type(torch.float32))
+    _fill(lat, lon, torch.cat(hours), torch.cat(sds), torch.cat(cds), torch.cat(dt4s), forcing, F, ch0)

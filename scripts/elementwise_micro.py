@@ -71,6 +71,17 @@ def main():
     f_in = 2 * F + 4 + info.forcing_dim
     by_c = B * N * (4 * (2 * F + info.forcing_dim) + 2 * 72) + 4 * 4 * N
     rows.append((f"AR concat (fp32 states -> bf16 x, F_in={f_in}, ld 72)", by_c, t_c))
+    # external forcings: 5 generated channels of every (sample, step) written into the forcing tensor
+    import datetime as dt
+    from py4cast_b200 import forcingutils as fu
+    H, W = 512, 640
+    lat = torch.linspace(55.4, 37.5, H, device=dev).view(H, 1).expand(H, W).contiguous()
+    lon = torch.linspace(-12.0, 16.0, W, device=dev).view(1, W).expand(H, W).contiguous()
+    fbuf = torch.zeros(B, T, H, W, info.forcing_dim, device=dev)
+    dates = [dt.datetime(2023, 6, 1 + b, 6 * (b % 4)) for b in range(B)]
+    terms = [dt.timedelta(hours=i + 1) for i in range(T)]
+    t_ff = timeit(lambda: fu.fill_external_forcings(fbuf, info.forcing_dim - 5, lat, lon, dates, terms))
+    rows.append(("external forcings (5 channels, incl. host date arithmetic)", B * T * N * 5 * 4 + 2 * 4 * N, t_ff))
     print(f"# element-wise kernels at batch {B}, T={T}, N={N}, F={F}; peak {peak:.0f} GB/s (MEASURED_PEAKS.json or fallback)")
     for label, by, t in rows:
         print(f"{label:60s} {t*1e3:8.3f} ms  {by/1e6:9.1f} MB  {by/t/1e9:7.0f} GB/s  {by/t/1e9/peak:5.2f} of peak")

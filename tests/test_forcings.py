@@ -1,0 +1,97 @@
+"""External forcings: the oracle restatement and the host-side date helpers
+against golden vectors produced by the VERBATIM reference forcingutils.py
+(oracle/make_golden_forcings.py), and the CUDA kernel against both."""
+import datetime as dt
+
+import pytest
+import torch
+
+from helpers import FP32_TOL, assert_close, load_golden
+
+CASES = ["summer_noon", "leap_year_night", "new_year"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forcing_oracle_matches_reference_golden(name):
+    from oracle import forcing_ref
+
+    G = load_golden("forcings.pt")
+    c = G["cases"][name]
+    f4 = forcing_ref.year_hour_forcing(c["date"], c["terms"])
+    assert torch.equal(f4.type(torch.float32), c["datetime_forcing"])
+    toa = forcing_ref.toa_radiation(G["lat"], G["lon"], c["date"], c["terms"])
+    assert toa.shape == c["toa"].shape
+    assert_close(toa, c["toa"], 1e-6, f"{name} toa (oracle)")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_date_helpers_match_reference_golden(name):
+    from py4cast_b200 import forcingutils as fu
+
+    c = load_golden("forcings.pt")["cases"][name]
+    assert torch.equal(fu.get_year_hour_forcing(c["date"], c["terms"]).type(torch.float32), c["datetime_forcing"])
+    days = fu.compute_day_of_years(c["date"], c["terms"])
+    assert days.min() >= 1 and days.max() <= 366
+    if name == "new_year":  # crosses into the next year: day of year restarts at 1
+        assert 1 in days.tolist()
+        secs = fu.compute_seconds_from_start_of_year(c["date"], c["terms"])
+        assert secs.max() > 365 * 86400  # the reference keeps counting from the START date's year
+
+
+def test_forcing_needs_cuda_tensors():
+    from py4cast_b200 import _lib
+    from py4cast_b200 import forcingutils as fu
+
+    lat = torch.zeros(4, 4)
+    with pytest.raises(_lib.P4CError):
+        fu.generate_toa_radiation_forcing(lat, lat, dt.datetime(2023, 1, 1), [dt.timedelta(hours=1)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_forcings_vs_reference_golden(cuda, name):
+    from py4cast_b200 import forcingutils as fu
+
+    G = load_golden("forcings.pt")
+    c = G["cases"][name]
+    lat, lon = G["lat"].to(cuda), G["lon"].to(cuda)
+    toa = fu.generate_toa_radiation_forcing(lat, lon, c["date"], c["terms"])
+    assert toa.shape == c["toa"].shape and toa.is_cuda
+    assert_close(toa.cpu(), c["toa"], FP32_TOL, f"{name} toa_radiation")
+    assert float(toa.min()) >= 0.0
+
+    class Grid:
+        pass
+
+    grid = Grid()
+    grid.lat, grid.lon = lat, lon
+    lf = fu.generate_forcings(c["date"], c["terms"], grid)
+    assert [t.feature_names for t in lf] == [["cos_hour", "sin_hour"], ["cos_doy", "sin_doy"], ["toa_radiation"]]
+    assert lf[0].names == ["timestep", "features"] and lf[2].names == ["timestep", "lat", "lon", "features"]
+    assert torch.equal(torch.cat([lf[0].tensor, lf[1].tensor], dim=1).cpu(), c["datetime_forcing"])
+
+
+@pytest.mark.gpu
+def test_gpu_fill_external_forcings_batch(cuda):
+    """One launch writes the five generated channels of every (sample, step) into the batch's forcing
+    tensor: equals expand + concat of the per-item reference tensors (base.py:503-515)."""
+    from oracle import forcing_ref
+    from py4cast_b200 import forcingutils as fu
+
+    G = load_golden("forcings.pt")
+    lat, lon = G["lat"], G["lon"]
+    H, W = lat.shape
+    dates = [G["cases"]["summer_noon"]["date"], G["cases"]["leap_year_night"]["date"], dt.datetime(2021, 3, 9, 5, 15)]
+    terms = [dt.timedelta(hours=3 * (i + 1)) for i in range(4)]
+    Ff, ch0 = 9, 3
+    torch.manual_seed(0)
+    forcing = torch.randn(len(dates), len(terms), H, W, Ff, device=cuda)
+    before = forcing.clone()
+    fu.fill_external_forcings(forcing, ch0, lat.to(cuda), lon.to(cuda), dates, terms)
+    for b, d in enumerate(dates):
+        blk = forcing_ref.external_forcing_block(lat, lon, d, terms)
+        assert_close(forcing[b, ..., ch0:ch0 + 5].cpu(), blk, FP32_TOL, f"sample {b} external forcings")
+    # the other channels are untouched
+    assert torch.equal(forcing[..., :ch0], before[..., :ch0]) and torch.equal(forcing[..., ch0 + 5:], before[..., ch0 + 5:])
+    with pytest.raises(ValueError):
+        fu.fill_external_forcings(forcing, ch0, lat.to(cuda), lon.to(cuda), dates[:2], terms)
