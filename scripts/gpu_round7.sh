@@ -3,12 +3,12 @@
 # m2g InteractionNet kernels (batch 2).  Usage: gpu_round7.sh [tag]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-TAG=${1:-r01k}
+TAG=${1:-r01s}
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu_info.txt 2>&1
 nproc > gpurun_out/host_cores.txt
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-  for f in test_gpu_kernels test_gpu_tc_features test_gpu_ws_forward test_gpu_ar_loss test_gpu_models test_gpu_trainer; do
+  for f in test_gpu_kernels test_gpu_tc_features test_gpu_ws_forward test_gpu_ar_loss test_gpu_models test_gpu_trainer test_forcings; do
     timeout 900 python -m pytest tests/$f.py -q -m gpu -x --timeout 600 > gpurun_out/$f.log 2>&1
     echo "$f exit=$?" >> gpurun_out/summary.txt
     tail -3 gpurun_out/$f.log >> gpurun_out/summary.txt
