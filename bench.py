@@ -10,11 +10,12 @@ HiLAM AR-rollout training throughput on B200 (BASELINE.json metric), one process
 A "step" = one optimiser step on one synthetic Titan-shaped batch per GPU: T-step AR rollout
 (fwd) + WeightedLoss(MSE) + backward + gradient all-reduce + AdamW (accumulate_grad_batches = 1).
 Workload = BASELINE configs[2] (HiLAM, 3 mesh levels, 512x640 grid, F=21, F_f=21, F_s=4,
-T_in=2, diff_ar, T=4, bf16); `--pred-steps 12` gives configs[3].  Batch 8 per GPU: the reference
-trains this grid with batch_size 2 on 32-GB parts (config/CLI/dataset/titan.yaml:7, with
-activation checkpointing); 180 GB of HBM3e hold 8 samples' activations (~3 GB each at T=4) with
-room, and the larger batch amortises the launch-bound mesh-level kernels
-(profiles/r01f_batch_sweep.txt: 64.5 / 83.5 / 96.8 samples/s at batch 2 / 4 / 8).
+T_in=2, diff_ar, T=4, bf16); `--pred-steps 12` gives configs[3].  Batch 16 per GPU at T <= 4 (64 / T
+beyond): the reference trains this grid with batch_size 2 on 32-GB parts (config/CLI/dataset/
+titan.yaml:7, with activation checkpointing); 180 GB of HBM3e hold 16 samples' activations (~3 GB
+each at T=4) with room, and the larger batch amortises the ~14 ms of launch-bound mesh-level kernels
+per step (profiles/r01f_batch_sweep.txt, r01t_batch_sweep.txt: 64.5 / 83.5 / 96.8 samples/s at batch
+2 / 4 / 8 early in the round, 108 / 113 / 119 at batch 8 / 12 / 16 at its end).
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -48,8 +49,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--pred-steps", type=int, default=4)
-    # reference config/CLI/dataset/titan.yaml:7: batch_size 2 per (32 GB) GPU; 8 fits 180 GB easily
-    ap.add_argument("--batch-per-gpu", type=int, default=8)
+    # reference config/CLI/dataset/titan.yaml:7: batch_size 2 per (32 GB) GPU.  0 = auto: 16 for
+    # rollouts of up to 4 steps (~3 GB of saved activations per sample), 64 // T for longer ones
+    ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--precision", default="bf16-true", choices=["bf16-true", "32-true"])
     ap.add_argument("--model", default="HiLAM", choices=["HiLAM", "GraphLAM", "HiLAMParallel"])
     ap.add_argument("--strategy", default="diff_ar", choices=["diff_ar", "scaled_ar"])
@@ -65,7 +67,10 @@ def parse_args():
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop after warm-up and exit "
                          "(for `ncu --profile-from-start off`; prints no bench line)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch_per_gpu <= 0:
+        args.batch_per_gpu = 16 if args.pred_steps <= 4 else max(1, 64 // args.pred_steps)
+    return args
 
 
 def workload_config(args, world):
