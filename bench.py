@@ -292,7 +292,7 @@ def gpu_arm(args):
     import torch.distributed as dist
 
     from py4cast_b200 import _lib
-    from py4cast_b200.datasets import synthetic_batch, synthetic_dataset_info
+    from py4cast_b200.datasets import ItemBatch, synthetic_dataset_info
     from py4cast_b200.lightning import AutoRegressiveLightning
     from py4cast_b200.trainer import DataParallelTrainer, init_distributed
 
@@ -319,8 +319,32 @@ def gpu_arm(args):
     ).to(dev)
     trainer = DataParallelTrainer(lm, total_steps=100000, num_streams=args.streams, cta_reserve=args.cta_reserve)
     B, T = args.batch_per_gpu, args.pred_steps
-    dev_batch = synthetic_batch(info, B, 2, T, seed=100 + rank, device=dev)
-    host_batches = [synthetic_batch(info, B, 2, T, seed=200 + rank + 10 * i, pin=True) for i in range(2)]
+    # synthetic N(0,1) fields, generated on the GPU (the host generator is single-threaded under
+    # torchrun); the pinned host batches of the end-to-end leg are copies of GPU-generated ones.  Two
+    # alternate when they fit 4 GB of pinned memory per rank, otherwise one is re-sent every step.
+    def gpu_batch(seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        shape = info.statics.grid_shape
+        names = ["batch", "timestep", "lat", "lon", "features"]
+        wn, fn = info.shortnames["input_output"], info.shortnames["forcing"]
+        mk = lambda steps, F: torch.randn(B, steps, *shape, F, generator=g, device=dev, dtype=torch.float32)  # noqa: E731
+        from py4cast_b200.namedtensor import NamedTensor
+        return ItemBatch(
+            inputs=NamedTensor(mk(2, len(wn)), names, wn), forcing=NamedTensor(mk(T, len(fn)), names, fn),
+            outputs=NamedTensor(mk(T, len(wn)), names, wn))
+
+    def to_pinned(b):
+        from py4cast_b200.namedtensor import NamedTensor
+        cp = lambda nt: NamedTensor(nt.tensor.cpu().pin_memory(), list(nt.names), list(nt.feature_names))  # noqa: E731
+        return type(b)(inputs=cp(b.inputs), forcing=cp(b.forcing), outputs=cp(b.outputs))
+
+    dev_batch = gpu_batch(100 + rank)
+    batch_bytes = sum(getattr(dev_batch, n).tensor.numel() * 4 for n in ("inputs", "forcing", "outputs"))
+    n_host = 2 if 2 * batch_bytes <= (4 << 30) else 1
+    host_batches = [to_pinned(gpu_batch(200 + rank + 10 * i)) for i in range(n_host)]
+    if n_host == 1:
+        host_batches = host_batches * 2
+    torch.cuda.empty_cache()
 
     if args.profile_step:
         for _ in range(3):
