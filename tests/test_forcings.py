@@ -95,3 +95,27 @@ def test_gpu_fill_external_forcings_batch(cuda):
     assert torch.equal(forcing[..., :ch0], before[..., :ch0]) and torch.equal(forcing[..., ch0 + 5:], before[..., ch0 + 5:])
     with pytest.raises(ValueError):
         fu.fill_external_forcings(forcing, ch0, lat.to(cuda), lon.to(cuda), dates[:2], terms)
+
+
+def test_forcing_oracle_matches_verbatim_reference_fresh_inputs():
+    """Where the reference tree is mounted (the build container): the restatement against the
+    reference's own forcingutils.py on inputs that are not in the fixtures."""
+    import importlib.util
+    import os
+
+    path = "/root/reference/py4cast/forcingutils.py"
+    if not os.path.isfile(path):
+        pytest.skip("needs /root/reference")
+    from oracle import forcing_ref
+
+    spec = importlib.util.spec_from_file_location("ref_forcingutils_live", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    g = torch.Generator().manual_seed(99)
+    lat = 30 + 30 * torch.rand(7, 9, generator=g)
+    lon = -20 + 50 * torch.rand(7, 9, generator=g)
+    date = dt.datetime(2020, 10, 17, 3, 45)
+    terms = [dt.timedelta(minutes=90 * (i + 1)) for i in range(7)]
+    assert torch.equal(forcing_ref.year_hour_forcing(date, terms), ref.get_year_hour_forcing(date, terms))
+    assert_close(forcing_ref.toa_radiation(lat, lon, date, terms),
+                 ref.generate_toa_radiation_forcing(lat, lon, date, terms), 1e-6, "toa vs verbatim reference")
