@@ -119,3 +119,36 @@ def test_forcing_oracle_matches_verbatim_reference_fresh_inputs():
     assert torch.equal(forcing_ref.year_hour_forcing(date, terms), ref.get_year_hour_forcing(date, terms))
     assert_close(forcing_ref.toa_radiation(lat, lon, date, terms),
                  ref.generate_toa_radiation_forcing(lat, lon, date, terms), 1e-6, "toa vs verbatim reference")
+
+
+def test_reference_known_answers_date_forcing():
+    """Known-answer test of the reference's own suite (tests/test_datasets.py:114-132): midnight of the
+    new year 2024 -> (sin, cos) of both angles = (0, 1), rescaled to (0.5, 1)."""
+    from oracle import forcing_ref
+    from py4cast_b200 import forcingutils as fu
+
+    date = dt.datetime(year=2023, month=12, day=31, hour=23)
+    terms = [dt.timedelta(hours=1), dt.timedelta(hours=2), dt.timedelta(hours=3)]
+    for fn in (fu.get_year_hour_forcing, forcing_ref.year_hour_forcing):
+        forcing = fn(date, terms)
+        assert forcing.shape == torch.Size((3, 4))
+        assert torch.allclose(forcing[0], torch.tensor([0.5, 1, 0.5, 1]))
+
+
+def test_reference_known_answer_solar_forcing_oracle():
+    """Known-answer test of the reference's own suite (tests/test_datasets.py:136-165): exercise 1.6.2.a
+    of Solar Engineering of Thermal Processes (zenith 66.5 degrees), margin 0.01 W/m2 — on the oracle
+    restatement (the CUDA kernel is held to the oracle / golden vectors at 1e-5 in the GPU tests)."""
+    import numpy as np
+
+    from oracle import forcing_ref
+
+    lat, lon = torch.tensor(43), torch.tensor(-89)
+    utc_date = dt.datetime(year=2023, month=2, day=13, hour=15, minute=26)
+    forcing = forcing_ref.toa_radiation(lat, lon, utc_date, [dt.timedelta(hours=0)])
+    solution = 1366 * np.cos(np.radians(66.5))
+    assert abs(float(forcing.reshape(-1)[0]) - solution) < 0.01
+    lat, lon = torch.rand(16, 16), torch.rand(16, 16)
+    terms = [dt.timedelta(hours=1), dt.timedelta(hours=2), dt.timedelta(hours=3)]
+    out = forcing_ref.toa_radiation(lat, lon, dt.datetime(2023, 5, 20, 13), terms)
+    assert out.shape == torch.Size((3, 16, 16, 1))
