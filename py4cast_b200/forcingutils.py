@@ -25,43 +25,37 @@ from ._lib import check, ptr, stream
 from .namedtensor import NamedTensor
 
 
+def _valid_times(date: dt.datetime, output_terms: Sequence[dt.timedelta]) -> List[dt.datetime]:
+    return [date + term for term in output_terms]
+
+
 def compute_day_of_years(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
-    """Day of the year of each term (1st of January is 1)."""
-    days = []
-    for term in output_terms:
-        date_tmp = date + term
-        days.append((date_tmp - dt.datetime(date_tmp.year, 1, 1)).days + 1)
-    return np.asarray(days)
+    """Day of the year of each valid time (1st of January is 1)."""
+    return np.asarray([t.timetuple().tm_yday for t in _valid_times(date, output_terms)])
 
 
 def compute_hours_of_day(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
-    """Hour of the day (with minutes as a fraction) of each term."""
-    hours = []
-    for term in output_terms:
-        date_tmp = date + term
-        hours.append(date_tmp.hour + date_tmp.minute / 60)
-    return np.asarray(hours)
+    """Hour of the day of each valid time, minutes as a fraction."""
+    return np.asarray([t.hour + t.minute / 60 for t in _valid_times(date, output_terms)])
 
 
 def compute_seconds_from_start_of_year(date: dt.datetime, output_terms: List[dt.timedelta]) -> np.ndarray:
-    """Seconds elapsed since the beginning of `date`'s year, per term."""
-    start_of_year = dt.datetime(date.year, 1, 1)
-    return np.asarray([(date + term - start_of_year).total_seconds() for term in output_terms])
+    """Seconds between the 1st of January of `date`'s year (not of the valid time's year: a window that
+    crosses the new year keeps counting, as in the reference) and each valid time."""
+    origin = dt.datetime(date.year, 1, 1)
+    return np.asarray([(t - origin).total_seconds() for t in _valid_times(date, output_terms)])
 
 
 def get_year_hour_forcing(date: dt.datetime, output_terms: List[dt.timedelta]) -> torch.Tensor:
-    """(N_t, 4) = (sin, cos) of the hour angle and of the year angle, rescaled to [0, 1] (host tensor:
-    four numbers per time slot, same float32 operations as the reference)."""
-    hours_of_day = compute_hours_of_day(date, output_terms)
-    seconds_from_start_of_year = compute_seconds_from_start_of_year(date, output_terms)
-    days_in_year = 366 if date.year % 4 == 0 else 365
-    seconds_in_year = days_in_year * 24 * 60 * 60
-    hour_angle = (torch.Tensor(hours_of_day) / 12) * torch.pi
-    year_angle = (torch.Tensor(seconds_from_start_of_year) / seconds_in_year) * 2 * torch.pi
-    datetime_forcing = torch.stack(
-        (torch.sin(hour_angle), torch.cos(hour_angle), torch.sin(year_angle), torch.cos(year_angle)), dim=1
-    )
-    return (datetime_forcing + 1) / 2
+    """(N_t, 4): sin / cos of the hour-of-day angle and of the time-of-year angle, mapped to [0, 1].
+    A host tensor — four numbers per time slot — computed with the reference's float32 operation
+    order (hours / 12 * pi, seconds / seconds_in_year * 2 * pi, (x + 1) / 2), so that it is bit-equal
+    to it; the reference's year length rule (366 days iff year % 4 == 0) is kept."""
+    seconds_in_year = (366 if date.year % 4 == 0 else 365) * 86400
+    hour_angle = (torch.Tensor(compute_hours_of_day(date, output_terms)) / 12) * torch.pi
+    year_angle = (torch.Tensor(compute_seconds_from_start_of_year(date, output_terms)) / seconds_in_year) * 2 * torch.pi
+    columns = [fn(angle) for angle in (hour_angle, year_angle) for fn in (torch.sin, torch.cos)]
+    return (torch.stack(columns, dim=1) + 1) / 2
 
 
 def _solar_scalars(date_utc: dt.datetime, output_terms: Sequence[dt.timedelta]):
