@@ -463,6 +463,63 @@ __global__ void loss_denom_kernel(float num_interior, const int* __restrict__ co
   *denom = num_interior - (count ? (float)*count : 0.f);
 }
 
+// ------------------------------------------------------------------------------- ACC metric
+// Anomaly correlation coefficient of reference py4cast/metrics.py:407-420 (MetricACC.update):
+//   acc[bt][f] = mean_s((p - c_f)(t - c_f) m) / sqrt(mean_s(((p - c_f) m)^2) * mean_s(((t - c_f) m)^2))
+// = S0 / sqrt(S1 * S2) with the three spatial sums below (the 1/N of the means cancels).  Same
+// partial / finalize structure as the loss (fixed summation order, no atomics): ONE pass over
+// prediction and target instead of the reference's ~10 temporaries.
+// partial[bt][chunk][3][F]
+__global__ void __launch_bounds__(LOSS_NT)
+acc_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                   const float* __restrict__ mask, const float* __restrict__ clim, int nodes, int F,
+                   float* __restrict__ partials) {
+  __shared__ float red[3][LOSS_NT];
+  const int npi = loss_nodes_per_iter(F);
+  const int active = npi * F;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, nchunks = gridDim.x;
+  const long long bt = blockIdx.y;
+  const int n0 = chunk * loss_chunk_nodes(F);
+  const int n1 = min(nodes, n0 + loss_chunk_nodes(F));
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  if (tid < active) {
+    const int f = tid % F, no = tid / F;
+    const float c = clim[f];
+    const long long base = bt * (long long)nodes * F;
+    for (int n = n0 + no; n < n1; n += npi) {
+      const long long idx = base + (long long)n * F + f;
+      const float m = mask ? mask[idx] : 1.0f;
+      const float a = (pred[idx] - c) * m, b = (target[idx] - c) * m;
+      s0 = fmaf((pred[idx] - c) * (target[idx] - c), m, s0);
+      s1 = fmaf(a, a, s1);
+      s2 = fmaf(b, b, s2);
+    }
+  }
+  red[0][tid] = s0;
+  red[1][tid] = s1;
+  red[2][tid] = s2;
+  __syncthreads();
+  if (tid < F) {
+    for (int k = 0; k < 3; ++k) {
+      float s = 0.f;
+      for (int j = 0; j < npi; ++j) s += red[k][tid + j * F];
+      partials[((bt * nchunks + chunk) * 3 + k) * F + tid] = s;
+    }
+  }
+}
+
+__global__ void acc_finalize_kernel(const float* __restrict__ partials, int nchunks, int F,
+                                    float* __restrict__ out) {
+  const long long bt = blockIdx.x;
+  const int f = threadIdx.x;
+  if (f >= F) return;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < nchunks; ++c)
+    for (int k = 0; k < 3; ++k) s[k] += partials[((bt * nchunks + c) * 3 + k) * F + f];
+  out[bt * F + f] = s[0] / sqrtf(s[1] * s[2]);
+}
+
 // --------------------------------------------------------------------- external forcings
 // The five generated forcing channels of one sample window (reference py4cast/forcingutils.py:61-132,
 // assembled by datasets/base.py:233-274 `generate_forcings` and broadcast over the grid at :509-511):
@@ -791,5 +848,26 @@ extern "C" int p4c_forcing_fill(const float* lat, const float* lon, const float*
   forcing_fill_kernel<<<dim3(bx, slots), 256, 0, (cudaStream_t)stream>>>(lat, lon, hour, sin_dec, cos_dec, datetime4,
                                                                          slots, nodes, out, ld, ch0);
   P4C_CHECK_LAUNCH("forcing_fill");
+  return P4C_OK;
+}
+
+
+extern "C" int64_t p4c_acc_partial_floats(int64_t bt, int32_t nodes, int32_t f) {
+  if (f <= 0 || f > LOSS_NT || bt <= 0 || nodes <= 0) return 0;
+  return bt * (int64_t)loss_nchunks(nodes, f) * 3 * f;
+}
+
+extern "C" int p4c_acc_forward(const float* pred, const float* target, const float* mask,
+                               const float* climate_means, int64_t bt, int32_t nodes, int32_t f,
+                               float* partials, float* out, void* stream) {
+  P4C_REQUIRE(pred && target && climate_means && partials && out, "acc_forward: null pointer");
+  P4C_REQUIRE(bt > 0 && bt <= 65535 && nodes > 0 && f > 0 && f <= LOSS_NT, "acc_forward: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunks = loss_nchunks(nodes, f);
+  acc_partial_kernel<<<dim3(nchunks, (unsigned)bt), LOSS_NT, 0, st>>>(pred, target, mask, climate_means, nodes, f,
+                                                                      partials);
+  P4C_CHECK_LAUNCH("acc_partial");
+  acc_finalize_kernel<<<(unsigned)bt, LOSS_NT, 0, st>>>(partials, nchunks, f, out);
+  P4C_CHECK_LAUNCH("acc_finalize");
   return P4C_OK;
 }

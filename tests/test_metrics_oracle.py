@@ -53,3 +53,24 @@ def test_psd_log_rmse_is_zero_for_identical_fields():
     m = torch.ones_like(x)
     assert np.allclose(metrics_ref.psd_log_rmse(x, x, m, 1), 0.0)
     assert (metrics_ref.psd_log_rmse(x, 2 * x, m, 0) > 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("P4C_EXPERIMENTAL") != "1",
+                    reason="p4c_acc_forward was written after the round's GPU budget was spent: opt-in until validated")
+@pytest.mark.parametrize("name", ["graph", "grid"])
+def test_gpu_acc_vs_reference_golden(cuda, name):
+    from py4cast_b200.metrics import acc_per_sample
+
+    c = load_golden("metrics.pt")["acc"][name]
+    per_sample = acc_per_sample(c["pred"].to(cuda), c["target"].to(cuda), c["mask"].to(cuda), c["climate_means"])
+    assert_close(per_sample.mean(dim=0).cpu(), c["acc"], 1e-5, f"acc {name}")
+
+
+def test_metric_acc_refuses_cpu_tensors():
+    from py4cast_b200 import _lib
+    from py4cast_b200.metrics import acc_per_sample
+
+    x = torch.randn(1, 1, 8, 2)
+    with pytest.raises(_lib.P4CError):
+        acc_per_sample(x, x, None, torch.zeros(2))
