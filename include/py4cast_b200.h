@@ -375,8 +375,7 @@ int p4c_forcing_fill(const float* lat, const float* lon, const float* hour, cons
  * MetricACC.update): out[bt][f] = S0 / sqrt(S1 * S2) over the spatial points of one (sample, step),
  * S0 = sum (p - c_f)(t - c_f) m, S1 = sum ((p - c_f) m)^2, S2 = sum ((t - c_f) m)^2; mask optional
  * (NULL = ones).  pred / target / mask: fp32 (bt, nodes, f) contiguous; partials: workspace of
- * p4c_acc_partial_floats() floats.  EXPERIMENTAL in round 1: written after the round's GPU budget was
- * spent — compiled and bound, not yet validated on hardware (its GPU test is opt-in).
+ * p4c_acc_partial_floats() floats.
  * ---------------------------------------------------------------------- */
 int64_t p4c_acc_partial_floats(int64_t bt, int32_t nodes, int32_t f);
 int p4c_acc_forward(const float* pred, const float* target, const float* mask,

@@ -1,13 +1,13 @@
 """
-Validation metrics on the device — EXPERIMENTAL in round 1.
+Validation metrics on the device.
 
 `MetricACC` mirrors reference py4cast/metrics.py:355-455 (same constructor argument, `update(preds,
 target, mask)`, `compute(prefix)`, `reset()`; no torchmetrics dependency: the two states it keeps,
 `sum_acc` and `step_count`, are plain tensors and `compute` returns the same dict of per-feature,
 per-step scalars).  The three spatial reductions of `update` run in one pass over prediction and
-target (`p4c_acc_forward`) instead of ~10 full-size temporaries.  Written after the round's GPU budget
-was spent: bound and compiled, its GPU test is opt-in (`P4C_EXPERIMENTAL=1`) until it has run on
-hardware.  PSD metrics (metrics.py:13-352): oracle only so far (`oracle/metrics_ref.py`).
+target (`p4c_acc_forward`) instead of ~10 full-size temporaries; parity with the verbatim reference
+at 1e-5 on golden vectors (tests/test_metrics_oracle.py).  PSD metrics (metrics.py:13-352): oracle only
+so far (`oracle/metrics_ref.py`).
 """
 
 from __future__ import annotations

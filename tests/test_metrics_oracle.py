@@ -1,6 +1,6 @@
-"""Validation metrics (prepared for the next round): the oracle restatement of the
-reference's PSD / ACC numerics against golden vectors from the VERBATIM reference metrics.py
-(oracle/make_golden_metrics.py).  CPU only — the CUDA side does not exist yet."""
+"""Validation metrics: the oracle restatement of the reference's PSD / ACC numerics
+against golden vectors from the VERBATIM reference metrics.py (oracle/make_golden_metrics.py), and the
+ACC reduction kernel against the same vectors.  PSD has no CUDA side yet."""
 import numpy as np
 import pytest
 import torch
@@ -56,8 +56,6 @@ def test_psd_log_rmse_is_zero_for_identical_fields():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("P4C_EXPERIMENTAL") != "1",
-                    reason="p4c_acc_forward was written after the round's GPU budget was spent: opt-in until validated")
 @pytest.mark.parametrize("name", ["graph", "grid"])
 def test_gpu_acc_vs_reference_golden(cuda, name):
     from py4cast_b200.metrics import acc_per_sample
