@@ -60,9 +60,6 @@ def parse_args():
                     help="mesh processor depth (reference hilam.yaml: 4); other values are for experiments only")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
-                    help="2: the two halves of the per-GPU batch run concurrently on two CUDA streams")
-    ap.add_argument("--cta-reserve", type=int, default=56)
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop after warm-up and exit "
@@ -81,7 +78,6 @@ def workload_config(args, world):
         "model_name": args.model, "grid": [H, W], "pred_steps": args.pred_steps,
         "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
         "strategy": args.strategy, "precision": args.precision, "parallelism": f"dp{world}",
-        "streams_per_gpu": args.streams,
         "l2": "per-step working set (several GB of activations) >> 126 MB L2: no flush needed",
     }
 
@@ -317,7 +313,7 @@ def gpu_arm(args):
         training_strategy=args.strategy, learning_rate=1e-3, min_learning_rate=3e-7, num_warmup_steps=1000,
         betas=(0.9, 0.95), precision=args.precision,
     ).to(dev)
-    trainer = DataParallelTrainer(lm, total_steps=100000, num_streams=args.streams, cta_reserve=args.cta_reserve)
+    trainer = DataParallelTrainer(lm, total_steps=100000)
     B, T = args.batch_per_gpu, args.pred_steps
     # synthetic N(0,1) fields, generated on the GPU (the host generator is single-threaded under
     # torchrun); the pinned host batches of the end-to-end leg are copies of GPU-generated ones.  Two

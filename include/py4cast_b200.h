@@ -57,6 +57,8 @@ int p4c_sizeof(int which);
  *   rowptr  [num_keys+1] int32 out
  *   perm    [E]  int32 out: edge ids grouped by key, ascending edge id inside a group
  *   scratch [E + num_keys + 1] int32 workspace
+ * Set-up entry point: outside CUDA-graph capture it synchronises the stream once to validate the
+ * keys and returns P4C_EINVAL when one lies outside [0, num_keys) (no kernel indexes with it).
  * ---------------------------------------------------------------------- */
 int p4c_csr_build(const int64_t* keys, int64_t E, int32_t num_keys, int32_t* rowptr,
                   int32_t* perm, int32_t* scratch, void* stream);

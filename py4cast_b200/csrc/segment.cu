@@ -92,22 +92,25 @@ __global__ void csr_scan_kernel(const int* __restrict__ counts, int n, int* __re
 }
 
 // unordered placement of edge ids into their key's segment
-__global__ void csr_fill_kernel(const long long* __restrict__ keys, long long E,
+__global__ void csr_fill_kernel(const long long* __restrict__ keys, long long E, int num_keys,
                                 const int* __restrict__ rowptr, int* __restrict__ cursor,
                                 int* __restrict__ tmp) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E;
        e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)keys[e];
+    const long long kk = keys[e];
+    if (kk < 0 || kk >= num_keys) continue;  // reported by csr_hist_kernel; never index with it
+    const int k = (int)kk;
     const int slot = atomicAdd(cursor + k, 1);
     tmp[rowptr[k] + slot] = (int)e;
   }
 }
 
 // rank every edge id inside its segment -> ascending edge id (== stable sort by key)
-__global__ void csr_rank_kernel(const long long* __restrict__ keys, long long E,
+__global__ void csr_rank_kernel(const long long* __restrict__ keys, int num_keys,
                                 const int* __restrict__ rowptr, const int* __restrict__ tmp,
                                 int* __restrict__ perm) {
-  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < E;
+  const long long placed = rowptr[num_keys];  // == E unless out-of-range keys were skipped
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < placed;
        j += (long long)gridDim.x * blockDim.x) {
     const int e = tmp[j];
     const int k = (int)keys[e];
@@ -247,6 +250,22 @@ extern "C" int p4c_csr_build(const int64_t* keys, int64_t E, int32_t num_keys, i
     csr_hist_kernel<<<grid_for(E, 256), 256, 0, st>>>((const long long*)keys, E, num_keys, counts, bad);
     P4C_CHECK_LAUNCH("csr_hist");
   }
+  if (E > 0) {
+    // Set-up path (runs once per edge set, never under graph capture): read the out-of-range flag
+    // back before any kernel indexes with the keys.  The one entry point that synchronises.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      int bad_h = 0;
+      e = cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_error("csr_build: reading the key check failed: %s", cudaGetErrorString(e));
+        return P4C_ECUDA;
+      }
+      P4C_REQUIRE(bad_h == 0, "csr_build: a key lies outside [0, %d)", num_keys);
+    }
+  }
   csr_scan_kernel<<<1, 1024, 0, st>>>(counts, num_keys, rowptr);
   P4C_CHECK_LAUNCH("csr_scan");
   if (E > 0) {
@@ -255,9 +274,9 @@ extern "C" int p4c_csr_build(const int64_t* keys, int64_t E, int32_t num_keys, i
       set_error("csr_build: memset failed: %s", cudaGetErrorString(e));
       return P4C_ECUDA;
     }
-    csr_fill_kernel<<<grid_for(E, 256), 256, 0, st>>>((const long long*)keys, E, rowptr, counts, tmp);
+    csr_fill_kernel<<<grid_for(E, 256), 256, 0, st>>>((const long long*)keys, E, num_keys, rowptr, counts, tmp);
     P4C_CHECK_LAUNCH("csr_fill");
-    csr_rank_kernel<<<grid_for(E, 256), 256, 0, st>>>((const long long*)keys, E, rowptr, tmp, perm);
+    csr_rank_kernel<<<grid_for(E, 256), 256, 0, st>>>((const long long*)keys, num_keys, rowptr, tmp, perm);
     P4C_CHECK_LAUNCH("csr_rank");
   }
   return P4C_OK;

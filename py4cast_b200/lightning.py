@@ -280,6 +280,15 @@ class AutoRegressiveLightning(nn.Module):
         self.model, model_settings = build_model_from_settings(
             model_name, num_input_features, num_output_features, self.settings_init_args, statics.grid_shape
         )
+        digest = getattr(self.model, "graph_digest", None)
+        if digest is not None:
+            from .nlam import _meshgrid_digest
+
+            if digest != _meshgrid_digest(statics.meshgrid):
+                raise ValueError(
+                    "the cached mesh graph under settings.tmp_dir was built for another domain "
+                    "(same grid shape, other coordinates): use a tmp_dir per domain"
+                )
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
 
@@ -416,32 +425,36 @@ class AutoRegressiveLightning(nn.Module):
         if hasattr(self.model, "begin_rollout"):
             # batch-independent embeddings and weight images: once per rollout, not per step
             self.model.begin_rollout(x_dtype)
-        prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
-        x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
-        states = []
-        for i in range(T):
-            for k in range(num_inter_steps):
-                y = self._run_model(x, spatial)
-                last_k = k == num_inter_steps - 1
-                more = i < T - 1 or not last_k
-                next_forcing = None
-                if more:
-                    next_forcing = forcing[:, i] if not last_k else forcing[:, i + 1]
-                cfg = {
-                    "truth": outputs[:, i] if border is not None else None,
-                    "border": border, "std": std, "mean": mean,
-                    "new_state": slab[:, i] if last_k else torch.empty(B, N, F, dtype=torch.float32, device=dev),
-                    "static": self._static_flat, "forcing_next": next_forcing, "x_dtype": x_dtype,
-                }
-                res = _ARStepFn.apply(cfg, y, *prevs)
-                if more:
-                    new_state, x = res
-                    prevs = prevs[1:] + [new_state]
-                else:
-                    new_state = res
-            states.append(new_state)
-        if hasattr(self.model, "end_rollout"):
-            self.model.end_rollout()
+        try:
+            prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
+            x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
+            states = []
+            for i in range(T):
+                for k in range(num_inter_steps):
+                    y = self._run_model(x, spatial)
+                    last_k = k == num_inter_steps - 1
+                    more = i < T - 1 or not last_k
+                    next_forcing = None
+                    if more:
+                        next_forcing = forcing[:, i] if not last_k else forcing[:, i + 1]
+                    cfg = {
+                        "truth": outputs[:, i] if border is not None else None,
+                        "border": border, "std": std, "mean": mean,
+                        "new_state": slab[:, i] if last_k else torch.empty(B, N, F, dtype=torch.float32, device=dev),
+                        "static": self._static_flat, "forcing_next": next_forcing, "x_dtype": x_dtype,
+                    }
+                    res = _ARStepFn.apply(cfg, y, *prevs)
+                    if more:
+                        new_state, x = res
+                        prevs = prevs[1:] + [new_state]
+                    else:
+                        new_state = res
+                states.append(new_state)
+        finally:
+            # always paired: an exception inside the rollout must not leave stale embeddings /
+            # weight images behind for the next one
+            if hasattr(self.model, "end_rollout"):
+                self.model.end_rollout()
         prediction = _SlabFn.apply(slab, *states).view(B, T, *spatial, F)
 
         if inference:

@@ -205,6 +205,15 @@ def _graph_path(tmp_dir, hierarchical: bool, grid_shape, n_max_levels) -> Path:
     return Path(tmp_dir) / f"p4c_b200_graph_{tag}_{grid_shape[0]}x{grid_shape[1]}_L{n_max_levels or 0}.pt"
 
 
+def _meshgrid_digest(meshgrid: torch.Tensor) -> str:
+    """Identifies the domain a cached graph was built for (two domains of the same shape but other
+    coordinates must not share a graph)."""
+    import hashlib
+
+    t = torch.as_tensor(meshgrid).detach().to("cpu", torch.float64).contiguous()
+    return hashlib.sha256(t.numpy().tobytes()).hexdigest()[:16]
+
+
 def _graph_to_dict(g: MeshGraph) -> dict:
     def es(e: EdgeSet):
         return {"edge_index": e.edge_index, "features": e.features, "num_send": e.num_send, "num_rec": e.num_rec}
@@ -249,7 +258,9 @@ class BaseGraphModel(ModelABC, nn.Module):
         path.parent.mkdir(parents=True, exist_ok=True)
         fd, tmp = tempfile.mkstemp(dir=str(path.parent), suffix=".tmp")
         os.close(fd)
-        torch.save(_graph_to_dict(graph), tmp)
+        payload = _graph_to_dict(graph)
+        payload["meshgrid_digest"] = _meshgrid_digest(meshgrid)
+        torch.save(payload, tmp)
         os.replace(tmp, path)
 
     def __init__(
@@ -276,7 +287,10 @@ class BaseGraphModel(ModelABC, nn.Module):
                 raise FileNotFoundError(
                     f"{path} not found: call {type(self).__name__}.rank_zero_setup(settings, meshgrid) first"
                 )
-            graph = _graph_from_dict(torch.load(path, map_location="cpu", weights_only=False))
+            # tensors, lists, ints and strings only: no pickle execution from a shared temp dir
+            payload = torch.load(path, map_location="cpu", weights_only=True)
+            self.graph_digest = payload.get("meshgrid_digest")
+            graph = _graph_from_dict(payload)
         if graph.hierarchical != self.hierarchical:
             raise ValueError("graph hierarchy flag does not match the model class")
         if graph.num_grid_nodes != self.input_shape[0] * self.input_shape[1]:

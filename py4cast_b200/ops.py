@@ -159,6 +159,17 @@ def _deferred_mode(meta: Optional[MlpMeta], nblocks: int, partial_floats: int, d
     return 2
 
 
+def reset_deferred_wgrads() -> None:
+    """Drops deferred weight-gradient state left behind by a backward pass that was never flushed
+    (a `loss.backward()` outside the trainer, or a step that raised before `flush_wgrads`): the
+    next backward then OVERWRITES its partials instead of accumulating onto stale ones.  Host-side
+    flags only (safe before or under CUDA-graph capture); the trainer calls it at the start of
+    every step."""
+    for meta, branch in _DEFERRED:
+        meta.partials_used[branch] = False
+    _DEFERRED.clear()
+
+
 def flush_wgrads() -> None:
     """Reduces the deferred weight-gradient partials of every MLP touched since the last flush
     into the parameters' gradient sinks: ONE launch per execution branch, branches in ascending
@@ -278,12 +289,10 @@ class GraphIndex:
             start = 0
             for n in edge_chunk_sizes:
                 stop = start + int(n)
-                # keys outside the chunk are parked on an extra trailing segment
+                # CSR of the chunk's own edges; perm holds GLOBAL edge ids (local + start)
                 def keyed(keys, nseg):
-                    k = torch.full_like(keys, nseg)
-                    k[start:stop] = keys[start:stop]
-                    c = csr_build(k, nseg + 1, drop_identity_perm=False)
-                    return Csr(c.rowptr[: nseg + 1].contiguous(), c.perm, nseg, c.inv_deg[:nseg].contiguous())
+                    c = csr_build(keys[start:stop].contiguous(), nseg, drop_identity_perm=False)
+                    return Csr(c.rowptr, (c.perm + start).contiguous(), nseg, c.inv_deg)
 
                 groups.append(EdgeGroup(start, stop, keyed(rec, num_rec), keyed(send, num_send)))
                 start = stop

@@ -110,19 +110,8 @@ class FusedAdamW:
 class DataParallelTrainer:
     """One rank of the data-parallel job (world size 1 works without torch.distributed)."""
 
-    def __init__(self, lm, total_steps: int = 1000, use_kernel_sinks: bool = True, num_streams: int = 1,
-                 cta_reserve: int = 56):
-        """num_streams = 2: the two halves of the per-GPU batch run as independent rollouts on two
-        CUDA streams (forward and backward), so that the latency-bound mesh-level kernels of one
-        half overlap the bandwidth-bound grid-level kernels of the other; `cta_reserve` CTA slots
-        are then kept free of the large persistent kernels (p4c_set_cta_reserve)."""
+    def __init__(self, lm, total_steps: int = 1000, use_kernel_sinks: bool = True):
         self.lm = lm
-        self.num_streams = int(num_streams)
-        if self.num_streams not in (1, 2):
-            raise ValueError("num_streams must be 1 or 2")
-        self._side_streams = None
-        if self.num_streams == 2:
-            _lib.load().p4c_set_cta_reserve(int(cta_reserve))
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.flat = FlatParams(lm)
@@ -148,50 +137,21 @@ class DataParallelTrainer:
 
     def _forward_backward(self, batch: ItemBatch) -> torch.Tensor:
         self.flat.zero_grad()
-        B = batch.inputs.tensor.shape[0]
-        model = self.lm.model
-        if self.num_streams == 2 and B >= 2 and B % 2 == 0 and hasattr(model, "precompute_static"):
-            loss = self._forward_two_streams(batch, B)
-        else:
-            loss = self.lm.training_step(batch, 1)
+        # stale deferred weight-gradient partials (a backward outside the trainer, or a step that
+        # raised before its flush) must not be accumulated into this step
+        ops.reset_deferred_wgrads()
+        # the reference records feature / dim names on the first batch of every epoch
+        # (lightning.py:541-545); `forward()` / phase="inference" need them after training
+        batch_idx = 0 if not hasattr(self.lm, "output_feature_names") else 1
+        loss = self.lm.training_step(batch, batch_idx)
         self.lm.training_step_losses.clear()
-        loss.backward()
-        if self._side_streams is not None:
-            # the backward kernels of each branch ran on its side stream; autograd only joins
-            # streams that hold AccumulateGrad nodes (ours write into the gradient sinks directly)
-            cur = torch.cuda.current_stream()
-            for s in self._side_streams:
-                cur.wait_stream(s)
-        ops.flush_wgrads()  # batched reduction of the deferred weight-gradient partials
-        return loss.detach()
-
-    def _forward_two_streams(self, batch: ItemBatch, B: int) -> torch.Tensor:
-        """Forward of the two half-batches on two side streams (autograd replays each node of the
-        backward on the stream of its forward).  Static embeddings and the weight images are
-        produced once, before the fork; each branch owns its weight-gradient partial buffers."""
-        lm, model = self.lm, self.lm.model
-        if self._side_streams is None:
-            self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        cur = torch.cuda.current_stream()
-        dt = lm._x_dtype()
-        model.begin_rollout(dt)
         try:
-            with torch.amp.autocast("cuda", dtype=lm.dtype, enabled=lm.dtype in (torch.bfloat16, torch.float16)):
-                model.precompute_static(dt)
-            h = B // 2
-            losses = []
-            for i, s in enumerate(self._side_streams):
-                s.wait_stream(cur)
-                with torch.cuda.stream(s):
-                    ops.set_branch(i)
-                    mb = _slice_batch(batch, i * h, (i + 1) * h)
-                    losses.append(lm.training_step(mb, 1) * 0.5)
-            for s in self._side_streams:
-                cur.wait_stream(s)
-        finally:
-            ops.set_branch(0)
-            model.end_rollout()
-        return losses[0] + losses[1]
+            loss.backward()
+            ops.flush_wgrads()  # batched reduction of the deferred weight-gradient partials
+        except BaseException:
+            ops.reset_deferred_wgrads()
+            raise
+        return loss.detach()
 
     # one optimiser step on `batch` (this rank's shard)
     def _step_impl(self, batch: ItemBatch) -> torch.Tensor:
