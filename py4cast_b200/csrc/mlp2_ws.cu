@@ -80,70 +80,6 @@ struct WsArgs {
   uint32_t batch, ntiles, full_rows;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" : : "r"(smem_u32(bar)) : "memory");
-}
-// wait with back-off (role warps wait for microseconds; a hot spin would steal issue slots from
-// the epilogue warps).  Traps after ~seconds instead of hanging the GPU on a protocol error.
-// RELAXED = true: no acquire fence (which would first drain the thread's outstanding global stores /
-// cp.async copies): for waits whose consumer is ordered by tcgen05.fence::after_thread_sync (TMEM
-// reads after a tcgen05.commit) or that only guard the re-use of a buffer (producer: stage free).
-template <int SLEEP_NS, bool RELAXED = false>
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    if (RELAXED) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(addr), "r"(parity)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(addr), "r"(parity)
-          : "memory");
-    }
-    if (done) return;
-    __nanosleep(SLEEP_NS);
-    if (spin > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-__device__ __forceinline__ uint4 ws_pack8(const float* f) {
-  uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
-  return u;
-}
-// bf16x2 -> two floats with integer ops (exact)
-__device__ __forceinline__ void ws_unpack2(uint32_t u, float& lo, float& hi) {
-  lo = __uint_as_float(u << 16);
-  hi = __uint_as_float(u & 0xFFFF0000u);
-}
-__device__ __forceinline__ void ws_unpack8(const uint4& u, float* f) {
-  ws_unpack2(u.x, f[0], f[1]); ws_unpack2(u.y, f[2], f[3]);
-  ws_unpack2(u.z, f[4], f[5]); ws_unpack2(u.w, f[6], f[7]);
-}
-
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid_constant__ WsArgs a) {
   extern __shared__ unsigned char smem_raw[];
   WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));

@@ -183,6 +183,84 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// ---- role-warp synchronisation (warp-specialised kernels) -----------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" : : "r"(smem_u32(bar)) : "memory");
+}
+// wait with back-off (role warps wait for microseconds; a hot spin would steal issue slots from
+// the epilogue warps).  Traps after ~seconds instead of hanging the GPU on a protocol error.
+// RELAXED = true: no acquire fence (which would first drain the thread's outstanding global stores /
+// cp.async copies): for waits whose consumer is ordered by tcgen05.fence::after_thread_sync (TMEM
+// reads after a tcgen05.commit) or that only guard the re-use of a buffer (producer: stage free).
+template <int SLEEP_NS, bool RELAXED = false>
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    if (RELAXED) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    }
+    if (done) return;
+    __nanosleep(SLEEP_NS);
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint4 ws_pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+// bf16x2 -> two floats with integer ops (exact)
+__device__ __forceinline__ void ws_unpack2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xFFFF0000u);
+}
+__device__ __forceinline__ void ws_unpack8(const uint4& u, float* f) {
+  ws_unpack2(u.x, f[0], f[1]); ws_unpack2(u.y, f[2], f[3]);
+  ws_unpack2(u.z, f[4], f[5]); ws_unpack2(u.w, f[6], f[7]);
+}
+
+// TMEM store: 32 lanes x 16 columns of 32-bit (thread i of the warp writes lane base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- segment sum of 64-wide bf16 rows into one 128-row swizzled smem tile ------------------------
 // Row r (< nrows) of the tile = sc[r] * sum_{e in [lo[r], hi[r])} src[sbase[r]*8 + (perm ? perm[e] : e)*64 ..]
 // (lo[r] == ~0u: zero row).  Work items = (row, edge group g < G, 16-byte chunk j < 8) with

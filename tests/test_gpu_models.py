@@ -3,7 +3,7 @@ same weights, and the reference's own model test (tests/test_models.py:63-142) m
 import pytest
 import torch
 
-from helpers import BF16_TOL, FP32_TOL, assert_close, pixel_meshgrid
+from helpers import BF16_TOL, FP32_TOL, REPORT, assert_close, pixel_meshgrid
 
 pytestmark = pytest.mark.gpu
 
@@ -50,11 +50,13 @@ def test_model_forward_backward_vs_oracle(cuda, tmp_path, name, dtype):
     flat_g = torch.cat([p.grad.flatten().cpu() for p in model.parameters()])
     flat_r = torch.cat([p.grad.flatten() for p in ref.parameters()])
     assert_close(flat_g, flat_r, tol, f"{name} all parameter grads")
-    worst = max(
-        ((p.grad.cpu() - q.grad).norm() / (q.grad.norm() + 1e-12)).item()
-        for p, q in zip(model.parameters(), ref.parameters())
-    )
-    assert worst < 50 * tol, f"worst per-parameter gradient error {worst:.2e}"
+    worst, worst_name = 0.0, ""
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        e = ((p.grad.float().cpu() - q.grad).norm() / (q.grad.norm() + 1e-30)).item()
+        if e > worst:
+            worst, worst_name = e, n
+    REPORT.append((f"{name} {dtype}", f"worst per-parameter gradient error ({worst_name})", worst, 5 * tol))
+    assert worst <= 5 * tol, f"worst per-parameter gradient error {worst:.2e} ({worst_name})"
 
 
 def test_model_under_bf16_autocast_selects_bf16(cuda, tmp_path):

@@ -1,0 +1,131 @@
+"""Parity of the configurations bench.py MEASURES, at their full size, against the oracle:
+
+  * BASELINE configs[2]: HiLAM, 3 mesh levels, 512x640 grid, F=21 / F_forcing=21 / F_static=4,
+    T_in=2, diff_ar, T=4, `bf16-true` — prediction, loss and every parameter gradient of one
+    training step vs the fp32 CPU oracle (oracle/graph_ref.HiLAM + the verbatim-pinned
+    oracle/ar_ref rollout and WeightedLoss) at the north-star bf16 bar (2e-2);
+  * BASELINE configs[1]: GraphLAM (flat multi-scale mesh), same grid, scaled_ar T=4, `32-true`, border
+    10 — same quantities at the fp32 bar (1e-5).
+
+Reference semantics: py4cast/lightning.py:479-493 (autocast wrapper: the model runs in bf16, the
+AR state stays fp32), :495-676 (rollout), :806-831 (training_step), losses.py:130-169.
+These are the sizes at which the warp-specialised kernels engage (>= 296 tiles of 128 rows); the
+tests assert that they really ran.
+"""
+import pytest
+import torch
+
+from helpers import BF16_TOL, FP32_TOL, REPORT, assert_close
+
+pytestmark = pytest.mark.gpu
+
+H, W = 512, 640
+
+
+def _setup(tmp_path, model_name, strategy, precision, T):
+    from oracle import graph_ref
+    from py4cast_b200.datasets import synthetic_dataset_info
+    from py4cast_b200.graph_build import build_mesh_graph
+    from py4cast_b200.lightning import AutoRegressiveLightning
+
+    info = synthetic_dataset_info(H, W)  # Titan-shaped: F=21, F_forcing=21, F_static=4, border 10
+    hier = model_name != "GraphLAM"
+    settings = {"tmp_dir": str(tmp_path)}
+    if hier:
+        settings["n_max_levels"] = 3
+    torch.manual_seed(0)
+    lm = AutoRegressiveLightning(
+        settings_init_args=settings, dataset_info=info, num_input_steps=2, num_pred_steps_train=T,
+        batch_size=1, model_name=model_name,
+        losses=[{"class": "WeightedLoss", "weight": 1.0, "params": {"loss": "MSELoss", "reduction": "none"}}],
+        training_strategy=strategy, precision=precision,
+    )
+    graph = build_mesh_graph(info.statics.meshgrid, hier, 3 if hier else None)
+    ref = getattr(graph_ref, model_name)(lm.model.in_channels, lm.model.out_channels, graph)
+    ref.load_state_dict(lm.model.state_dict())
+    return lm, ref, info
+
+
+def _oracle_step(ref, info, batch, strategy):
+    """fp32 CPU: rollout + WeightedLoss(MSE) + backward.  Returns (pred, loss)."""
+    from oracle import ar_ref
+
+    fn = info.shortnames["input_output"]
+    std, mean = info.diff_stats.to_list("std", fn), info.diff_stats.to_list("mean", fn)
+    w = torch.tensor([info.state_weights[n] for n in fn]) / std**2
+    border = info.statics.border_mask.flatten(0, 1)
+    static = info.statics.grid_statics.tensor.flatten(0, 1).unsqueeze(0)
+    tgt = batch.outputs.tensor.flatten(2, 3)
+    pred = ar_ref.ar_rollout(
+        ref, batch.inputs.tensor.flatten(2, 3), batch.forcing.tensor.flatten(2, 3), tgt, static, border,
+        1 - border, std, mean, strategy,
+    )
+    loss = ar_ref.weighted_loss(pred, tgt, torch.ones_like(tgt), w, (1 - border).squeeze(-1),
+                                (1 - border).sum().item()).mean()
+    loss.backward()
+    return pred.detach(), loss.detach()
+
+
+def _compare(lm, ref, pred_g, loss_g, pred_r, loss_r, tol, tag):
+    assert_close(pred_g.float().cpu().reshape(pred_r.shape), pred_r, tol, f"{tag} prediction (B,T,N,F)")
+    for t in range(pred_r.shape[1]):
+        assert_close(pred_g[:, t].float().cpu().reshape(pred_r[:, t].shape), pred_r[:, t], tol,
+                     f"{tag} prediction, AR step {t}")
+    assert_close(loss_g.float().cpu(), loss_r, tol, f"{tag} loss")
+    flat_g = torch.cat([p.grad.flatten().float().cpu() for p in lm.model.parameters()])
+    flat_r = torch.cat([p.grad.flatten() for p in ref.parameters()])
+    assert_close(flat_g, flat_r, tol, f"{tag} all parameter gradients")
+    worst, worst_name = 0.0, ""
+    for (n, p), (_, q) in zip(lm.model.named_parameters(), ref.named_parameters()):
+        e = ((p.grad.float().cpu() - q.grad).norm() / (q.grad.norm() + 1e-30)).item()
+        if e > worst:
+            worst, worst_name = e, n
+    REPORT.append((tag, f"worst per-parameter gradient error ({worst_name})", worst, 5 * tol))
+    assert worst <= 5 * tol, f"{tag}: worst per-parameter gradient error {worst:.3e} ({worst_name}) > {5 * tol:.1e}"
+
+
+def test_benchmarked_hilam_bf16_diff_ar_T4_vs_oracle(cuda, tmp_path):
+    """The exact bench.py workload (configs[2]) at batch 1: error growth over 4 AR steps x 46
+    InteractionNets in bf16 storage stays within the north-star bar."""
+    from py4cast_b200 import _lib
+    from py4cast_b200.datasets import synthetic_batch
+    from py4cast_b200.trainer import _fresh
+
+    T = 4
+    lm, ref, info = _setup(tmp_path, "HiLAM", "diff_ar", "bf16-true", T)
+    lm = lm.to(cuda)
+    cpu_batch = synthetic_batch(info, 1, 2, T, seed=11)
+    gpu_batch = synthetic_batch(info, 1, 2, T, seed=11, device=cuda)
+    lib = _lib.load()
+    ws0 = lib.p4c_ws_launch_count()
+    with torch.no_grad():
+        pred, _ = lm.common_step(_fresh(gpu_batch), 0, "train")
+    loss = lm.training_step(_fresh(gpu_batch), 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert lib.p4c_ws_launch_count() > ws0, "the pipelined forward kernel did not run at bench size"
+    pred_r, loss_r = _oracle_step(ref, info, cpu_batch, "diff_ar")
+    _compare(lm, ref, pred.tensor.detach(), loss.detach(), pred_r, loss_r, BF16_TOL, "titan HiLAM bf16 diff_ar T=4")
+
+
+def test_config1_graphlam_fp32_scaled_ar_T4_vs_oracle(cuda, tmp_path):
+    """BASELINE configs[1]: GraphLAM, fp32, 4-step scaled AR rollout with a 10-pixel border blend."""
+    from py4cast_b200.datasets import synthetic_batch
+    from py4cast_b200.trainer import _fresh
+
+    T = 4
+    lm, ref, info = _setup(tmp_path, "GraphLAM", "scaled_ar", "32-true", T)
+    lm = lm.to(cuda)
+    cpu_batch = synthetic_batch(info, 1, 2, T, seed=12)
+    gpu_batch = synthetic_batch(info, 1, 2, T, seed=12, device=cuda)
+    with torch.no_grad():
+        pred, _ = lm.common_step(_fresh(gpu_batch), 0, "train")
+    loss = lm.training_step(_fresh(gpu_batch), 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    pred_r, loss_r = _oracle_step(ref, info, cpu_batch, "scaled_ar")
+    # border rows are the ground truth, bit for bit (lightning.py:625-633)
+    border = info.statics.border_mask.flatten(0, 1).squeeze(-1).bool()
+    tgt = cpu_batch.outputs.tensor.flatten(2, 3)
+    assert torch.equal(pred.tensor.detach().cpu().reshape(tgt.shape)[:, :, border], tgt[:, :, border])
+    _compare(lm, ref, pred.tensor.detach(), loss.detach(), pred_r, loss_r, FP32_TOL, "titan GraphLAM fp32 scaled_ar T=4")
