@@ -217,8 +217,8 @@ typedef struct {
   const float* dy_a_scale;
   int64_t dy_a_batch_stride;
   const void* dy_b;
-  const void* h1;        /* saved by forward */
-  const float* stats;    /* saved by forward (layer_norm only) */
+  const void* h1;        /* saved by forward; may be NULL when p4c_mlp_bwd_caps(m) & 1 */
+  const float* stats;    /* saved by forward (layer_norm only); NULL with h1 */
   void* dh1_out;
   void* dx[P4C_MAX_SRC];
   int32_t dx_ld[P4C_MAX_SRC];
@@ -232,7 +232,32 @@ typedef struct {
    * 2: this call ADDS to the partials already in the workspace (same grid), reduction deferred.
    * Deferred modes need a workspace that belongs to this MLP alone (g_* are ignored).          */
   int32_t partials_mode;
+  /* ---- outputs only the pipelined recomputing backward engine produces (see p4c_mlp_bwd_caps) ----
+   * dx0_batch_sum: optional [rows][64]: sum over the samples of dh1[b] x W1[:, K-block of src[0]] — the
+   *   gradient of a 64-wide identity-indexed src[0] that is SHARED by the batch (batch_stride 0: static
+   *   edge embeddings), written (not accumulated).  Replaces a (B, E, 64) input gradient + batch sum.
+   * dx_group_out: optional [batch][full_rows / dx_group][64], ACCUMULATED in place: the input gradient
+   *   of gathered source `dx_group_src` when row r gathers source row r / dx_group (receiver-sorted
+   *   edges of uniform in-degree dx_group = 1, 2, 4 or 8): out[b][r / group] += sum over the group's
+   *   rows of dh1 x W1[:, block].  Replaces one p4c_seg_linear pass over dh1.                          */
+  void* dx0_batch_sum;
+  void* dx_group_out;
+  int32_t dx_group;
+  int32_t dx_group_src;
 } p4c_mlp_bwd_t;
+
+/* Capabilities of the backward engine that will serve the problem `m` (as the BACKWARD describes it:
+ * segment-sum sources replaced by their saved sums), bit mask:
+ *   1  recomputes h1 and the LayerNorm statistics from the sources: g->h1 / g->stats may be NULL, i.e.
+ *      the forward need not save them (pass save_h1 = save_stats = NULL).  Not valid with dy_a_scale.
+ *   2  produces dx0_batch_sum        4  produces dx_group_out
+ * 0 = the classic engines (h1 and stats required, none of the extra outputs).  The pipelined engine
+ * (one persistent CTA per SM: producer / MMA / two compute groups, 512 TMEM columns) takes bf16 calls
+ * with LayerNorm, 64 outputs, packed weights and at least p4c_get_ws_bwd_min_tiles() 128-row tiles. */
+int32_t p4c_mlp_bwd_caps(const p4c_mlp_t* m);
+void p4c_set_ws_bwd_min_tiles(int64_t n); /* n <= 0: default (2 * 148; env P4C_WS_BWD_MIN_TILES) */
+int64_t p4c_get_ws_bwd_min_tiles(void);
+int64_t p4c_ws_bwd_launch_count(void);
 
 /* number of per-CTA partial blocks p4c_mlp_backward writes for this problem (its grid) */
 int32_t p4c_mlp_wgrad_blocks(const p4c_mlp_t* m);

@@ -81,6 +81,10 @@ class MlpBwd(C.Structure):
         ("wgrad_partials", C.c_void_p),
         ("wgrad_partials_floats", C.c_int64),
         ("partials_mode", C.c_int32),
+        ("dx0_batch_sum", C.c_void_p),
+        ("dx_group_out", C.c_void_p),
+        ("dx_group", C.c_int32),
+        ("dx_group_src", C.c_int32),
     ]
 
 
@@ -151,6 +155,10 @@ SYMBOLS = {
     "p4c_set_ws_min_tiles": (None, [_i64]),
     "p4c_get_ws_min_tiles": (_i64, []),
     "p4c_ws_launch_count": (_i64, []),
+    "p4c_mlp_bwd_caps": (_i32, [C.POINTER(Mlp)]),
+    "p4c_set_ws_bwd_min_tiles": (None, [_i64]),
+    "p4c_get_ws_bwd_min_tiles": (_i64, []),
+    "p4c_ws_bwd_launch_count": (_i64, []),
     "p4c_set_bwd_tpr": (None, [C.c_int]),
     "p4c_get_bwd_tpr": (C.c_int, []),
     "p4c_get_engine": (_int, []),

@@ -46,6 +46,11 @@ int launch_wgrad_reduce_single(const p4c_wgrad_t* e, cudaStream_t st);
 bool tc_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g);
 int tc_backward_grid(const p4c_mlp_t* m);
 int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st);
+// warp-specialised pipelined backward that recomputes h1 / LayerNorm statistics (mlp2_ws_bwd.cu)
+bool ws_backward_shape_ok(const p4c_mlp_t* m);
+bool ws_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g);
+int ws_backward_grid(const p4c_mlp_t* m);
+int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int total_blocks, cudaStream_t st);
 // P4C_ENGINE=simt forces the CUDA-core engine for every call (A/B testing); default: tensor cores
 // wherever the shape allows (bf16 storage, 64-wide sources)
 bool tc_engine_enabled();

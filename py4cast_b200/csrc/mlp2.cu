@@ -819,8 +819,14 @@ extern "C" int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m) {
 extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream) {
   int rc = validate(m);
   if (rc) return rc;
-  P4C_REQUIRE(g != nullptr && g->dy_a != nullptr && g->h1 != nullptr, "mlp_backward: dy_a / h1 null");
-  P4C_REQUIRE(!m->layer_norm || g->stats != nullptr, "mlp_backward: LayerNorm stats missing");
+  P4C_REQUIRE(g != nullptr && g->dy_a != nullptr, "mlp_backward: dy_a null");
+  // the pipelined engine recomputes h1 and the LayerNorm statistics; every other engine reads them
+  const bool ws = tc_engine_enabled() && ws_backward_supported(m, g);
+  P4C_REQUIRE(ws || g->h1 != nullptr,
+              "mlp_backward: h1 null (only calls with p4c_mlp_bwd_caps(m) & 1 and no dy_a_scale may omit it)");
+  P4C_REQUIRE(ws || !m->layer_norm || g->stats != nullptr, "mlp_backward: LayerNorm stats missing");
+  P4C_REQUIRE(ws || (!g->dx_group_out && !g->dx0_batch_sum),
+              "mlp_backward: dx_group_out / dx0_batch_sum need the pipelined engine (p4c_mlp_bwd_caps)");
   P4C_REQUIRE(g->wgrad_partials != nullptr &&
                   g->wgrad_partials_floats >= p4c_mlp_wgrad_partial_floats(m),
               "mlp_backward: wgrad workspace too small");
@@ -830,7 +836,12 @@ extern "C" int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void
   P4C_REQUIRE(g->partials_mode >= 0 && g->partials_mode <= 2, "mlp_backward: bad partials_mode %d", g->partials_mode);
   cudaStream_t st = (cudaStream_t)stream;
   int grid;
-  if (tc_engine_enabled() && tc_backward_supported(m, g)) {
+  if (ws) {
+    grid = ws_backward_grid(m);
+    rc = launch_mlp2_ws_backward(m, g, p4c_mlp_wgrad_blocks(m), st);
+    if (rc) return rc;
+    if (g->partials_mode != 0) return P4C_OK;
+  } else if (tc_engine_enabled() && tc_backward_supported(m, g)) {
     grid = tc_backward_grid(m);
     rc = launch_mlp2_tc_backward(m, g, st);
     if (rc) return rc;

@@ -40,33 +40,6 @@ struct BwdCtl {
 };
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
-// column sums over the 32 lanes of a warp (fixed order): a transposing butterfly that halves the
-// columns a lane holds at every step.  N = 32: lane l ends with the sum of column l; N = 16: lanes
-// 2c and 2c+1 both end with the sum of column c.
-template <int N>
-__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
-  int n = N;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    if (n > 1) {
-      const int h = n / 2;
-      const bool hi = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < N / 2; ++i) {
-        if (i < h) {
-          const float send = hi ? v[i] : v[i + h];
-          const float keep = hi ? v[i + h] : v[i];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-      }
-      n = h;
-    } else {
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-    }
-  }
-  return v[0];
-}
-
 // bf16x2 -> two floats with integer ops (exact)
 __device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
   lo = __uint_as_float(u << 16);
@@ -96,21 +69,6 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 #ifndef P4C_BWD_PACKED_SILU
 #define P4C_BWD_PACKED_SILU 0
 #endif
-__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf2_tanh(uint32_t a) {
-  uint32_t d;
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
-  return d;
-}
 // h (bf16x2) -> a = h * sigmoid(h), g = sigmoid(h) * (1 + h * (1 - sigmoid(h)))
 __device__ __forceinline__ void bf2_silu_and_grad(uint32_t h, uint32_t& a, uint32_t& g) {
   constexpr uint32_t HALF = 0x3F003F00u, NEG1 = 0xBF80BF80u;  // (0.5, 0.5), (-1, -1)

@@ -360,6 +360,50 @@ __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ s
   if (trace) trace[14] = clock64();
 }
 
+// column sums over the 32 lanes of a warp (fixed order): a transposing butterfly that halves the
+// columns a lane holds at every step.  N = 32: lane l ends with the sum of column l; N = 16: lanes
+// 2c and 2c+1 both end with the sum of column c.
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
+  int n = N;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int h = n / 2;
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < h) {
+          const float send = hi ? v[i] : v[i + h];
+          const float keep = hi ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  return v[0];
+}
+
+// ---- packed bf16x2 arithmetic (two elements per instruction) -----------------------------------------
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_tanh(uint32_t a) {
+  uint32_t d;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
 // ---- K-blocks of the layer-1 input ----------------------------------------------------------------
 // A source of width w contributes ceil(w/64) blocks of 64 columns (the last one zero-padded): the
 // unit of the gather (one 128x64 bf16 smem tile), of the W1 image and of the dW1 / dX products.

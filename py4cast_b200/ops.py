@@ -534,6 +534,13 @@ def empty_rows(shape: Sequence[int], dtype: torch.dtype, device, zero: bool = Fa
     return buf[..., :w]
 
 
+def _bwd_recomputes(lib, desc: Mlp) -> bool:
+    """True when the backward of the problem `desc` (described as the BACKWARD sees it: plain sources)
+    will be served by the pipelined engine that recomputes h1 / LayerNorm statistics
+    (p4c_mlp_bwd_caps & 1): the forward then saves neither."""
+    return bool(lib.p4c_mlp_bwd_caps(C.byref(desc)) & 1)
+
+
 # -------------------------------------------------------------------- fused MLP
 class _MLPFn(torch.autograd.Function):
     """y = [LN](W2 silu(W1 x + b1) + b2) [+ x]   for one dense, identity-indexed source."""
@@ -555,14 +562,12 @@ class _MLPFn(torch.autograd.Function):
         dt = x.dtype
         need_grad = any(ctx.needs_input_grad)
         out = torch.empty((R, out_features) if shared else (B, R, out_features), dtype=dt, device=x.device)
-        h1 = torch.empty(B * R, HIDDEN, dtype=dt, device=x.device) if need_grad else None
-        stats = (
-            torch.empty(B * R, 2, dtype=torch.float32, device=x.device)
-            if (need_grad and gamma is not None)
-            else None
-        )
         desc = Mlp()
         _fill_mlp(desc, R, B, 0, [_SrcSpec(x)], (w1, b1, w2, b2, gamma, beta), out_features, dt, meta)
+        # the pipelined backward engine recomputes h1 and the LayerNorm statistics: nothing to save
+        save = need_grad and not _bwd_recomputes(lib, desc)
+        h1 = torch.empty(B * R, HIDDEN, dtype=dt, device=x.device) if save else None
+        stats = torch.empty(B * R, 2, dtype=torch.float32, device=x.device) if (save and gamma is not None) else None
         check(
             lib.p4c_mlp_forward(C.byref(desc), ptr(x) if residual else None, ptr(out), None,
                                 ptr(h1), ptr(stats), stream()),
@@ -693,11 +698,11 @@ class _InteractionNetFn(torch.autograd.Function):
         msg = None if fuse_epilogue else torch.empty(B, E, HIDDEN, dtype=dt, device=dev)
         aggr = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
         edge_out = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if update_edges else None
-        h1_e = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if need_grad else None
-        st_e = torch.empty(B, E, 2, dtype=torch.float32, device=dev) if need_grad else None
+        edge_descs = []
         for gidx, (grp, w) in enumerate(zip(gi.groups, ew)):
             n = grp.stop - grp.start
             if n == 0:
+                edge_descs.append(None)
                 continue
             desc = Mlp()
             _fill_mlp(
@@ -709,11 +714,23 @@ class _InteractionNetFn(torch.autograd.Function):
                 ],
                 w, HIDDEN, dt, metas[gidx],
             )
+            edge_descs.append(desc)
+        # h1 / LayerNorm statistics are saved only for the engines that read them back: the pipelined
+        # backward recomputes both (mean aggregation scales dy per row, which that engine does not take)
+        save_e = need_grad and not (
+            tc and not mean and all(d is None or _bwd_recomputes(lib, d) for d in edge_descs))
+        h1_e = torch.empty(B, E, HIDDEN, dtype=dt, device=dev) if save_e else None
+        st_e = torch.empty(B, E, 2, dtype=torch.float32, device=dev) if save_e else None
+        for gidx, (grp, w) in enumerate(zip(gi.groups, ew)):
+            n = grp.stop - grp.start
+            if n == 0:
+                continue
+            desc = edge_descs[gidx]
             o = grp.start * HIDDEN
             args = (
                 _off(edge_out, o) if update_edges else None,
-                _off(h1_e, o) if need_grad else None,
-                _off(st_e, grp.start * 2) if need_grad else None,
+                _off(h1_e, o) if save_e else None,
+                _off(st_e, grp.start * 2) if save_e else None,
             )
             if fuse_epilogue:
                 check(
@@ -732,8 +749,16 @@ class _InteractionNetFn(torch.autograd.Function):
 
         rec_b = rec if rec.dim() == 3 else rec.unsqueeze(0).expand(B, Nr, HIDDEN).contiguous()
         rec_out = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev)
-        h1_n = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev) if need_grad else None
-        st_n = torch.empty(B, Nr, 2, dtype=torch.float32, device=dev) if need_grad else None
+        save_n = need_grad
+        if tc and need_grad:
+            save_n = False
+            for ci, ((n0, n1), w) in enumerate(zip(node_chunks, nw)):
+                bdesc = Mlp()  # the problem as the backward describes it (saved sums as plain rows)
+                _fill_mlp(bdesc, n1 - n0, B, Nr, [_SrcSpec(rec_b, row_offset=n0), _SrcSpec(aggr, row_offset=n0)], w,
+                          HIDDEN, dt, metas[n_eg + ci])
+                save_n = save_n or not _bwd_recomputes(lib, bdesc)
+        h1_n = torch.empty(B, Nr, HIDDEN, dtype=dt, device=dev) if save_n else None
+        st_n = torch.empty(B, Nr, 2, dtype=torch.float32, device=dev) if save_n else None
         for ci, ((n0, n1), w) in enumerate(zip(node_chunks, nw)):
             desc = Mlp()
             if seg_in_prologue:
@@ -746,8 +771,8 @@ class _InteractionNetFn(torch.autograd.Function):
             check(
                 lib.p4c_mlp_forward(
                     C.byref(desc), _off(rec_b, o), _off(rec_out, o), None,
-                    _off(h1_n, o) if need_grad else None,
-                    _off(st_n, n0 * 2) if need_grad else None, stream(),
+                    _off(h1_n, o) if save_n else None,
+                    _off(st_n, n0 * 2) if save_n else None, stream(),
                 ),
                 "p4c_mlp_forward(node)",
             )
@@ -804,7 +829,8 @@ class _InteractionNetFn(torch.autograd.Function):
             o = n0 * HIDDEN
             g = MlpBwd()
             g.dy_a, g.dy_a_batch_stride = _off(d_rec_out, o), Nr * HIDDEN
-            g.h1, g.stats = _off(h1_n, o), _off(st_n, n0 * 2)
+            if h1_n is not None:
+                g.h1, g.stats = _off(h1_n, o), _off(st_n, n0 * 2)
             g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_rec, o), HIDDEN, 0
             g.dx[1], g.dx_ld[1], g.dx_accumulate[1] = _off(d_aggr, o), HIDDEN, 0
             g.dx0_add_dy = 2
@@ -848,8 +874,15 @@ class _InteractionNetFn(torch.autograd.Function):
             g.dy_a_scale = ptr(gi.by_rec.inv_deg) if ctx.mean else None
             g.dy_a_batch_stride = Nr * HIDDEN
             g.dy_b = _off(d_edge_out, o) if d_edge_out is not None else None
-            g.h1, g.stats = _off(h1_e, o), _off(st_e, grp.start * 2)
+            if h1_e is not None:
+                g.h1, g.stats = _off(h1_e, o), _off(st_e, grp.start * 2)
             g.dh1_out = _off(dh1, o)
+            # receiver-sorted edges of uniform in-degree: the pipelined engine sums the receiver gradient
+            # over each group of rows in its epilogue and accumulates it into d_rec (no pass over dh1)
+            rec_in_epilogue = (tc and need_rec and gi.uniform_deg > 0 and n_eg == 1 and not ctx.mean
+                               and bool(lib.p4c_mlp_bwd_caps(C.byref(desc)) & 4))
+            if rec_in_epilogue:
+                g.dx_group_out, g.dx_group, g.dx_group_src = ptr(d_rec), gi.uniform_deg, 2
             if need_edge and not edge_by_linearity:
                 g.dx[0], g.dx_ld[0], g.dx_accumulate[0] = _off(d_edge, o), HIDDEN, 0
                 g.dx0_add_dy = 1 if d_edge_out is not None else 0
@@ -862,7 +895,7 @@ class _InteractionNetFn(torch.autograd.Function):
                     bc = _batch_rows_csr(gi, B, dev)
                     seg_linear(dh1.view(1, B * E, HIDDEN), Csr(bc.rowptr[grp.start: grp.stop + 1], bc.perm, n),
                                1, w[0], 0, d_edge[grp.start: grp.stop].unsqueeze(0), False, meta=metas[gidx])
-                if need_rec:
+                if need_rec and not rec_in_epilogue:
                     seg_linear(dh1, grp.by_rec, B, w[0], 2 * HIDDEN, d_rec, True, meta=metas[gidx])
                 if need_send:
                     if same_nodes:
