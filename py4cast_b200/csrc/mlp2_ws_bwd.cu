@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       uint32_t nn[2] = {0u, 0u};
       int stage[2] = {0, 0};
       bool done[2] = {ntl < 1, ntl < 2};
-      uint32_t acc2 = 0u, acc1 = 0u;  // dW2 / dW1 accumulators: the first product issued into each overwrites
+      // The weight-gradient products are issued in TILE order (g3_next / g4_next), whatever the relative
+      // progress of the two contexts: the fp32 accumulation order, and with it every bit of the result,
+      // is the same in every run.  The first product issued into an accumulator overwrites it.
+      uint32_t g3_next = 0u, g4_next = 0u;
       while (!(done[0] && done[1])) {
         bool progress = false;
 #pragma unroll
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
             stage[c] = 2;
             progress = true;
           } else if (stage[c] == 2) {
-            if (!wb_mbar_test(&S.dh2_full[c], par)) continue;
+            if (g3_next != t || !wb_mbar_test(&S.dh2_full[c], par)) continue;
             tc_fence_after();
 #pragma unroll
             for (int q = 0; q < 4; ++q)  // G2: da1 = dh2 W2  (W2 tile [o][h]: K = o along the rows, N = h contiguous)
@@ -283,25 +286,25 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
 #pragma unroll
             for (int q = 0; q < 8; ++q)  // G3: dW2 += [a1 | 1]^T dh2 (K = 128 tile rows, 16 per MMA)
               mma_bf16_ss(tmem + WB_COL_DW2, make_desc_sw128(a1 + q * 2048, ones - (a1 + q * 2048), 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (acc2 | q) ? 1u : 0u);
-            acc2 = 1u;
+                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
+            g3_next = t + 1;
             mma_commit(&S.da1_full[c]);
             stage[c] = 3;
             progress = true;
           } else if (stage[c] == 3) {
-            if (!wb_mbar_test(&S.dh1_full[c], par)) continue;
+            if (g4_next != t || !wb_mbar_test(&S.dh1_full[c], par)) continue;
             tc_fence_after();
 #pragma unroll
             for (int q = 0; q < 8; ++q)  // G4: dW1 (K-blocks 0, 1) += [X0 | X1]^T dh1
               mma_bf16_ss(tmem + WB_COL_DW1A, make_desc_sw128(xa + q * 2048, WB_BLK, 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (acc1 | q) ? 1u : 0u);
+                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {  // dW1 (K-block 2) and db1: [X2 | 1]^T dh1, or [1 | 1]^T dh1
               const uint32_t ab = nblk == 3 ? xa + 2 * WB_BLK + q * 2048 : ones;
               mma_bf16_ss(tmem + WB_COL_DW1B, make_desc_sw128(ab, ones - ab, 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (acc1 | q) ? 1u : 0u);
+                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
             }
-            acc1 = 1u;
+            g4_next = t + 1;
             mma_commit(&S.x_empty[c]);
             stage[c] = 4;
             progress = true;
