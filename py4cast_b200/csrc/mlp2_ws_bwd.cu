@@ -9,7 +9,7 @@
 //   warps 16-19 producer   cp.async gather of the up-to-three 64-column K-blocks of tile t into the X tiles
 //                          of its context (four complete 128-byte rows per instruction), gather indices
 //                          one tile ahead, L2 prefetch of the next tile's rows.
-//   warp  20    MMA        one lane drives both contexts' state machines, polling the mbarriers:
+//   warps 20-21 MMA        one warp per context (one elected lane issues), in the order of the context's chain:
 //        G0  h1  = X W1^T                               -> chain scratch of the context (TMEM)
 //        G1  h2  = a1 W2^T            (LayerNorm input)  -> chain scratch
 //        G2  da1 = dh2 W2             (W2 tile read MN-major) -> chain scratch
@@ -51,16 +51,18 @@ constexpr int WB_CWARPS = 16, WB_PWARPS = 4;
 constexpr int WB_MMA_WARP = WB_CWARPS + WB_PWARPS;
 constexpr int WB_THREADS = (WB_CWARPS + WB_PWARPS + 4) * 32;  // warps 21-23 only pad the MMA warp's warpgroup
 // registers: the launch bound (768 threads) caps the kernel at 80 per thread; the compute warpgroups
-// raise their share to 96, the producer and MMA warpgroups drop to 48: 16 x 32 x 96 + 8 x 32 x 48 = 768 x 80,
+// raise their share to 96, the producer / MMA warpgroups drop to 40 / 56: 32 x (16 x 96 + 4 x 40 + 4 x 56) = 768 x 80,
 // the pool setmaxnreg redistributes is what the CTA was launched with, not the whole register file
-constexpr int WB_REGS_COMPUTE = 96, WB_REGS_OTHER = 48;
+constexpr int WB_REGS_COMPUTE = 96, WB_REGS_PRODUCER = 40, WB_REGS_MMA = 56;
 constexpr uint32_t WB_TMEM_COLS = 512;
 constexpr uint32_t WB_COL_DW1A = 0, WB_COL_DW1B = 64, WB_COL_DW2 = 128, WB_COL_CH = 192, WB_COL_DX = 320;
 constexpr uint32_t kWbNoRow = 0xFFFFFFFFu;
 constexpr int WB_ONES_BYTES = 2048;
 
 struct WbSmem {
-  uint8_t X[2][P4C_MAX_SRC][WB_BLK];  // per context; the K-blocks of a context are adjacent (M = 128 operands)
+  // X ring: 2 stages of 3 K-blocks, or 3 stages of <= 2 (stage s at X + s * stage_blocks * 16 KB); the K-blocks of
+  // a stage are adjacent (M = 128 operands span two of them)
+  uint8_t X[2 * P4C_MAX_SRC][WB_BLK];
   uint8_t A1[2][WB_BLK];
   uint8_t DH[2][WB_BLK];
   uint8_t W1[P4C_MAX_SRC][WB_WBLK];
@@ -68,9 +70,10 @@ struct WbSmem {
   uint8_t ONES[WB_ONES_BYTES];
   float vec[4][WB_HID];  // b1, b2, gamma, beta
   float4 ln_part[2][2][WB_TM];  // [group][column half][row]
-  uint64_t x_full[2], x_empty[2], h1_full[2], a1_full[2], h2_full[2], dh2_full[2], da1_full[2], dh1_full[2],
+  uint64_t x_full[3], x_empty[3], h1_full[2], a1_full[2], h2_full[2], dh2_full[2], da1_full[2], dh1_full[2],
       dx_full[2];
-  uint64_t dxs_empty;
+  uint64_t dxs_empty[2];
+  uint64_t g3_turn[2], g4_turn[2];  // weight-gradient products of a context's tile issued (MMA warp -> MMA warp)
   uint32_t tmem_base;
 };
 
@@ -85,7 +88,13 @@ struct WbArgs {
   unsigned long long div_magic;  // ceil(2^64 / batch): row block = umul64hi(tile, magic)
   uint32_t batch, ntiles, full_rows;
   int total_blocks;  // partial blocks of this MLP's workspace (blocks >= gridDim.x are zeroed in mode 1)
+  long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's tile 2, see scripts/trace_ws_bwd.py
 };
+// slots 0.. compute group 0 (warp 0), 16.. MMA lane (context 0), 32.. producer warp 0
+#define P4C_WB_TRACE(cond, i)                                   \
+  do {                                                          \
+    if (a.trace && blockIdx.x == 0 && (cond)) a.trace[i] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ bool wb_mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -107,11 +116,18 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   WbSmem& S = *reinterpret_cast<WbSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const p4c_mlp_t& m = a.m;
   const p4c_mlp_bwd_t& g = a.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index is broadcast from lane 0 so that the compiler KNOWS it is warp-uniform: everything the MMA
+  // warps derive from it (context, tile addresses, descriptors) then lives in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nblk = a.kb.nblk;
   const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
   const int nslot = a.nslot;
+  // X ring depth: three stages when a stage is at most two K-blocks (the gather of tile t + 2 then runs while
+  // tiles t, t + 1 compute), two otherwise (shared memory); dX scratch: one per context when a tile has a
+  // single dX product, else one pair shared by the contexts (TMEM columns)
+  const uint32_t xns = nblk <= 2 ? 3u : 2u, xsb = nblk <= 2 ? 2u : 3u;
+  const bool dx_shared = nslot > 1;
 
   // ---- set-up: weight image, ONES, barriers, TMEM
   if (a.zero_x) {
@@ -129,9 +145,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   if (tid < WB_ONES_BYTES / 16)
     reinterpret_cast<uint4*>(S.ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (tid == 0) {
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 3; ++c) {
       mbar_init(&S.x_full[c], WB_PWARPS);
       mbar_init(&S.x_empty[c], 1);
+    }
+    for (int c = 0; c < 2; ++c) {
       mbar_init(&S.h1_full[c], 1);
       mbar_init(&S.a1_full[c], 8);
       mbar_init(&S.h2_full[c], 1);
@@ -140,7 +158,12 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       mbar_init(&S.dh1_full[c], 8);
       mbar_init(&S.dx_full[c], 1);
     }
-    mbar_init(&S.dxs_empty, 8);
+    mbar_init(&S.dxs_empty[0], 8);
+    mbar_init(&S.dxs_empty[1], 8);
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(&S.g3_turn[c], 1);
+      mbar_init(&S.g4_turn[c], 1);
+    }
     mbar_fence_init();
   }
   __syncwarp();
@@ -158,7 +181,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
 
   if (warp >= WB_CWARPS && warp < WB_MMA_WARP) {
     // =============================== producer ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" : : "n"(WB_REGS_OTHER));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" : : "n"(WB_REGS_PRODUCER));
     const int pw = warp - WB_CWARPS;
     const int sub = lane >> 3, j = lane & 7;  // lane -> (row within a group of 4, 16-byte chunk)
     int32_t idx_next[P4C_MAX_SRC];
@@ -197,14 +220,17 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     uint32_t off[P4C_MAX_SRC];
     row_offsets(off);
     for (uint32_t t = 0; t < ntl; ++t) {
-      const uint32_t c = t & 1u, n = t >> 1;
+      const uint32_t c = t % xns, n = t / xns;
+      const bool trc = t == 2 && pw == 0 && lane == 0;
+      P4C_WB_TRACE(trc, 32);
       load_indices(t + 1);
       if (n > 0) mbar_wait_backoff<100, true>(&S.x_empty[c], (n - 1) & 1u);
+      P4C_WB_TRACE(trc, 33);
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
         if (k < nblk) {
           const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[a.kb.src[k]].ptr);
-          const uint32_t xs = smem_u32(S.X[c][k]);
+          const uint32_t xs = smem_u32(S.X[c * xsb + k]);
           const bool fetch = j < a.kb.nchunks[k];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -219,6 +245,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         }
       }
       cp_async_commit();
+      P4C_WB_TRACE(trc, 34);
       // next tile: row offsets (its index loads were issued above) and an L2 prefetch of its rows
       row_offsets(off);
 #pragma unroll
@@ -226,107 +253,126 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         if (k < nblk && off[k] != kWbNoRow)
           wb_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(m.src[a.kb.src[k]].ptr) + (static_cast<size_t>(off[k]) << 3));
       cp_async_wait<0>();
+      P4C_WB_TRACE(trc, 35);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.x_full[c]);
     }
   } else if (warp >= WB_MMA_WARP) {
     // ================================= MMA ==================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" : : "n"(WB_REGS_OTHER));
-    if (warp == WB_MMA_WARP && lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" : : "n"(WB_REGS_MMA));
+    if (warp < WB_MMA_WARP + 2) {
+      // Two MMA warps, one per context (warp-uniform control flow: all 32 lanes run the loop, one elected lane
+      // issues).  Every product is a run of MMAs whose operand descriptors advance by a constant (K-major: 32
+      // bytes = 2 address units per K = 16; MN-major: 16 tile rows = 2048 bytes = 128 units): one base
+      // descriptor per operand, one 64-bit add per MMA.
+      // The weight-gradient products (G3, G4) of tile t are issued only after those of tile t - 1 (the other
+      // warp signals g3_turn / g4_turn after issuing): the fp32 accumulation order, and with it every bit of the
+      // result, is the same in every run.  The first product issued into an accumulator overwrites it.
       constexpr uint32_t IDESC_KK = make_idesc_bf16(WB_TM, WB_HID, 0, 0);  // A, B K-major
       constexpr uint32_t IDESC_KM = make_idesc_bf16(WB_TM, WB_HID, 0, 1);  // A K-major, B MN-major
       constexpr uint32_t IDESC_MM = make_idesc_bf16(WB_TM, WB_HID, 1, 1);  // A, B MN-major
-      const uint32_t ones = smem_u32(S.ONES), w2 = smem_u32(S.W2);
-      uint32_t nn[2] = {0u, 0u};
-      int stage[2] = {0, 0};
-      bool done[2] = {ntl < 1, ntl < 2};
-      // The weight-gradient products are issued in TILE order (g3_next / g4_next), whatever the relative
-      // progress of the two contexts: the fp32 accumulation order, and with it every bit of the result,
-      // is the same in every run.  The first product issued into an accumulator overwrites it.
-      uint32_t g3_next = 0u, g4_next = 0u;
-      while (!(done[0] && done[1])) {
-        bool progress = false;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (done[c]) continue;
-          const uint32_t n = nn[c], t = 2u * n + c, par = n & 1u;
-          const uint32_t ch = tmem + WB_COL_CH + c * WB_HID;
-          const uint32_t xa = smem_u32(S.X[c][0]), a1 = smem_u32(S.A1[c]), da = smem_u32(S.DH[c]);
-          if (stage[c] == 0) {
-            if (!wb_mbar_test(&S.x_full[c], par)) continue;
-            tc_fence_after();
-            for (int k = 0; k < nblk; ++k) {  // G0: h1 = X W1^T (the forward's GEMM 1, same operand order)
-              const uint32_t xk = xa + k * WB_BLK, wa = smem_u32(S.W1[k]);
-              const int nk = (a.kb.kvalid[k] + 15) >> 4;
-              for (int q = 0; q < nk; ++q)
-                mma_bf16_ss(ch, make_desc_sw128(xk + q * 32, 16, 1024), make_desc_sw128(wa + q * 32, 16, 1024),
-                            IDESC_KK, (k | q) ? 1u : 0u);
-            }
-            mma_commit(&S.h1_full[c]);
-            stage[c] = 1;
-            progress = true;
-          } else if (stage[c] == 1) {
-            if (!wb_mbar_test(&S.a1_full[c], par)) continue;
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)  // G1: h2 = a1 W2^T
-              mma_bf16_ss(ch, make_desc_sw128(a1 + q * 32, 16, 1024), make_desc_sw128(w2 + q * 32, 16, 1024),
-                          IDESC_KK, q ? 1u : 0u);
-            mma_commit(&S.h2_full[c]);
-            stage[c] = 2;
-            progress = true;
-          } else if (stage[c] == 2) {
-            if (g3_next != t || !wb_mbar_test(&S.dh2_full[c], par)) continue;
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)  // G2: da1 = dh2 W2  (W2 tile [o][h]: K = o along the rows, N = h contiguous)
-              mma_bf16_ss(ch, make_desc_sw128(da + q * 32, 16, 1024), make_desc_sw128(w2 + q * 2048, WB_WBLK, 1024),
-                          IDESC_KM, q ? 1u : 0u);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)  // G3: dW2 += [a1 | 1]^T dh2 (K = 128 tile rows, 16 per MMA)
-              mma_bf16_ss(tmem + WB_COL_DW2, make_desc_sw128(a1 + q * 2048, ones - (a1 + q * 2048), 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
-            g3_next = t + 1;
-            mma_commit(&S.da1_full[c]);
-            stage[c] = 3;
-            progress = true;
-          } else if (stage[c] == 3) {
-            if (g4_next != t || !wb_mbar_test(&S.dh1_full[c], par)) continue;
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)  // G4: dW1 (K-blocks 0, 1) += [X0 | X1]^T dh1
-              mma_bf16_ss(tmem + WB_COL_DW1A, make_desc_sw128(xa + q * 2048, WB_BLK, 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {  // dW1 (K-block 2) and db1: [X2 | 1]^T dh1, or [1 | 1]^T dh1
-              const uint32_t ab = nblk == 3 ? xa + 2 * WB_BLK + q * 2048 : ones;
-              mma_bf16_ss(tmem + WB_COL_DW1B, make_desc_sw128(ab, ones - ab, 1024),
-                          make_desc_sw128(da + q * 2048, WB_BLK, 1024), IDESC_MM, (t | q) ? 1u : 0u);
-            }
-            g4_next = t + 1;
-            mma_commit(&S.x_empty[c]);
-            stage[c] = 4;
-            progress = true;
-          } else {
-            // G5: dX products into the dX scratch shared by the contexts (free once tile t - 1 was read)
-            if (nslot > 0 && t > 0 && !wb_mbar_test(&S.dxs_empty, (t - 1) & 1u)) continue;
-            tc_fence_after();
-            for (int s = 0; s < nslot; ++s) {
-              const uint32_t wa = smem_u32(S.W1[a.slot_blk[s]]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)  // W1 tile [n][c]: K = n along the rows, N = c contiguous
-                mma_bf16_ss(tmem + WB_COL_DX + s * WB_HID, make_desc_sw128(da + q * 32, 16, 1024),
-                            make_desc_sw128(wa + q * 2048, WB_WBLK, 1024), IDESC_KM, q ? 1u : 0u);
-            }
-            mma_commit(&S.dx_full[c]);
-            nn[c] = n + 1;
-            stage[c] = 0;
-            if (2u * (n + 1) + c >= ntl) done[c] = true;
-            progress = true;
+      constexpr long long KSTEP = 2, MNSTEP = 128;
+      // [tile rows | ONES] as an MN-major M = 128 operand: the address moves on, the ONES block does not
+      constexpr long long ONES_STEP = MNSTEP - (MNSTEP << 16);
+      const uint32_t c = warp - WB_MMA_WARP;
+      const uint32_t ones = smem_u32(S.ONES), a1 = smem_u32(S.A1[c]), da = smem_u32(S.DH[c]);
+      const uint32_t ch = tmem + WB_COL_CH + c * WB_HID;
+      const uint32_t dxc = tmem + WB_COL_DX + (dx_shared ? 0u : c * WB_HID);
+      const uint64_t w2_k = make_desc_sw128(smem_u32(S.W2), 16, 1024);
+      const uint64_t w2_mn = make_desc_sw128(smem_u32(S.W2), WB_WBLK, 1024);
+      const uint64_t a1_k = make_desc_sw128(a1, 16, 1024), a1_ones = make_desc_sw128(a1, ones - a1, 1024);
+      const uint64_t dh_k = make_desc_sw128(da, 16, 1024), dh_mn = make_desc_sw128(da, WB_BLK, 1024);
+      for (uint32_t n = 0, t = c; t < ntl; ++n, t += 2) {
+        const uint32_t par = n & 1u;
+        const uint32_t xst = t % xns, xpar = (t / xns) & 1u;  // X ring stage of the tile
+        const uint32_t xa = smem_u32(S.X[xst * xsb]);
+        // turn of tile t - 1 (the other context's tile n - 1 for context 0, tile n for context 1)
+        const uint32_t tpar = (c == 0 ? n - 1u : n) & 1u;
+        const bool trc = t == 2;
+
+        // ---- G0: h1 = X W1^T (the forward's GEMM 1, same operand order)
+        mbar_wait_backoff<20>(&S.x_full[xst], xpar);
+        P4C_WB_TRACE(trc && lane == 0, 21);
+        tc_fence_after();
+        {
+          uint32_t acc = 0u;
+          for (int k = 0; k < nblk; ++k) {
+            uint64_t xd = make_desc_sw128(xa + k * WB_BLK, 16, 1024), wd = make_desc_sw128(smem_u32(S.W1[k]), 16, 1024);
+            const int nk = (a.kb.kvalid[k] + 15) >> 4;
+            for (int q = 0; q < nk; ++q, xd += KSTEP, wd += KSTEP, acc = 1u) mma_bf16_ss_elect(ch, xd, wd, IDESC_KK, acc);
           }
         }
-        if (!progress) __nanosleep(20);
+        mma_commit_elect(&S.h1_full[c]);
+        P4C_WB_TRACE(trc && lane == 0, 16);
+
+        // ---- G1: h2 = a1 W2^T
+        mbar_wait_backoff<20>(&S.a1_full[c], par);
+        P4C_WB_TRACE(trc && lane == 0, 22);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mma_bf16_ss_elect(ch, a1_k + q * KSTEP, w2_k + q * KSTEP, IDESC_KK, q ? 1u : 0u);
+        mma_commit_elect(&S.h2_full[c]);
+        P4C_WB_TRACE(trc && lane == 0, 17);
+
+        // ---- G2: da1 = dh2 W2 (W2 tile [o][h]: K = o along the rows, N = h contiguous); G3: dW2 += [a1 | 1]^T dh2
+        mbar_wait_backoff<20>(&S.dh2_full[c], par);
+        P4C_WB_TRACE(trc && lane == 0, 23);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mma_bf16_ss_elect(ch, dh_k + q * KSTEP, w2_mn + q * MNSTEP, IDESC_KM, q ? 1u : 0u);
+        if (t > 0) {
+          mbar_wait_backoff<20>(&S.g3_turn[c ^ 1u], tpar);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)  // K = 128 tile rows, 16 per MMA
+          mma_bf16_ss_elect(tmem + WB_COL_DW2, a1_ones + q * ONES_STEP, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
+        tc_fence_before();
+        mbar_arrive_elect(&S.g3_turn[c]);
+        mma_commit_elect(&S.da1_full[c]);
+        P4C_WB_TRACE(trc && lane == 0, 18);
+
+        // ---- G4: dW1 (K-blocks 0, 1) += [X0 | X1]^T dh1; dW1 (K-block 2), db1: [X2 | 1]^T dh1 or [1 | 1]^T dh1
+        mbar_wait_backoff<20>(&S.dh1_full[c], par);
+        P4C_WB_TRACE(trc && lane == 0, 24);
+        if (t > 0) mbar_wait_backoff<20>(&S.g4_turn[c ^ 1u], tpar);
+        tc_fence_after();
+        {
+          const uint64_t x01 = make_desc_sw128(xa, WB_BLK, 1024);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            mma_bf16_ss_elect(tmem + WB_COL_DW1A, x01 + q * MNSTEP, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
+          const uint64_t x2o = nblk == 3 ? make_desc_sw128(xa + 2 * WB_BLK, ones - (xa + 2 * WB_BLK), 1024)
+                                         : make_desc_sw128(ones, 0, 1024);
+          const long long x2step = nblk == 3 ? ONES_STEP : 0ll;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            mma_bf16_ss_elect(tmem + WB_COL_DW1B, x2o + q * x2step, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
+        }
+        tc_fence_before();
+        mbar_arrive_elect(&S.g4_turn[c]);
+        mma_commit_elect(&S.x_empty[xst]);
+        P4C_WB_TRACE(trc && lane == 0, 19);
+
+        // ---- G5: dX products into the dX scratch: the context's own (free once its previous tile was read) or
+        //      the pair shared by the contexts (free once tile t - 1 was read)
+        if (nslot > 0) {
+          if (dx_shared) {
+            if (t > 0) mbar_wait_backoff<20>(&S.dxs_empty[0], (t - 1) & 1u);
+          } else if (n > 0) {
+            mbar_wait_backoff<20>(&S.dxs_empty[c], (n - 1) & 1u);
+          }
+          tc_fence_after();
+          for (int s = 0; s < nslot; ++s) {
+            const uint64_t wd = make_desc_sw128(smem_u32(S.W1[a.slot_blk[s]]), WB_WBLK, 1024);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)  // W1 tile [n][c]: K = n along the rows, N = c contiguous
+              mma_bf16_ss_elect(dxc + s * WB_HID, dh_k + q * KSTEP, wd + q * MNSTEP, IDESC_KM, q ? 1u : 0u);
+          }
+        }
+        mma_commit_elect(&S.dx_full[c]);
+        P4C_WB_TRACE(trc && lane == 0, 20);
       }
     }
   } else {
@@ -339,7 +385,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     const uint32_t a1s = smem_u32(S.A1[grp]), dhs = smem_u32(S.DH[grp]);
     const uint32_t tm_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t tm_ch = tm_lane + WB_COL_CH + grp * WB_HID + col0;
-    const uint32_t tm_dx = tm_lane + WB_COL_DX + col0;
+    const uint32_t tm_dx = tm_lane + WB_COL_DX + (dx_shared ? 0u : grp * WB_HID) + col0;
     const int pair_bar = 1 + grp * 4 + quad;  // named barrier of the two warps that share these rows
     const float* const b1 = S.vec[0] + col0;
     const float* const b2 = S.vec[1] + col0;
@@ -372,8 +418,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         for (int c = 0; c < 4; ++c) dyr[c] = zero4;
       }
 
+      const bool trc = t == 2 && tid == 0;
+      P4C_WB_TRACE(trc, 0);
       // ---- a. h1 -> a1 = SiLU(h1) -> A1 tile; SiLU'(h1) -> registers
-      mbar_wait_backoff<64, true>(&S.h1_full[grp], par);
+      mbar_wait_backoff<32, true>(&S.h1_full[grp], par);
+      P4C_WB_TRACE(trc, 1);
       tc_fence_after();
       uint4 gs[4];
       {
@@ -404,6 +453,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.a1_full[grp]);
+      P4C_WB_TRACE(trc, 2);
 
       // dy += dy_b (identity rows; edge-update / residual branches)
       if (dyb && valid) {
@@ -420,7 +470,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       }
 
       // ---- c. LayerNorm backward from the recomputed h2
-      mbar_wait_backoff<64, true>(&S.h2_full[grp], par);
+      mbar_wait_backoff<32, true>(&S.h2_full[grp], par);
+      P4C_WB_TRACE(trc, 3);
       tc_fence_after();
       {
         float xh[32];
@@ -470,15 +521,18 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.dh2_full[grp]);
+        P4C_WB_TRACE(trc, 4);
         // column sums over the rows of the warp while the tensor core runs G2 / G3
         vacc0 += warp_colsum<32>(xh, lane);
 #pragma unroll
         for (int c = 0; c < 4; ++c) ws_unpack8(dyr[c], xh + c * 8);
         vacc1 += warp_colsum<32>(xh, lane);
+        P4C_WB_TRACE(trc, 5);
       }
 
       // ---- e. dh1 = da1 * SiLU'(h1) -> DH tile (overwrites dh2: G2, G3 are complete), then to HBM
-      mbar_wait_backoff<64, true>(&S.da1_full[grp], par);
+      mbar_wait_backoff<32, true>(&S.da1_full[grp], par);
+      P4C_WB_TRACE(trc, 6);
       tc_fence_after();
       {
         float v[32];
@@ -499,6 +553,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.dh1_full[grp]);
+      P4C_WB_TRACE(trc, 7);
       if (dh1_out) {  // coalesced: lane -> 16-byte chunk j of row 8 i + sub of this warp's rows
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -509,8 +564,22 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         }
       }
 
+      // the group-summed receiver gradient is accumulated in place: pull this lane's slice of the row into L1
+      // while G4 / G5 run (the read-modify-write below would otherwise expose the load latency)
+      const int gsz = g.dx_group;
+      int cbase = 0;
+      if (g.dx_group_out) {
+        if (gsz > 1 && (lane & 1)) cbase += 16;
+        if (gsz > 2 && (lane & 2)) cbase += 8;
+        if (gsz > 4 && (lane & 4)) cbase += 4;
+        if (valid)
+          asm volatile("prefetch.global.L1 [%0];" : : "l"(reinterpret_cast<__nv_bfloat16*>(g.dx_group_out) +
+                                                         static_cast<long long>(orow / gsz) * WB_HID + col0 + cbase));
+      }
       // ---- g. dX epilogues (G4 / G5 complete: the DH and X tiles of the context are free afterwards)
-      mbar_wait_backoff<64, true>(&S.dx_full[grp], par);
+      P4C_WB_TRACE(trc, 8);
+      mbar_wait_backoff<32, true>(&S.dx_full[grp], par);
+      P4C_WB_TRACE(trc, 9);
       tc_fence_after();
       for (int s = 0; s < nslot; ++s) {
         float v[32];
@@ -553,8 +622,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         } else {
           // sum over the `dx_group` consecutive rows (= lanes) that gather the same source row:
           // transposing butterfly (fp32, fixed order; rows beyond the problem hold zeros)
-          const int gsz = g.dx_group;
-          int cbase = 0;
 #define P4C_WB_GRP_STEP(OFF, N)                                              \
           if (gsz > OFF) {                                                   \
             const bool up = (lane & OFF) != 0;                               \
@@ -563,7 +630,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
               const float keep = up ? v[i + (N) / 2] : v[i];                 \
               v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);         \
             }                                                                \
-            if (up) cbase += (N) / 2;                                        \
           }
           P4C_WB_GRP_STEP(1, 32)
           P4C_WB_GRP_STEP(2, 16)
@@ -600,8 +666,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       if (nslot > 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.dxs_empty);
+        if (lane == 0) mbar_arrive(&S.dxs_empty[dx_shared ? 0 : grp]);
       }
+      P4C_WB_TRACE(trc, 10);
     }
   }
 
@@ -792,6 +859,7 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   a.ntiles = static_cast<uint32_t>((rows + WB_TM - 1) / WB_TM * nb);
   a.full_rows = static_cast<uint32_t>(m->full_rows > 0 ? m->full_rows : m->rows);
   a.total_blocks = total_blocks;
+  a.trace = tc_get_trace();
   const int grid = ws_backward_grid(m);
   const size_t smem = sizeof(WbSmem) + 1024;
   static bool configured = false;

@@ -54,6 +54,47 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// Warp-uniform variants for a dedicated MMA warp: EVERY lane of the (converged) warp executes the
+// call, one elected lane issues.  With the issuing code in warp-uniform control flow the descriptors
+// live in uniform registers; under `if (lane == 0)` the compiler wraps every UTCHMMA in an
+// ELECT / BRA.U.ANY "waterfall" loop (~15 instructions per MMA).
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(bar))
+      : "memory");
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
