@@ -405,17 +405,17 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       const bool valid = rr < rows;
       const int32_t orow = valid ? static_cast<int32_t>(bsamp * full + rr) : -1;  // row in the output-like arrays
 
-      // dy part-row: issued before the first wait of the tile
+      // dy part-row: only PREFETCHED (L2) here.  The loads themselves are issued after the proxy fence of
+      // phase a: fence.proxy.async is a MEMBAR.ALL.CTA in SASS and waits for every outstanding global access
+      // of the thread, i.e. an HBM-latency load in flight would stall the hand-over of a1 to the MMA warp
+      // (measured: phase a 1 750 -> 3 900 cycles when dy are identity rows of a tensor larger than L2).
       const __nv_bfloat16* dy_row = dya;
       uint4 dyr[4];
       if (valid) {
         const long long ia = g.dy_a_index ? static_cast<long long>(__ldg(g.dy_a_index + rr)) : static_cast<long long>(rr);
         dy_row = dya + static_cast<long long>(bsamp) * g.dy_a_batch_stride + ia * WB_HID + col0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dyr[c] = *reinterpret_cast<const uint4*>(dy_row + c * 8);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dyr[c] = zero4;
+        wb_prefetch_l2(dy_row);
+        if (dyb) wb_prefetch_l2(dyb + static_cast<long long>(orow) * WB_HID + col0);
       }
 
       const bool trc = t == 2 && tid == 0;
@@ -455,6 +455,13 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       if (lane == 0) mbar_arrive(&S.a1_full[grp]);
       P4C_WB_TRACE(trc, 2);
 
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dyr[c] = *reinterpret_cast<const uint4*>(dy_row + c * 8);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dyr[c] = zero4;
+      }
       // dy += dy_b (identity rows; edge-update / residual branches)
       if (dyb && valid) {
         const __nv_bfloat16* dyb_row = dyb + static_cast<long long>(orow) * WB_HID + col0;
@@ -591,7 +598,39 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
           const int ld = g.dx_ld[src];
           const int nch = a.kb.nchunks[kblk];
           const bool add_dy = kblk == 0 && g.dx0_add_dy != 0;
-          if (valid) {
+          if (!g.dx_accumulate[src]) {
+            // bf16 rows staged in the (free) DH tile, then stored with complete 64-byte row segments per
+            // lane group; the residual pass-through d src0 += dy comes from the registers that still hold dy
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float* o = v + c * 8;
+              float e[8];
+              if (add_dy && valid) {
+                if (g.dx0_add_dy == 2) {
+                  if (dyb) ws_unpack8(*reinterpret_cast<const uint4*>(dy_row + c * 8), e);  // dyr holds dy_a + dy_b
+                  else ws_unpack8(dyr[c], e);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) o[q] += e[q];
+                }
+                if (dyb) {
+                  ws_unpack8(*reinterpret_cast<const uint4*>(dyb + static_cast<long long>(orow) * WB_HID + col0 + c * 8), e);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) o[q] += e[q];
+                }
+              }
+              sts128(dhs + sw128_offset(row, hsel * 4 + c), ws_pack8(o));
+            }
+            __syncwarp();
+            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dx[src]) + a.kb.col0[kblk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + sub;
+              const int32_t orr = __shfl_sync(0xffffffffu, orow, r);
+              const uint4 u = lds128(dhs + sw128_offset(quad * 32 + r, j));
+              if (orr >= 0 && j < nch) *reinterpret_cast<uint4*>(base + static_cast<long long>(orr) * ld + j * 8) = u;
+            }
+            __syncwarp();
+          } else if (valid) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.dx[src]) + a.kb.col0[kblk] +
                                  static_cast<long long>(orow) * ld + col0;
 #pragma unroll
@@ -860,6 +899,14 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   a.full_rows = static_cast<uint32_t>(m->full_rows > 0 ? m->full_rows : m->rows);
   a.total_blocks = total_blocks;
   a.trace = tc_get_trace();
+  {  // developer aid: P4C_WB_TRACE_NBLK=n restricts the phase trace to calls with n K-blocks
+    static int want = -1;
+    if (want < 0) {
+      const char* e = getenv("P4C_WB_TRACE_NBLK");
+      want = e ? atoi(e) : 0;
+    }
+    if (want > 0 && a.kb.nblk != want) a.trace = nullptr;
+  }
   const int grid = ws_backward_grid(m);
   const size_t smem = sizeof(WbSmem) + 1024;
   static bool configured = false;

@@ -111,6 +111,40 @@ def generate_forcings(date: dt.datetime, timedeltas: List[dt.timedelta], grid) -
     ]
 
 
+def external_forcing_scalars(dates: Sequence[dt.datetime], timedeltas: Sequence[dt.timedelta]) -> torch.Tensor:
+    """The host part of the external forcings of a batch, for the input pipeline: a (B * T, 7) float32
+    tensor [hour of day, sin / cos of the solar declination, cos_hour, sin_hour, cos_doy, sin_doy] per
+    (sample, step) — 28 bytes per slot, computed by the data-loading workers with the reference's own date
+    arithmetic (forcingutils.py:19-117) and shipped INSTEAD of five per-pixel channels."""
+    rows = []
+    for d in dates:
+        h, sd, cd = _solar_scalars(d, timedeltas)
+        dt4 = get_year_hour_forcing(d, list(timedeltas)).type(torch.float32)
+        rows.append(torch.cat([h.unsqueeze(1), sd.unsqueeze(1), cd.unsqueeze(1), dt4], dim=1))
+    return torch.cat(rows).to(torch.float32).contiguous()
+
+
+def fill_external_forcings_from_scalars(forcing: torch.Tensor, ch0: int, lat: torch.Tensor, lon: torch.Tensor,
+                                        scalars: torch.Tensor) -> None:
+    """`fill_external_forcings` with the date arithmetic already done (`external_forcing_scalars`, on the
+    device): one kernel launch, nothing on the host — what the training input path calls every step."""
+    if not (forcing.is_cuda and forcing.dtype == torch.float32 and forcing.is_contiguous()):
+        raise _lib.P4CError("fill_external_forcings: forcing must be a contiguous fp32 CUDA tensor")
+    if not (scalars.is_cuda and scalars.dtype == torch.float32 and scalars.dim() == 2 and scalars.shape[1] == 7):
+        raise _lib.P4CError("fill_external_forcings: scalars must be a (B * T, 7) fp32 CUDA tensor")
+    F = forcing.shape[-1]
+    slots = scalars.shape[0]
+    if forcing.numel() != slots * lat.numel() * F:
+        raise ValueError("fill_external_forcings: forcing / scalars / grid sizes do not match")
+    cols = scalars.t().contiguous()  # (7, slots): hour, sin_dec, cos_dec, then the (slots, 4) block below
+    dt4 = scalars[:, 3:7].contiguous()
+    check(
+        _lib.load().p4c_forcing_fill(ptr(lat), ptr(lon), ptr(cols[0]), ptr(cols[1]), ptr(cols[2]), ptr(dt4), slots,
+                                     lat.numel(), ptr(forcing), F, ch0, stream()),
+        "p4c_forcing_fill",
+    )
+
+
 def fill_external_forcings(forcing: torch.Tensor, ch0: int, lat: torch.Tensor, lon: torch.Tensor,
                            dates: Sequence[dt.datetime], timedeltas: Sequence[dt.timedelta]) -> None:
     """Writes [cos_hour, sin_hour, cos_doy, sin_doy, toa_radiation] of every (sample, step) into

@@ -21,7 +21,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Callable, List, Optional
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -126,7 +127,9 @@ class DataParallelTrainer:
         self._static_loss: Optional[torch.Tensor] = None
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._staging: Optional[ItemBatch] = None
-        self._staged_for: Optional[ItemBatch] = None
+        self._staged_for = None
+        self._staging_host: Optional[dict] = None
+        self._ext_grid: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
     def sync_gradients(self) -> float:
         """ONE all-reduce (sum) of the flat gradient buffer; returns the scale that turns the sum
@@ -182,8 +185,59 @@ class DataParallelTrainer:
         with torch.cuda.graph(self._graph):
             self._static_loss = self._forward_backward(_fresh(self._static_batch))
 
-    def load_inputs(self, batch: ItemBatch) -> None:
-        """Copies a (host or device) batch into the captured input buffers (H2D when pinned)."""
+    # ------------------------------------------------------------- input pipeline
+    def configure_external_forcings(self, lat: torch.Tensor, lon: torch.Tensor) -> None:
+        """Declares that the LAST five forcing channels are the external forcings of reference
+        datasets/base.py:503-515 ([cos_hour, sin_hour, cos_doy, sin_doy, toa_radiation], appended after the
+        NWP forcing parameters): `pack_host_batch` then ships their 28-byte-per-slot scalars instead of the
+        fields and `load_inputs` rebuilds them on the device.  lat / lon: CUDA tensors (lat, lon), degrees."""
+        self._ext_grid = (lat.to(torch.float32).contiguous(), lon.to(torch.float32).contiguous())
+
+    def _ship_dtype(self) -> torch.dtype:
+        precision = getattr(getattr(self.lm, "trainer", None), "precision", "32-true")
+        return torch.bfloat16 if precision == "bf16-true" else torch.float32
+
+    def pack_host_batch(self, batch: ItemBatch, dates: Optional[Sequence] = None,
+                        timedeltas: Optional[Sequence] = None) -> HostBatch:
+        """The collate stage of the input pipeline: a host ItemBatch (fp32, every channel, reference
+        base.py:173-195) -> pinned tensors in the form that crosses PCIe (see HostBatch).  With
+        `configure_external_forcings` and `dates` / `timedeltas` (reference date of every sample, lead times of
+        the T steps) the five external channels are dropped and replaced by their scalars."""
+        from .forcingutils import external_forcing_scalars
+
+        f = batch.forcing.tensor
+        ext = None
+        if self._ext_grid is not None and dates is not None:
+            ext = external_forcing_scalars(dates, timedeltas).pin_memory()
+            f = f[..., : f.shape[-1] - 5]
+        pin = lambda t, dt: t.detach().to("cpu", dt).contiguous().pin_memory()  # noqa: E731
+        return HostBatch(inputs=pin(batch.inputs.tensor, torch.float32), outputs=pin(batch.outputs.tensor, torch.float32),
+                         forcing=pin(f, self._ship_dtype()), ext_scalars=ext)
+
+    def _load_host_batch(self, hb: HostBatch, staged: Optional[dict] = None) -> None:
+        """HostBatch (or its staged device copy) -> the captured fp32 input buffers."""
+        src = staged if staged is not None else {"inputs": hb.inputs, "outputs": hb.outputs, "forcing": hb.forcing,
+                                                 "ext": hb.ext_scalars}
+        sb = self._static_batch
+        sb.inputs.tensor.copy_(src["inputs"].reshape(sb.inputs.tensor.shape), non_blocking=True)
+        sb.outputs.tensor.copy_(src["outputs"].reshape(sb.outputs.tensor.shape), non_blocking=True)
+        dst = sb.forcing.tensor
+        fs = src["forcing"]
+        n_ship = fs.shape[-1]
+        dst[..., :n_ship].copy_(fs.reshape(*dst.shape[:-1], n_ship), non_blocking=True)  # cast + channel slice
+        if src["ext"] is not None:
+            from .forcingutils import fill_external_forcings_from_scalars
+
+            ext = src["ext"].to(dst.device, non_blocking=True)
+            fill_external_forcings_from_scalars(dst, n_ship, self._ext_grid[0], self._ext_grid[1], ext)
+        elif n_ship != dst.shape[-1]:
+            raise ValueError("HostBatch ships fewer forcing channels than the model reads and carries no ext_scalars")
+
+    def load_inputs(self, batch) -> None:
+        """Copies a batch into the captured input buffers: an ItemBatch (host or device, fp32, every channel)
+        or a HostBatch (the pinned, slimmed form of `pack_host_batch`)."""
+        if isinstance(batch, HostBatch):
+            return self._load_host_batch(batch)
         for name in ("inputs", "forcing", "outputs"):
             dst = getattr(self._static_batch, name).tensor
             src = getattr(batch, name).tensor
@@ -199,16 +253,32 @@ class DataParallelTrainer:
             raise RuntimeError("call capture() first")
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
-            self._staging = _clone_batch(self._static_batch)
             self._staged_ready = torch.cuda.Event()
             self._staging_free = torch.cuda.Event()
             self._staging_free.record(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._staging_free)  # the previous staged batch was consumed
-            for name in ("inputs", "forcing", "outputs"):
-                dst = getattr(self._staging, name).tensor
-                src = getattr(batch, name).tensor
-                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            if isinstance(batch, HostBatch):
+                # same bytes on the device as on the wire: the cast / channel placement / forcing kernel run
+                # on the compute stream when the batch is consumed
+                dev = self._static_batch.inputs.tensor.device
+                if self._staging_host is None or any(
+                        self._staging_host[k].shape != t.shape or self._staging_host[k].dtype != t.dtype
+                        for k, t in (("inputs", batch.inputs), ("outputs", batch.outputs), ("forcing", batch.forcing))):
+                    self._staging_host = {k: torch.empty(t.shape, dtype=t.dtype, device=dev)
+                                          for k, t in (("inputs", batch.inputs), ("outputs", batch.outputs),
+                                                       ("forcing", batch.forcing))}
+                for k, t in (("inputs", batch.inputs), ("outputs", batch.outputs), ("forcing", batch.forcing)):
+                    self._staging_host[k].copy_(t, non_blocking=True)
+                self._staging_host["ext"] = (None if batch.ext_scalars is None
+                                             else batch.ext_scalars.to(dev, non_blocking=True))
+            else:
+                if self._staging is None:
+                    self._staging = _clone_batch(self._static_batch)
+                for name in ("inputs", "forcing", "outputs"):
+                    dst = getattr(self._staging, name).tensor
+                    src = getattr(batch, name).tensor
+                    dst.copy_(src.reshape(dst.shape), non_blocking=True)
             self._staged_ready.record(self._copy_stream)
         self._staged_for = batch
 
@@ -222,7 +292,10 @@ class DataParallelTrainer:
             if self._staged_for is batch:
                 cur = torch.cuda.current_stream()
                 cur.wait_event(self._staged_ready)
-                self.load_inputs(self._staging)
+                if isinstance(batch, HostBatch):
+                    self._load_host_batch(batch, staged=self._staging_host)
+                else:
+                    self.load_inputs(self._staging)
                 self._staging_free.record(cur)
                 self._staged_for = None
             else:
@@ -232,6 +305,29 @@ class DataParallelTrainer:
         self._graph.replay()
         self.opt.step(grad_scale=self.sync_gradients())
         return self._static_loss
+
+
+@dataclass
+class HostBatch:
+    """What the collate stage hands to `DataParallelTrainer.replay` for one step, in pinned host memory and in
+    the form that crosses PCIe (reference: datasets/base.py:173-195 `collate_fn` builds fp32 tensors of every
+    channel and Lightning moves them as they are):
+      inputs / outputs  fp32 (B, T, lat, lon, F): state and truth stay fp32 (loss and AR state are fp32);
+      forcing           the channels that cannot be generated, in the dtype the model input is built in
+                        (bf16 under `bf16-true`: the forcing only ever feeds the bf16 `x`, so rounding it on
+                        the host is bit-identical to rounding it in the concat kernel);
+      ext_scalars       (B * T, 7) fp32 from `forcingutils.external_forcing_scalars`, or None: the five
+                        date / solar channels are then rebuilt on the device by p4c_forcing_fill instead of
+                        being shipped as per-pixel fields."""
+
+    inputs: torch.Tensor
+    outputs: torch.Tensor
+    forcing: torch.Tensor
+    ext_scalars: Optional[torch.Tensor] = None
+
+    def nbytes(self) -> int:
+        n = sum(t.numel() * t.element_size() for t in (self.inputs, self.outputs, self.forcing))
+        return n + (self.ext_scalars.numel() * 4 if self.ext_scalars is not None else 0)
 
 
 def shard_indices(num_samples: int, rank: int, world: int) -> list:

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--grid", default="512x640")
     a = ap.parse_args()
     from py4cast_b200.datasets import synthetic_dataset_info
     from py4cast_b200.losses import ScaledLoss, WeightedLoss
@@ -33,8 +34,9 @@ def main():
     pk = os.path.join(root, "MEASURED_PEAKS.json")
     peak = float(json.load(open(pk))["hbm_gbs"]) if os.path.isfile(pk) else 6650.0
     dev = torch.device("cuda:0")
-    info = synthetic_dataset_info(512, 640)
-    B, T, N, F = a.batch, a.steps, 512 * 640, info.weather_dim
+    GH, GW = (int(v) for v in a.grid.split('x'))
+    info = synthetic_dataset_info(GH, GW)
+    B, T, N, F = a.batch, a.steps, GH * GW, info.weather_dim
     fn = info.shortnames["input_output"]
     names = ["batch", "timestep", "ngrid", "features"]
     pred = torch.randn(B, T, N, F, device=dev, requires_grad=True)
@@ -74,7 +76,7 @@ def main():
     # external forcings: 5 generated channels of every (sample, step) written into the forcing tensor
     import datetime as dt
     from py4cast_b200 import forcingutils as fu
-    H, W = 512, 640
+    H, W = GH, GW
     lat = torch.linspace(55.4, 37.5, H, device=dev).view(H, 1).expand(H, W).contiguous()
     lon = torch.linspace(-12.0, 16.0, W, device=dev).view(1, W).expand(H, W).contiguous()
     fbuf = torch.zeros(B, T, H, W, info.forcing_dim, device=dev)

@@ -152,3 +152,25 @@ def test_reference_known_answer_solar_forcing_oracle():
     terms = [dt.timedelta(hours=1), dt.timedelta(hours=2), dt.timedelta(hours=3)]
     out = forcing_ref.toa_radiation(lat, lon, dt.datetime(2023, 5, 20, 13), terms)
     assert out.shape == torch.Size((3, 16, 16, 1))
+
+
+def test_external_forcing_scalars_carry_the_reference_date_features():
+    """The 28-byte-per-slot host part of the input pipeline: columns 3..6 are get_year_hour_forcing's,
+    columns 0..2 the hour of day and sin / cos of the solar declination of the reference formula."""
+    import datetime as dt
+
+    import numpy as np
+
+    from py4cast_b200 import forcingutils as fu
+
+    dates = [dt.datetime(2023, 12, 31, 22), dt.datetime(2024, 2, 29, 5, 30)]
+    leads = [dt.timedelta(hours=h) for h in (1, 2, 3)]
+    s = fu.external_forcing_scalars(dates, leads)
+    assert s.shape == (6, 7) and s.dtype == torch.float32
+    for b, d in enumerate(dates):
+        blk = s[3 * b: 3 * b + 3]
+        assert torch.equal(blk[:, 3:], fu.get_year_hour_forcing(d, leads).float())
+        assert np.allclose(blk[:, 0].numpy(), fu.compute_hours_of_day(d, leads))
+        doy = fu.compute_day_of_years(d, leads)
+        dec = np.deg2rad(23.45 * np.sin(2 * np.pi * (284 + doy) / 365))
+        assert np.allclose(blk[:, 1].numpy(), np.sin(dec), atol=1e-6) and np.allclose(blk[:, 2].numpy(), np.cos(dec), atol=1e-6)

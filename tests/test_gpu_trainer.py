@@ -226,3 +226,54 @@ def _fresh_batch(batch):
     from py4cast_b200.trainer import _fresh
 
     return _fresh(batch)
+
+
+def test_host_batch_input_pipeline_fills_the_captured_buffers(cuda, tmp_path):
+    """The slimmed host batch (NWP forcing channels in bf16, external forcings as 28 bytes of scalars per
+    slot) lands in the captured fp32 input buffers exactly as the full fp32 batch would: shipped channels
+    bit-equal to their bf16 rounding (what the bf16 `x` holds anyway), the five external channels equal to
+    `fill_external_forcings`, inputs / outputs untouched - directly and through the prefetch stream."""
+    import datetime as dt
+
+    from py4cast_b200.datasets import synthetic_batch, synthetic_dataset_info
+    from py4cast_b200.forcingutils import fill_external_forcings
+    from py4cast_b200.lightning import AutoRegressiveLightning
+    from py4cast_b200.trainer import DataParallelTrainer, HostBatch
+
+    H, W, T, B = 64, 64, 3, 2
+    info = synthetic_dataset_info(H, W, num_features=5, num_forcing=8, border_size=4)
+    torch.manual_seed(0)
+    lm = AutoRegressiveLightning(
+        settings_init_args={"tmp_dir": str(tmp_path), "processor_layers": 1}, dataset_info=info, num_input_steps=2,
+        num_pred_steps_train=T, batch_size=B, model_name="GraphLAM", training_strategy="diff_ar",
+        precision="bf16-true").to(cuda)
+    tr = DataParallelTrainer(lm, total_steps=100)
+    lat = torch.linspace(51, 41, H, device=cuda).view(H, 1).expand(H, W).contiguous()
+    lon = torch.linspace(-6, 10, W, device=cuda).view(1, W).expand(H, W).contiguous()
+    tr.configure_external_forcings(lat, lon)
+    dates = [dt.datetime(2023, 12, 31, 21), dt.datetime(2024, 6, 1, 6)]
+    leads = [dt.timedelta(hours=h + 1) for h in range(T)]
+    batches = [synthetic_batch(info, B, 2, T, seed=s, device=cuda) for s in (1, 2)]
+    expected = []
+    for b in batches:
+        f = b.forcing.tensor.clone()
+        f[..., :3] = f[..., :3].bfloat16().float()
+        fill_external_forcings(f, 3, lat, lon, dates, leads)
+        expected.append(f)
+    tr.capture(batches[0], warmup=1)
+    hbs = [tr.pack_host_batch(b, dates, leads) for b in batches]
+    assert isinstance(hbs[0], HostBatch) and hbs[0].forcing.dtype == torch.bfloat16 and hbs[0].forcing.shape[-1] == 3
+    assert hbs[0].nbytes() < sum(getattr(batches[0], n).tensor.numel() * 4 for n in ("inputs", "forcing", "outputs"))
+    tr.load_inputs(hbs[1])
+    torch.cuda.synchronize()
+    assert torch.equal(tr._static_batch.forcing.tensor, expected[1])
+    assert torch.equal(tr._static_batch.inputs.tensor, batches[1].inputs.tensor)
+    assert torch.equal(tr._static_batch.outputs.tensor, batches[1].outputs.tensor)
+    # through the copy stream: step on batch 0 while batch 1 is prefetched, then step on batch 1
+    l0 = tr.replay(hbs[0], prefetch=hbs[1]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(tr._static_batch.forcing.tensor, expected[0])
+    l1 = tr.replay(hbs[1]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(tr._static_batch.forcing.tensor, expected[1])
+    assert torch.isfinite(l0) and torch.isfinite(l1)
