@@ -409,6 +409,38 @@ int p4c_acc_forward(const float* pred, const float* target, const float* mask,
                     const float* climate_means, int64_t bt, int32_t nodes, int32_t f,
                     float* partials, float* out, void* stream);
 
+/* -------------------------------------------------------------------------
+ * Power spectral density (reference py4cast/metrics.py:253-352 `dct_2d`, `dct_var`,
+ * `radial_bin_dct`, `power_spectral_density`, called by MetricPSDK.add_psd :121-144 and
+ * MetricPSDVar.update :186-213).  The reference's radial binning reads the flattened variance spectrum at
+ * 2 r - 1, 2 r, 2 r + 1 (metrics.py:311-315): the first 2 Rmax + 1 entries of its first row and its last
+ * entry.  This entry point produces exactly those, per (sample-step, feature) field, in one pass:
+ *   x, mask (optional, NULL = ones): fp32 (bt, H, W, F) contiguous (features last);
+ *   wy [H] = cos(pi (2 y + 1)(H - 1) / (2 H))  (last-row DCT weights, host-computed once);
+ *   spec (bt, F, J + 1): entries j < J = (1 / W^2) DCT2(x m)[0][j]^2, entry J = (1 / W^2) DCT2(x m)[H-1][W-1]^2;
+ *   partials: workspace of p4c_psd_partial_floats() floats.
+ * ---------------------------------------------------------------------- */
+int64_t p4c_psd_partial_floats(int64_t bt, int32_t H, int32_t W, int32_t F);
+int p4c_psd_first_row(const float* x, const float* mask, const float* wy, int64_t bt, int32_t H,
+                      int32_t W, int32_t F, int32_t J, float* partials, float* spec, void* stream);
+
+/* -------------------------------------------------------------------------
+ * Dataset statistics (reference py4cast/datasets/compute_dataset_stats.py:11-127).
+ * Per (sample, feature) of x (B, X, F) fp32 — or of x - prev when prev != NULL (time differences of
+ * compute_time_step_stats :88-127): out (B, F, 4) = NaN-ignoring mean over X (`nanmean`, :47 / :112),
+ * NaN-ignoring mean of squares (:48 / :113), min with NaN -> +inf (:50), max with NaN -> -inf (:54).
+ * fp64 accumulation in a fixed order.  partials: workspace of p4c_feature_stats_partial_bytes() BYTES.
+ * ---------------------------------------------------------------------- */
+int64_t p4c_feature_stats_partial_bytes(int32_t B, int64_t X, int32_t F);
+int p4c_feature_stats(const float* x, const float* prev, int32_t B, int64_t X, int32_t F,
+                      void* partials, float* out, void* stream);
+
+/* Un-normalisation of predictions in place (reference py4cast/lightning.py:1162-1169): for every row
+ * x[r][f] = x[r][f] * scale[f] + shift[f], rounded after the product and after the sum like the
+ * reference's `*= std` followed by `+= mean`.  x: fp32 (rows, F) contiguous. */
+int p4c_scale_shift(float* x, int64_t rows, int32_t F, const float* scale, const float* shift,
+                    void* stream);
+
 /* ------------------------------------------------------------------------
  * Optimiser: AdamW on one flat fp32 buffer (reference lightning.py:442-467:
  * torch.optim.AdamW + cosine-with-min-lr schedule with warm-up).

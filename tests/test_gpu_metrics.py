@@ -1,0 +1,158 @@
+"""SURVEY 8(f) ranks 3 / 4 on the device: PSD (one-pass first-row DCT kernel) against golden vectors of the
+VERBATIM reference metrics.py and against the oracle restatement, MetricPSDVar / MetricPSDK state handling,
+dataset statistics and un-normalisation against plain torch restatements of the reference formulas
+(compute_dataset_stats.py:11-127, lightning.py:1162-1169)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["square", "wide", "tall"])
+def test_psd_kernel_vs_reference_golden(cuda, name):
+    from py4cast_b200.metrics import power_spectral_density
+
+    c = load_golden("metrics.pt")["psd"][name]
+    x = c["x"].float()  # (B, C, H, W) -> features last
+    got = power_spectral_density(x.permute(0, 2, 3, 1).contiguous().to(cuda)).cpu().double().numpy()
+    exp = c["psd"].numpy()
+    assert got.shape == exp.shape
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.allclose(got[ok], exp[ok], rtol=2e-4, atol=1e-9)  # fp32 fields, fp32 column sums
+
+
+def test_psd_kernel_vs_oracle_with_mask_at_titan_shape(cuda):
+    from oracle import metrics_ref
+    from py4cast_b200.metrics import power_spectral_density
+
+    g = torch.Generator().manual_seed(0)
+    B, H, W, F = 2, 128, 160, 3
+    x = torch.randn(B, H, W, F, generator=g)
+    mask = (torch.rand(B, H, W, F, generator=g) > 0.05).float()
+    got = power_spectral_density(x.to(cuda), mask.to(cuda)).cpu()
+    exp = metrics_ref.power_spectral_density((x * mask).permute(0, 3, 1, 2).double().numpy())
+    assert_close(got.double(), torch.from_numpy(exp), 2e-4, "psd profile, masked")
+
+
+def test_metric_psd_var_and_psdk_accumulate_like_the_reference(cuda):
+    from oracle import metrics_ref
+    from py4cast_b200.metrics import MetricPSDK, MetricPSDVar
+    from py4cast_b200.namedtensor import NamedTensor
+
+    g = torch.Generator().manual_seed(1)
+    B, T, H, W, F = 2, 3, 32, 32, 2
+    names = ["batch", "timestep", "ngrid", "features"]
+    fn = ["u", "v"]
+    var, psdk = MetricPSDVar(pred_step=1), MetricPSDK(pred_step=1)
+    exp_sum = np.zeros(F)
+    for step in range(2):
+        p = torch.randn(B, T, H, W, F, generator=g)
+        t = p + 0.5 * torch.randn(B, T, H, W, F, generator=g)
+        m = torch.ones(B, T, H, W, F)
+        exp_sum += metrics_ref.psd_log_rmse(p.double(), t.double(), m.double(), 1)
+        # graph-shaped tensors + `shape`, as validation_step passes them (lightning.py:995-1004)
+        args = (NamedTensor(p.flatten(2, 3).to(cuda), names, fn), NamedTensor(t.flatten(2, 3).to(cuda), names, fn),
+                m.flatten(2, 3).to(cuda), (B, T, H, W, F))
+        var.update(*args)
+        psdk.update(*args)
+    out = var.compute("val")
+    assert sorted(out) == ["val_rmse_psd/u", "val_rmse_psd/v"] and var.step_count == 0
+    got = np.array([float(out[f"val_rmse_psd/{n}"]) for n in fn])
+    assert np.allclose(got, exp_sum / 2, rtol=1e-3, atol=1e-5)
+    spectra = psdk.compute()
+    assert set(spectra) == set(fn) and spectra["u"][0].shape == spectra["u"][1].shape == (11,)
+
+
+def _torch_mean_std_min_max(batches, attr):
+    """compute_dataset_stats.py:11-75 restated with the reference's own torch expressions (fp64 sums)."""
+    first = getattr(batches[0], attr).tensor
+    flat = first.flatten(0, first.dim() - 2)
+    best_min = torch.min(torch.nan_to_num(flat, nan=torch.inf), dim=0).values
+    best_max = torch.max(torch.nan_to_num(flat, nan=-torch.inf), dim=0).values
+    sm = sq = 0
+    n = 0
+    for b in batches:
+        t = getattr(b, attr).tensor.flatten(1, 3).double()
+        n += t.shape[0]
+        sm = sm + torch.nansum(t.nanmean(dim=1), dim=0)
+        sq = sq + torch.nansum((t**2).nanmean(dim=1), dim=0)
+        best_min = torch.min(torch.stack([best_min, torch.min(torch.nan_to_num(t.float(), nan=torch.inf), 1).values[0]]), 0).values
+        best_max = torch.max(torch.stack([best_max, torch.max(torch.nan_to_num(t.float(), nan=-torch.inf), 1).values[0]]), 0).values
+    mean = sm / n
+    return mean, torch.sqrt(sq / n - mean**2), best_min, best_max
+
+
+def test_dataset_stats_vs_reference_formulas(cuda):
+    from py4cast_b200 import dataset_stats as ds
+    from py4cast_b200.datasets import synthetic_batch, synthetic_dataset_info
+
+    info = synthetic_dataset_info(48, 56, num_features=4, num_forcing=3, border_size=2)
+    host = [synthetic_batch(info, 3, 2, 3, seed=s) for s in range(3)]
+    for b in host:  # un-standardised fields with some missing values
+        b.inputs.tensor.mul_(3.0).add_(1.5)
+        b.inputs.tensor[0, 0, 5:9, 7, 1] = float("nan")
+        b.outputs.tensor[1, 2, :, 3, 0] = float("nan")
+    from py4cast_b200.namedtensor import NamedTensor
+
+    mv = lambda nt: NamedTensor(nt.tensor.to(cuda), list(nt.names), list(nt.feature_names))  # noqa: E731
+    dev = [type(b)(inputs=mv(b.inputs), forcing=mv(b.forcing), outputs=mv(b.outputs)) for b in host]
+    for attr in ("inputs", "outputs", "forcing"):
+        got = ds.compute_mean_std_min_max(dev, attr)
+        mean, std, mn, mx = _torch_mean_std_min_max(host, attr)
+        names = getattr(host[0], attr).feature_names
+        assert list(got) == list(names)
+        for i, n in enumerate(names):
+            assert_close(got[n]["mean"].cpu().double(), mean[i], 1e-5, f"{attr} mean {n}")
+            assert_close(got[n]["std"].cpu().double(), std[i], 1e-5, f"{attr} std {n}")
+            assert float(got[n]["min"]) == float(mn[i]) and float(got[n]["max"]) == float(mx[i])
+    allst = ds.compute_parameters_stats(lambda: dev)
+    assert set(allst) == set(host[0].inputs.feature_names) | set(host[0].forcing.feature_names)
+    # diff stats (compute_dataset_stats.py:95-127)
+    got = ds.compute_time_step_stats(dev)
+    sm = sq = 0
+    n = 0
+    for b in host:
+        io = torch.cat([b.inputs.tensor, b.outputs.tensor], dim=1).double()
+        d = (io[:, 1:] - io[:, :-1]).flatten(1, 3)
+        n += io.shape[0]
+        sm = sm + torch.nansum(d.nanmean(dim=1), dim=0)
+        sq = sq + torch.nansum((d**2).nanmean(dim=1), dim=0)
+    mean = sm / n
+    std = torch.sqrt(sq / n - mean**2)
+    for i, nme in enumerate(host[0].inputs.feature_names):
+        assert_close(got[nme]["mean"].cpu().double(), mean[i], 1e-5, f"diff mean {nme}")
+        assert_close(got[nme]["std"].cpu().double(), std[i], 1e-5, f"diff std {nme}")
+    for nme in host[0].forcing.feature_names:
+        assert int(got[nme]["mean"]) == 0 and int(got[nme]["std"]) == 1
+
+
+def test_unnormalize_is_bit_equal_to_the_reference_loop(cuda):
+    from py4cast_b200.dataset_stats import unnormalize_
+    from py4cast_b200.datasets import synthetic_dataset_info
+    from py4cast_b200.namedtensor import NamedTensor
+
+    info = synthetic_dataset_info(16, 20, num_features=5, num_forcing=2, border_size=2)
+    fn = info.shortnames["input_output"]
+    x = torch.randn(2, 3, 16, 20, 5)
+    ref = x.clone()
+    for i, n in enumerate(fn):  # lightning.py:1162-1169
+        ref[:, :, :, :, i] *= torch.asarray(info.stats[n]["std"])
+        ref[:, :, :, :, i] += torch.asarray(info.stats[n]["mean"])
+    nt = NamedTensor(x.to(cuda), ["batch", "timestep", "lat", "lon", "features"], list(fn))
+    out = unnormalize_(nt, info.stats)
+    assert out is nt and torch.equal(nt.tensor.cpu(), ref)
+
+
+def test_metrics_and_stats_refuse_cpu_tensors():
+    from py4cast_b200 import _lib
+    from py4cast_b200.dataset_stats import feature_stats
+    from py4cast_b200.metrics import power_spectral_density
+
+    with pytest.raises(_lib.P4CError):
+        power_spectral_density(torch.zeros(1, 8, 8, 1))
+    with pytest.raises(_lib.P4CError):
+        feature_stats(torch.zeros(1, 8, 2))
