@@ -417,12 +417,15 @@ int p4c_acc_forward(const float* pred, const float* target, const float* mask,
  * entry.  This entry point produces exactly those, per (sample-step, feature) field, in one pass:
  *   x, mask (optional, NULL = ones): fp32 (bt, H, W, F) contiguous (features last);
  *   wy [H] = cos(pi (2 y + 1)(H - 1) / (2 H))  (last-row DCT weights, host-computed once);
+ *   ctab [W][J + 1]: ctab[x][j] = cos(pi (2 x + 1) j / (2 W)) for j < J, ctab[x][J] = the same with
+ *     j = W - 1 (host-computed once per grid shape, in fp64);
  *   spec (bt, F, J + 1): entries j < J = (1 / W^2) DCT2(x m)[0][j]^2, entry J = (1 / W^2) DCT2(x m)[H-1][W-1]^2;
  *   partials: workspace of p4c_psd_partial_floats() floats.
  * ---------------------------------------------------------------------- */
 int64_t p4c_psd_partial_floats(int64_t bt, int32_t H, int32_t W, int32_t F);
-int p4c_psd_first_row(const float* x, const float* mask, const float* wy, int64_t bt, int32_t H,
-                      int32_t W, int32_t F, int32_t J, float* partials, float* spec, void* stream);
+int p4c_psd_first_row(const float* x, const float* mask, const float* wy, const float* ctab,
+                      int64_t bt, int32_t H, int32_t W, int32_t F, int32_t J, float* partials,
+                      float* spec, void* stream);
 
 /* -------------------------------------------------------------------------
  * Dataset statistics (reference py4cast/datasets/compute_dataset_stats.py:11-127).

@@ -43,27 +43,40 @@ __global__ void __launch_bounds__(SM_NT) psd_colsum_kernel(const float* __restri
   partial[(ys * gridDim.y + bt) * WF + e] = make_float2(a, b);
 }
 
+// s[bt][e] = sum over the row splits of partial (fixed order), in place in split 0
+__global__ void __launch_bounds__(SM_NT) psd_split_reduce_kernel(float2* __restrict__ partial, int nsplit, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * SM_NT + threadIdx.x;
+  if (i >= n) return;
+  float2 a = partial[i];
+  for (int ys = 1; ys < nsplit; ++ys) {
+    const float2 v = partial[ys * n + i];
+    a.x += v.x;
+    a.y += v.y;
+  }
+  partial[i] = a;
+}
+
 // spec[bt][f][j], j < J: ((alpha_0(H) alpha_j(W) sum_x s1[x] cos(pi (2x+1) j / 2W))^2) / W^2   (first spectrum row)
 // spec[bt][f][J]       : ((alpha_{H-1}(H) alpha_{W-1}(W) sum_x s2[x] cos(pi (2x+1)(W-1) / 2W))^2) / W^2   (last entry)
-__global__ void __launch_bounds__(SM_NT) psd_finalize_kernel(const float2* __restrict__ partial, int nsplit, long long bt_n,
-                                                             int H, int W, int F, int J, float* __restrict__ spec) {
+// ctab [W][J + 1]: the cosines (column J = those of k = W - 1), computed once per grid shape in fp64 on the host.
+// fp64 accumulation: the sums cancel strongly for smooth fields.
+__global__ void __launch_bounds__(SM_NT) psd_finalize_kernel(const float2* __restrict__ s, const float* __restrict__ ctab,
+                                                             long long bt_n, int H, int W, int F, int J,
+                                                             float* __restrict__ spec) {
   const long long idx = static_cast<long long>(blockIdx.x) * SM_NT + threadIdx.x;
   const long long total = bt_n * F * (J + 1);
   if (idx >= total) return;
   const int j = static_cast<int>(idx % (J + 1));
   const int f = static_cast<int>((idx / (J + 1)) % F);
   const long long bt = idx / (static_cast<long long>(J + 1) * F);
-  const long long WF = static_cast<long long>(W) * F;
   const bool last = j == J;
   const int k = last ? W - 1 : j;
+  const float2* sp = s + bt * W * F + f;
+  const float* cp = ctab + j;
   double acc = 0.0;
   for (int x = 0; x < W; ++x) {
-    double s = 0.0;
-    for (int ys = 0; ys < nsplit; ++ys) {  // fixed order over the row splits
-      const float2 v = partial[(ys * bt_n + bt) * WF + static_cast<long long>(x) * F + f];
-      s += last ? v.y : v.x;
-    }
-    acc += s * cospi(static_cast<double>(2 * x + 1) * k / (2.0 * W));
+    const float2 v = sp[static_cast<long long>(x) * F];
+    acc = fma(static_cast<double>(last ? v.y : v.x), static_cast<double>(cp[static_cast<long long>(x) * (J + 1)]), acc);
   }
   const double ax = k == 0 ? sqrt(1.0 / W) : sqrt(2.0 / W);
   const double ay = last ? (H == 1 ? 1.0 : sqrt(2.0 / H)) : sqrt(1.0 / H);
@@ -87,18 +100,33 @@ __global__ void __launch_bounds__(SM_NT) feature_stats_kernel(const float* __res
   StatPart a = {0.0, 0.0, 0.0, INFINITY, -INFINITY};
   if (r < R) {
     const long long x0 = c * rows_per_chunk, x1 = min(X, x0 + rows_per_chunk);
-    for (long long i = x0 + r; i < x1; i += R) {
-      const long long o = (b * X + i) * F + f;
-      float v = x[o];
-      if (prev) v -= prev[o];
-      if (v == v) {  // not NaN
-        a.n += 1.0;
-        a.s += v;
-        a.q += static_cast<double>(v) * v;
-        a.mn = fmin(a.mn, static_cast<double>(v));
-        a.mx = fmax(a.mx, static_cast<double>(v));
+    // groups of 8 rows: loads issued together, group sums in fp32 (8 terms), accumulation over groups in fp64
+    float mn = INFINITY, mx = -INFINITY;
+    for (long long i0 = x0 + r; i0 < x1; i0 += 8ll * R) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + static_cast<long long>(u) * R;
+        const long long o = (b * X + i) * F + f;
+        v[u] = i < x1 ? (prev ? x[o] - prev[o] : x[o]) : __int_as_float(0x7fc00000);
       }
+      float n8 = 0.f, s8 = 0.f, q8 = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (v[u] == v[u]) {  // not NaN
+          n8 += 1.f;
+          s8 += v[u];
+          q8 = fmaf(v[u], v[u], q8);
+          mn = fminf(mn, v[u]);
+          mx = fmaxf(mx, v[u]);
+        }
+      }
+      a.n += n8;
+      a.s += s8;
+      a.q += q8;
     }
+    a.mn = mn;
+    a.mx = mx;
   }
   red[tid] = a;
   __syncthreads();
@@ -132,13 +160,28 @@ __global__ void feature_stats_finalize_kernel(const StatPart* __restrict__ parti
 
 // ------------------------------------------------------------------------------- un-normalisation
 // x[i][f] = x[i][f] * scale[f] + shift[f], two roundings as the reference's `*=` then `+=`
-__global__ void __launch_bounds__(SM_NT) scale_shift_kernel(float* __restrict__ x, long long n, int F,
-                                                            const float* __restrict__ scale,
+// thread = (row within a group of R = 256 / F rows, feature): consecutive threads touch consecutive addresses,
+// the feature index is computed once; a block walks `rows_per_block` rows
+__global__ void __launch_bounds__(SM_NT) scale_shift_kernel(float* __restrict__ x, long long rows, int F, int R,
+                                                            long long rows_per_block, const float* __restrict__ scale,
                                                             const float* __restrict__ shift) {
-  const long long i = static_cast<long long>(blockIdx.x) * SM_NT + threadIdx.x;
-  if (i >= n) return;
-  const int f = static_cast<int>(i % F);
-  x[i] = __fadd_rn(__fmul_rn(x[i], scale[f]), shift[f]);
+  const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+  if (r >= R) return;
+  const float sc = scale[f], sh = shift[f];
+  const long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (long long i0 = r0 + r; i0 < r1; i0 += 4ll * R) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + static_cast<long long>(u) * R;
+      if (i < r1) v[u] = x[i * F + f];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + static_cast<long long>(u) * R;
+      if (i < r1) x[i * F + f] = __fadd_rn(__fmul_rn(v[u], sc), sh);
+    }
+  }
 }
 
 }  // namespace p4c
@@ -155,9 +198,9 @@ extern "C" int64_t p4c_psd_partial_floats(int64_t bt, int32_t H, int32_t W, int3
   return 2ll * psd_splits(H) * bt * W * F;
 }
 
-extern "C" int p4c_psd_first_row(const float* x, const float* mask, const float* wy, int64_t bt, int32_t H, int32_t W,
-                                 int32_t F, int32_t J, float* partials, float* spec, void* stream) {
-  P4C_REQUIRE(x && wy && partials && spec, "psd_first_row: null pointer");
+extern "C" int p4c_psd_first_row(const float* x, const float* mask, const float* wy, const float* ctab, int64_t bt,
+                                 int32_t H, int32_t W, int32_t F, int32_t J, float* partials, float* spec, void* stream) {
+  P4C_REQUIRE(x && wy && ctab && partials && spec, "psd_first_row: null pointer");
   P4C_REQUIRE(bt > 0 && H > 0 && W > 0 && F > 0, "psd_first_row: empty problem");
   P4C_REQUIRE(J >= 1 && J <= W, "psd_first_row: J=%d spectrum entries requested from a row of %d", J, W);
   P4C_REQUIRE(bt <= 65535, "psd_first_row: more than 65535 fields per call");
@@ -168,9 +211,15 @@ extern "C" int p4c_psd_first_row(const float* x, const float* mask, const float*
   dim3 grid(static_cast<unsigned>((WF + SM_NT - 1) / SM_NT), static_cast<unsigned>(bt), static_cast<unsigned>(ns));
   psd_colsum_kernel<<<grid, SM_NT, 0, st>>>(x, mask, wy, H, WF, rps, reinterpret_cast<float2*>(partials));
   P4C_CHECK_LAUNCH("psd_colsum");
+  const long long n = bt * WF;
+  if (ns > 1) {
+    psd_split_reduce_kernel<<<static_cast<unsigned>((n + SM_NT - 1) / SM_NT), SM_NT, 0, st>>>(
+        reinterpret_cast<float2*>(partials), ns, n);
+    P4C_CHECK_LAUNCH("psd_split_reduce");
+  }
   const long long total = bt * F * (J + 1);
   psd_finalize_kernel<<<static_cast<unsigned>((total + SM_NT - 1) / SM_NT), SM_NT, 0, st>>>(
-      reinterpret_cast<const float2*>(partials), ns, bt, H, W, F, J, spec);
+      reinterpret_cast<const float2*>(partials), ctab, bt, H, W, F, J, spec);
   P4C_CHECK_LAUNCH("psd_finalize");
   return P4C_OK;
 }
@@ -206,8 +255,11 @@ extern "C" int p4c_feature_stats(const float* x, const float* prev, int32_t B, i
 extern "C" int p4c_scale_shift(float* x, int64_t rows, int32_t F, const float* scale, const float* shift, void* stream) {
   P4C_REQUIRE(x && scale && shift, "scale_shift: null pointer");
   P4C_REQUIRE(rows > 0 && F > 0, "scale_shift: empty problem");
-  const long long n = rows * F;
-  scale_shift_kernel<<<static_cast<unsigned>((n + SM_NT - 1) / SM_NT), SM_NT, 0, (cudaStream_t)stream>>>(x, n, F, scale, shift);
+  P4C_REQUIRE(F <= SM_NT, "scale_shift: F=%d > 256", F);
+  const int R = SM_NT / F;
+  const long long rpb = 64ll * R;  // 64 iterations of R rows per block
+  scale_shift_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), SM_NT, 0, (cudaStream_t)stream>>>(x, rows, F, R, rpb,
+                                                                                                       scale, shift);
   P4C_CHECK_LAUNCH("scale_shift");
   return P4C_OK;
 }

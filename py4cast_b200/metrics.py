@@ -111,18 +111,23 @@ def power_spectral_density(x: torch.Tensor, mask: Optional[torch.Tensor] = None)
         present = torch.from_numpy(_psd_bins(H, W)).to(x.device)
         wy = torch.tensor([math.cos(math.pi * (2 * y + 1) * (H - 1) / (2 * H)) for y in range(H)],
                           dtype=torch.float32, device=x.device)
-        _PSD_CONST[key] = (present, wy)
-    present, wy = _PSD_CONST[key]
+        R = present.numel()
+        J = 2 * R  # flat spectrum entries 0 .. 2 R - 1 (+ the last one)
+        if J > W or R < 1:
+            raise NotImplementedError("PSD: the reference's flat indexing leaves the first spectrum row for this shape")
+        xs = torch.arange(W, dtype=torch.float64).unsqueeze(1)
+        ks = torch.cat([torch.arange(J, dtype=torch.float64), torch.tensor([W - 1.0], dtype=torch.float64)]).unsqueeze(0)
+        ctab = torch.cos(math.pi * (2 * xs + 1) * ks / (2 * W)).to(torch.float32).contiguous().to(x.device)
+        _PSD_CONST[key] = (present, wy, ctab)
+    present, wy, ctab = _PSD_CONST[key]
     R = present.numel()
-    J = 2 * R  # flat spectrum entries 0 .. 2 R - 1 (+ the last one)
-    if J > W or R < 1:
-        raise NotImplementedError("PSD: the reference's flat indexing leaves the first spectrum row for this shape")
+    J = 2 * R
     xf = x.float().contiguous()
     m = None if mask is None else mask.to(torch.float32).expand_as(xf).contiguous()
     lib = _lib.load()
     ws = torch.empty(max(1, lib.p4c_psd_partial_floats(B, H, W, F)), dtype=torch.float32, device=x.device)
     spec = torch.empty(B, F, J + 1, dtype=torch.float32, device=x.device)
-    check(lib.p4c_psd_first_row(ptr(xf), ptr(m), ptr(wy), B, H, W, F, J, ptr(ws), ptr(spec), stream()),
+    check(lib.p4c_psd_first_row(ptr(xf), ptr(m), ptr(wy), ptr(ctab), B, H, W, F, J, ptr(ws), ptr(spec), stream()),
           "p4c_psd_first_row")
     flat = spec.mean(dim=0)  # (F, J + 1): batch mean of the variance spectrum (metrics.py:343)
     r = torch.arange(R, device=x.device)

@@ -84,6 +84,20 @@ def main():
     terms = [dt.timedelta(hours=i + 1) for i in range(T)]
     t_ff = timeit(lambda: fu.fill_external_forcings(fbuf, info.forcing_dim - 5, lat, lon, dates, terms))
     rows.append(("external forcings (5 channels, incl. host date arithmetic)", B * T * N * 5 * 4 + 2 * 4 * N, t_ff))
+    scal = fu.external_forcing_scalars(dates, terms).to(dev)
+    t_fs = timeit(lambda: fu.fill_external_forcings_from_scalars(fbuf, info.forcing_dim - 5, lat, lon, scal))
+    rows.append(("external forcings (5 channels, scalars prepared by the loader)", B * T * N * 5 * 4 + 2 * 4 * N, t_fs))
+    # PSD of one prediction step, dataset statistics, un-normalisation
+    from py4cast_b200 import dataset_stats as dstat
+    from py4cast_b200.metrics import power_spectral_density
+    field = torch.randn(B, H, W, F, device=dev)
+    t_p = timeit(lambda: power_spectral_density(field))
+    rows.append(("PSD profile of (B, H, W, F) fields (column sums + first-row DCT)", 4 * B * N * F, t_p))
+    t_s = timeit(lambda: dstat.feature_stats(tgt.detach()))
+    rows.append(("feature statistics (nanmean, nanmean of squares, min, max)", 4 * B * T * N * F, t_s))
+    nt = NamedTensor(tgt.detach().clone(), names, fn)
+    t_u = timeit(lambda: dstat.unnormalize_(nt, info.stats))
+    rows.append(("un-normalise predictions in place", 2 * 4 * B * T * N * F, t_u))
     print(f"# element-wise kernels at batch {B}, T={T}, N={N}, F={F}; peak {peak:.0f} GB/s (MEASURED_PEAKS.json or fallback)")
     for label, by, t in rows:
         print(f"{label:60s} {t*1e3:8.3f} ms  {by/1e6:9.1f} MB  {by/t/1e9:7.0f} GB/s  {by/t/1e9/peak:5.2f} of peak")
