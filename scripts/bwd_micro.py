@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--engines", default="classic,pipelined")
     args = ap.parse_args()
     from py4cast_b200 import _lib, ops
     from py4cast_b200.graph_build import build_mesh_graph, unit_meshgrid
@@ -44,6 +45,8 @@ def main():
         else:
             edge = torch.randn(es.num_edges, 64, device=dev, generator=g).bfloat16().requires_grad_(True)
         for engine, thr in (("classic", 1 << 40), ("pipelined", 0)):
+            if engine not in args.engines.split(","):
+                continue
             lib.p4c_set_ws_bwd_min_tiles(thr)
             tf, tb = [], []
             trace = torch.zeros(64, dtype=torch.int64, device=dev)
