@@ -33,6 +33,7 @@
 // cat(edge, send[sender], rec[receiver]) and InteractionNet.aggregate.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace p4c {
 namespace tc {
@@ -78,6 +79,10 @@ struct WsArgs {
   // other samples from L2 instead of being re-read per sample (m2g edge embedding: 168 MB > L2).
   unsigned long long div_magic;  // ceil(2^64 / batch): row block = umul64hi(tile, magic)
   uint32_t batch, ntiles, full_rows;
+  // identity-indexed K-blocks arrive by TMA (bit k of tma_mask; tma_b[k] = 0 for a source shared by the batch)
+  int tma_mask;
+  int tma_b[P4C_MAX_SRC];
+  alignas(64) CUtensorMap tmap[P4C_MAX_SRC];
 };
 
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid_constant__ WsArgs a) {
@@ -166,11 +171,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
                a.kb.col0[k]) >> 3);
         }
       }
+      const uint32_t b_cur = b_next, row0 = rr_next - static_cast<uint32_t>(pw * 32 + lane);
       load_indices(t + 1);
       if (n > 0) mbar_wait_backoff<200, true>(&S.x_empty[s], (n - 1) & 1u);
+      if (a.tma_mask && pw == 0 && lane == 0) {  // whole tiles by TMA: bytes counted on the stage's barrier
+#pragma unroll
+        for (int k = 0; k < P4C_MAX_SRC; ++k)
+          if (k < nblk && (a.tma_mask >> k & 1)) {
+            mbar_expect_tx(&S.x_full[s], WS_XBLK);
+            tma_load_3d(smem_u32(S.X[s][k]), &a.tmap[k], &S.x_full[s], a.kb.col0[k], static_cast<int>(row0),
+                        a.tma_b[k] ? static_cast<int>(b_cur) : 0);
+          }
+      }
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
-        if (k < nblk) {
+        if (k < nblk && !(a.tma_mask >> k & 1)) {
           const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[a.kb.src[k]].ptr);
           const uint32_t xs = smem_u32(S.X[s][k]);
           const bool fetch = j < a.kb.nchunks[k];
@@ -512,8 +527,16 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   a.agg_group = aggr_out ? agg_group : 1;
   a.agg_scale = agg_scale;
   a.residual_x0 = residual != nullptr;
+  a.tma_mask = 0;
+  for (int k = 0; k < a.kb.nblk; ++k) {
+    const p4c_src_t& src = m->src[a.kb.src[k]];
+    a.tma_b[k] = (m->batch > 1 && src.batch_stride != 0) ? 1 : 0;
+    if (tma_enabled() && !src.index && !src.seg_rowptr &&
+        tma_rows_map(&a.tmap[k], src.ptr, src.ld, m->rows, src.ld, m->batch, src.batch_stride))
+      a.tma_mask |= 1 << k;
+  }
   a.zero_x = 0;
-  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8 && !(a.tma_mask >> k & 1);
   const unsigned long long rows = static_cast<unsigned long long>(m->rows);
   const unsigned long long nb = static_cast<unsigned long long>(m->batch);
   a.div_magic = nb == 1 ? 0ull : (~0ull / nb) + 1ull;  // ceil(2^64 / batch) for batch >= 2 (batch 1: not used)

@@ -39,6 +39,7 @@
 // (SURVEY.md §3.2, K1-K6), reached from py4cast/lightning.py:586-596.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace p4c {
 namespace tc {
@@ -88,6 +89,10 @@ struct WbArgs {
   unsigned long long div_magic;  // ceil(2^64 / batch): row block = umul64hi(tile, magic)
   uint32_t batch, ntiles, full_rows;
   int total_blocks;  // partial blocks of this MLP's workspace (blocks >= gridDim.x are zeroed in mode 1)
+  // identity-indexed K-blocks arrive by TMA (bit k of tma_mask; tma_b[k] = 0 for a source shared by the batch)
+  int tma_mask;
+  int tma_b[P4C_MAX_SRC];
+  alignas(64) CUtensorMap tmap[P4C_MAX_SRC];
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's tile 2, see scripts/trace_ws_bwd.py
 };
 // slots 0.. compute group 0 (warp 0), 16.. MMA lane (context 0), 32.. producer warp 0
@@ -185,13 +190,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     const int pw = warp - WB_CWARPS;
     const int sub = lane >> 3, j = lane & 7;  // lane -> (row within a group of 4, 16-byte chunk)
     int32_t idx_next[P4C_MAX_SRC];
-    uint32_t b_next = 0;
+    uint32_t b_next = 0, blk_next = 0;
     bool valid_next = false;
     auto load_indices = [&](uint32_t t) {  // gather indices of tile t (graph constants)
       const uint32_t tile = blockIdx.x + t * gridDim.x;
       const uint32_t blk = nbatch == 1 ? tile
                                        : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
       b_next = tile - blk * nbatch;
+      blk_next = blk;
       const uint32_t rr = blk * WB_TM + pw * 32 + lane;
       valid_next = t < ntl && rr < rows;
 #pragma unroll
@@ -223,12 +229,22 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       const uint32_t c = t % xns, n = t / xns;
       const bool trc = t == 2 && pw == 0 && lane == 0;
       P4C_WB_TRACE(trc, 32);
+      const uint32_t b_cur = b_next, row0 = blk_next * WB_TM;
       load_indices(t + 1);
       if (n > 0) mbar_wait_backoff<100, true>(&S.x_empty[c], (n - 1) & 1u);
       P4C_WB_TRACE(trc, 33);
+      if (a.tma_mask && pw == 0 && lane == 0) {  // whole tiles by TMA: bytes counted on the stage's barrier
+#pragma unroll
+        for (int k = 0; k < P4C_MAX_SRC; ++k)
+          if (k < nblk && (a.tma_mask >> k & 1)) {
+            mbar_expect_tx(&S.x_full[c], WB_BLK);
+            tma_load_3d(smem_u32(S.X[c * xsb + k]), &a.tmap[k], &S.x_full[c], a.kb.col0[k], static_cast<int>(row0),
+                        a.tma_b[k] ? static_cast<int>(b_cur) : 0);
+          }
+      }
 #pragma unroll
       for (int k = 0; k < P4C_MAX_SRC; ++k) {
-        if (k < nblk) {
+        if (k < nblk && !(a.tma_mask >> k & 1)) {
           const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(m.src[a.kb.src[k]].ptr);
           const uint32_t xs = smem_u32(S.X[c * xsb + k]);
           const bool fetch = j < a.kb.nchunks[k];
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       const bool trc = t == 2 && tid == 0;
       P4C_WB_TRACE(trc, 0);
       // ---- a. h1 -> a1 = SiLU(h1) -> A1 tile; SiLU'(h1) -> registers
-      mbar_wait_backoff<32, true>(&S.h1_full[grp], par);
+      mbar_wait_suspend(&S.h1_full[grp], par);
       P4C_WB_TRACE(trc, 1);
       tc_fence_after();
       uint4 gs[4];
@@ -477,7 +493,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       }
 
       // ---- c. LayerNorm backward from the recomputed h2
-      mbar_wait_backoff<32, true>(&S.h2_full[grp], par);
+      mbar_wait_suspend(&S.h2_full[grp], par);
       P4C_WB_TRACE(trc, 3);
       tc_fence_after();
       {
@@ -538,7 +554,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       }
 
       // ---- e. dh1 = da1 * SiLU'(h1) -> DH tile (overwrites dh2: G2, G3 are complete), then to HBM
-      mbar_wait_backoff<32, true>(&S.da1_full[grp], par);
+      mbar_wait_suspend(&S.da1_full[grp], par);
       P4C_WB_TRACE(trc, 6);
       tc_fence_after();
       {
@@ -585,7 +601,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       }
       // ---- g. dX epilogues (G4 / G5 complete: the DH and X tiles of the context are free afterwards)
       P4C_WB_TRACE(trc, 8);
-      mbar_wait_backoff<32, true>(&S.dx_full[grp], par);
+      mbar_wait_suspend(&S.dx_full[grp], par);
       P4C_WB_TRACE(trc, 9);
       tc_fence_after();
       for (int s = 0; s < nslot; ++s) {
@@ -889,8 +905,16 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   a.slot_blk[0] = a.slot_blk[1] = 0;
   a.slot_kind[0] = a.slot_kind[1] = 0;
   a.nslot = wb_slots(m, g, a.kb, a.slot_blk, a.slot_kind);
+  a.tma_mask = 0;
+  for (int k = 0; k < a.kb.nblk; ++k) {
+    const p4c_src_t& src = m->src[a.kb.src[k]];
+    a.tma_b[k] = (m->batch > 1 && src.batch_stride != 0) ? 1 : 0;
+    if (tma_enabled() && !src.index && !src.seg_rowptr &&
+        tma_rows_map(&a.tmap[k], src.ptr, src.ld, m->rows, src.ld, m->batch, src.batch_stride))
+      a.tma_mask |= 1 << k;
+  }
   a.zero_x = 0;
-  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8;
+  for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8 && !(a.tma_mask >> k & 1);
   const unsigned long long rows = static_cast<unsigned long long>(m->rows);
   const unsigned long long nb = static_cast<unsigned long long>(m->batch);
   a.div_magic = nb == 1 ? 0ull : (~0ull / nb) + 1ull;

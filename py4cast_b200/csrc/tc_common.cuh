@@ -264,6 +264,27 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     if (spin > (1u << 24)) __trap();
   }
 }
+// Wait with the hardware's own suspension: try_wait with a suspend-time hint parks the warp until the phase
+// completes (or the hint expires) without issuing instructions, and wakes it immediately -- instead of a
+// poll / nanosleep loop, whose instructions were 37 % of everything the pipelined backward issued
+// (profiles/r02v_ws_bwd_edge_lines.txt).  Relaxed: the consumer is ordered by tcgen05.fence::after_thread_sync.
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 22)) __trap();
+  }
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
