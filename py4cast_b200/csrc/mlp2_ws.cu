@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
   extern __shared__ unsigned char smem_raw[];
   WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const p4c_mlp_t& m = a.m;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index broadcast from lane 0: provably warp-uniform for the compiler (MMA warp: uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nblk = a.kb.nblk;
   const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
@@ -222,34 +223,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     if (lane == 0) mbar_arrive(&S.x_full[(ntl - 1) % WS_NS]);
   } else if (warp == WS_EPI_WARPS + WS_PROD_WARPS) {
     // ================================= MMA ==================================
-    if (lane == 0) {
+    // warp-uniform control flow (every lane runs the loop, one elected lane issues): the operand descriptors
+    // then live in uniform registers; under `if (lane == 0)` the compiler wrapped every UTCHMMA in an
+    // ELECT / BRA.U.ANY loop of ~15 instructions.  One base descriptor per operand, a 64-bit add per MMA.
+    {
       constexpr uint32_t IDESC = make_idesc_bf16(WS_TM, WS_HID, 0, 0);
+      constexpr long long KSTEP = 2;  // 32 bytes = K 16 bf16 columns, in descriptor address units
+      const uint64_t w2d = make_desc_sw128(smem_u32(S.W2), 16, 1024);
       for (uint32_t t = 0; t <= ntl; ++t) {
         if (t < ntl) {
           const uint32_t s = t % WS_NS, n = t / WS_NS, buf = t & 1u;
           mbar_wait_backoff<20>(&S.x_full[s], n & 1u);
           tc_fence_after();
+          uint32_t acc = 0u;
           for (int k = 0; k < nblk; ++k) {
-            const uint32_t xa = smem_u32(S.X[s][k]), wa = smem_u32(S.W1[k]);
+            uint64_t xd = make_desc_sw128(smem_u32(S.X[s][k]), 16, 1024), wd = make_desc_sw128(smem_u32(S.W1[k]), 16, 1024);
             const int nk = (a.kb.kvalid[k] + 15) >> 4;
-            for (int q = 0; q < nk; ++q)
-              mma_bf16_ss(tmem + buf * WS_HID, make_desc_sw128(xa + q * 32, 16, 1024),
-                          make_desc_sw128(wa + q * 32, 16, 1024), IDESC, (k | q) ? 1u : 0u);
+            for (int q = 0; q < nk; ++q, xd += KSTEP, wd += KSTEP, acc = 1u)
+              mma_bf16_ss_elect(tmem + buf * WS_HID, xd, wd, IDESC, acc);
           }
-          mma_commit(&S.x_empty[s]);
-          mma_commit(&S.d1_full[buf]);
+          mma_commit_elect(&S.x_empty[s]);
+          mma_commit_elect(&S.d1_full[buf]);
         }
         if (t >= 1) {
           const uint32_t u = t - 1, buf = u & 1u, nn = u >> 1;
           mbar_wait_backoff<20>(&S.a2_full[buf], nn & 1u);
           if (nn > 0) mbar_wait_backoff<20>(&S.d2_empty[buf], (nn - 1) & 1u);
           tc_fence_after();
-          const uint32_t aa = smem_u32(S.A2[buf]), wa = smem_u32(S.W2);
+          const uint64_t ad = make_desc_sw128(smem_u32(S.A2[buf]), 16, 1024);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            mma_bf16_ss(tmem + 2 * WS_HID + buf * WS_HID, make_desc_sw128(aa + q * 32, 16, 1024),
-                        make_desc_sw128(wa + q * 32, 16, 1024), IDESC, q ? 1u : 0u);
-          mma_commit(&S.d2_full[buf]);
+            mma_bf16_ss_elect(tmem + 2 * WS_HID + buf * WS_HID, ad + q * KSTEP, w2d + q * KSTEP, IDESC, q ? 1u : 0u);
+          mma_commit_elect(&S.d2_full[buf]);
         }
       }
     }
