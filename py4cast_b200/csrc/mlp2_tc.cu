@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
   FwdSmem& S = *reinterpret_cast<FwdSmem*>(
       smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const p4c_mlp_t& m = a.m;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // uniform for the compiler
   const int quad = warp & 3, cg = warp >> 2;  // TMEM lane quadrant (rows) / column group
   const int row = quad * 32 + lane, col0 = cg * CPT;
   const long long total_rows = static_cast<long long>(m.rows) * m.batch;
@@ -263,16 +263,16 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     P4C_TRACE(4);
 
     // ---- GEMM 1: D1[128x64] = X[128 x 64*nblk] * W1^T
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       for (int k = 0; k < nblk; ++k) {
         const uint32_t xa = smem_u32(S.X[k]), wa = smem_u32(S.W1[k]);
         const int nk = (a.kb.kvalid[k] + 15) >> 4;  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
         for (int j = 0; j < nk; ++j)
-          mma_bf16_ss(tmem, make_desc_sw128(xa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024),
+          mma_bf16_ss_elect(tmem, make_desc_sw128(xa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024),
                       IDESC, (k | j) ? 1u : 0u);
       }
-      mma_commit(&S.mbar[0]);
+      mma_commit_elect(&S.mbar[0]);
     }
     // meanwhile: addressing of the next tile
     const long long next = tile + gridDim.x;
@@ -311,14 +311,14 @@ __global__ void __launch_bounds__(NT, 2) mlp2_tc_fwd_kernel(const __grid_constan
     P4C_TRACE(6);
 
     // ---- GEMM 2: D2[128x64] = A2[128x64] * W2^T
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t aa = smem_u32(S.A2), wa = smem_u32(S.W2);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        mma_bf16_ss(tmem + HID, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024),
+        mma_bf16_ss_elect(tmem + HID, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024),
                     IDESC, j ? 1u : 0u);
-      mma_commit(&S.mbar[1]);
+      mma_commit_elect(&S.mbar[1]);
     }
     // residual / edge rows of this tile: fetched while GEMM 2 runs (consumed at the very end)
     uint4 res_pre[CPT / 8];

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
   uint8_t* ONES = W1T + ndx * WBLK;
   BwdCtl& C = *reinterpret_cast<BwdCtl*>(ONES + ONES_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // uniform for the compiler
   const int quad = warp & 3, hsel = warp >> 2;  // TMEM lane quadrant (rows) / column group
   const int row = quad * 32 + lane, col0 = hsel * CPT;
   const int quad_bar = 1 + quad;  // named barrier of the TPR warps that share these rows
@@ -440,14 +440,14 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       if (!(args.ablate & 32)) fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0 && !(args.ablate & 8)) {
+      if (warp == 0 && !(args.ablate & 8)) {
         tc_fence_after();
         const uint32_t aa = smem_u32(A1), wa = smem_u32(W2s);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(aa + j * 32, 16, 1024),
+          mma_bf16_ss_elect(tmem + COL_SCRATCH, make_desc_sw128(aa + j * 32, 16, 1024),
                       make_desc_sw128(wa + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
-        mma_commit(&C.mbar[0]);
+        mma_commit_elect(&C.mbar[0]);
       }
       if (!(args.ablate & 8)) mbar_wait(&C.mbar[0], parity);
       tc_fence_after();
@@ -522,21 +522,21 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
 
     // ---- d. G2: da1 = dh2 W2 -> scratch ;  G3: dW2 += a1^T dh2
     P4C_BWD_TRACE(6);
-    if (tid == 0 && !(args.ablate & 8)) {
+    if (warp == 0 && !(args.ablate & 8)) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), wt = smem_u32(W2T), a1 = smem_u32(A1);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+        mma_bf16_ss_elect(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
                     make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
       {
         const uint32_t ones = smem_u32(ONES);
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // K = 128 rows, 16 per MMA = 2 groups of 8 rows = 2048 bytes
-          mma_bf16_ss(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, ones - (a1 + j * 2048), 1024),
+          mma_bf16_ss_elect(tmem + COL_DW2, make_desc_sw128(a1 + j * 2048, ones - (a1 + j * 2048), 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
       }
-      mma_commit(&C.mbar[1]);
+      mma_commit_elect(&C.mbar[1]);
     }
     if (!(args.ablate & 8)) mbar_wait(&C.mbar[1], parity);
     tc_fence_after();
@@ -576,21 +576,21 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
     P4C_BWD_TRACE(9);
 
     // ---- f. G4: dW1 += X^T dh1 ; G5(0): dX = dh1 W1[:, s0]
-    if (tid == 0 && !(args.ablate & 8)) {
+    if (warp == 0 && !(args.ablate & 8)) {
       tc_fence_after();
       const uint32_t da = smem_u32(DH), xa = smem_u32(Xs);
       {
         const uint32_t ones = smem_u32(ONES);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          mma_bf16_ss(tmem + COL_DW1A, make_desc_sw128(xa + j * 2048, BLK, 1024),
+          mma_bf16_ss_elect(tmem + COL_DW1A, make_desc_sw128(xa + j * 2048, BLK, 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
         // dW1B: lanes 0..63 = X2^T dh1 (three K-blocks) or ones; lanes 64..127 = 1^T dh1 = db1
         const uint32_t x2 = nblk == 3 ? xa + 2 * BLK : ones;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t ab = nblk == 3 ? x2 + j * 2048 : ones;
-          mma_bf16_ss(tmem + COL_DW1B, make_desc_sw128(ab, ones - ab, 1024),
+          mma_bf16_ss_elect(tmem + COL_DW1B, make_desc_sw128(ab, ones - ab, 1024),
                       make_desc_sw128(da + j * 2048, BLK, 1024), IDESC_MM, (acc | j) ? 1u : 0u);
         }
       }
@@ -598,10 +598,10 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
         const uint32_t wt = smem_u32(W1T);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+          mma_bf16_ss_elect(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
                       make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
       }
-      mma_commit(&C.mbar[2]);
+      mma_commit_elect(&C.mbar[2]);
     }
     // meanwhile: dh1 to global memory (this thread's own chunks, read back from the DH tile), the
     // next tile's h1 rows into the A1 tile (free: G1, G3 complete), its source offsets (index
@@ -635,14 +635,14 @@ __global__ void __launch_bounds__(TM * TPR, 2) mlp2_tc_bwd_kernel(const __grid_c
       if (d == 1) {
         tc_fence_before();
         __syncthreads();  // everyone has read the scratch of dX(0)
-        if (tid == 0) {
+        if (warp == 0) {
           tc_fence_after();
           const uint32_t da = smem_u32(DH), wt = smem_u32(W1T + WBLK);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            mma_bf16_ss(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
+            mma_bf16_ss_elect(tmem + COL_SCRATCH, make_desc_sw128(da + j * 32, 16, 1024),
                         make_desc_sw128(wt + j * 32, 16, 1024), IDESC_KK, j ? 1u : 0u);
-          mma_commit(&C.mbar[3]);
+          mma_commit_elect(&C.mbar[3]);
         }
         mbar_wait(&C.mbar[3], parity);
         tc_fence_after();

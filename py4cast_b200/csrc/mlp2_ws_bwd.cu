@@ -282,9 +282,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       // issues).  Every product is a run of MMAs whose operand descriptors advance by a constant (K-major: 32
       // bytes = 2 address units per K = 16; MN-major: 16 tile rows = 2048 bytes = 128 units): one base
       // descriptor per operand, one 64-bit add per MMA.
-      // The weight-gradient products (G3, G4) of tile t are issued only after those of tile t - 1 (the other
-      // warp signals g3_turn / g4_turn after issuing): the fp32 accumulation order, and with it every bit of the
-      // result, is the same in every run.  The first product issued into an accumulator overwrites it.
+      // The weight-gradient products (G3, G4) of tile t are issued only after those of tile t - 1 have
+      // COMPLETED (the other warp commits them to g3_turn / g4_turn): the fp32 accumulation order, and with it
+      // every bit of the result, is the same in every run.  The first product issued into an accumulator
+      // overwrites it.
       constexpr uint32_t IDESC_KK = make_idesc_bf16(WB_TM, WB_HID, 0, 0);  // A, B K-major
       constexpr uint32_t IDESC_KM = make_idesc_bf16(WB_TM, WB_HID, 0, 1);  // A K-major, B MN-major
       constexpr uint32_t IDESC_MM = make_idesc_bf16(WB_TM, WB_HID, 1, 1);  // A, B MN-major
@@ -344,8 +345,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // K = 128 tile rows, 16 per MMA
           mma_bf16_ss_elect(tmem + WB_COL_DW2, a1_ones + q * ONES_STEP, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
-        tc_fence_before();
-        mbar_arrive_elect(&S.g3_turn[c]);
+        mma_commit_elect(&S.g3_turn[c]);  // COMPLETION, not issue: products of different issuing warps are not
+                                          // executed in issue order (measured: dW2 varied in its last bits)
         mma_commit_elect(&S.da1_full[c]);
         P4C_WB_TRACE(trc && lane == 0, 18);
 
@@ -366,8 +367,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
           for (int q = 0; q < 8; ++q)
             mma_bf16_ss_elect(tmem + WB_COL_DW1B, x2o + q * x2step, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
         }
-        tc_fence_before();
-        mbar_arrive_elect(&S.g4_turn[c]);
+        mma_commit_elect(&S.g4_turn[c]);
         mma_commit_elect(&S.x_empty[xst]);
         P4C_WB_TRACE(trc && lane == 0, 19);
 

@@ -141,7 +141,7 @@ struct SegLinArgs {
 __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_constant__ SegLinArgs a) {
   extern __shared__ unsigned char smem_raw[];
   SegLinSmem& S = *reinterpret_cast<SegLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // uniform for the compiler
   const int quad = warp & 3, hsel = warp >> 2;
   const int row = quad * 32 + lane, col0 = hsel * 32;
   const long long total = static_cast<long long>(a.num_seg) * a.batch;
@@ -197,14 +197,14 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t aa = smem_u32(S.A), wa = smem_u32(S.W);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        mma_bf16_ss(tmem, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024), IDESC,
+        mma_bf16_ss_elect(tmem, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024), IDESC,
                     j ? 1u : 0u);
-      mma_commit(&S.mbar);
+      mma_commit_elect(&S.mbar);
     }
     mbar_wait(&S.mbar, it & 1u);
     tc_fence_after();

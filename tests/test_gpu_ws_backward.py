@@ -181,10 +181,12 @@ def test_pipelined_backward_is_bit_reproducible(lib, cuda):
         return [xx.grad.clone()] + [w.grad.clone() for w in ws]
 
     n0 = lib.p4c_ws_bwd_launch_count()
-    a, b = run(), run()
-    assert lib.p4c_ws_bwd_launch_count() - n0 == 2
-    for u, v in zip(a, b):
-        assert torch.equal(u, v)
+    a = run()
+    for rep in range(8):  # the two MMA warps race differently from run to run: the result must not
+        b = run()
+        for u, v in zip(a, b):
+            assert torch.equal(u, v), f"repetition {rep}"
+    assert lib.p4c_ws_bwd_launch_count() - n0 == 9
 
 
 def test_trainer_step_with_deferred_partials_through_the_pipelined_backward(lib, cuda, tmp_path):
