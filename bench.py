@@ -33,8 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (NCCL prints its version there)
+# keep stdout to the ONE JSON line: whatever NCCL prints (its version banner at any debug level) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 
