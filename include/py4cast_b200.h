@@ -176,12 +176,6 @@ void p4c_set_ws_min_tiles(int64_t n);
 int64_t p4c_get_ws_min_tiles(void);
 /* launches of the pipelined forward kernel so far (tests assert that it really ran) */
 int64_t p4c_ws_launch_count(void);
-/* Thread shape of the tensor-core backward kernel: 2 threads per tile row (256-thread CTAs, 32
- * columns each; default, faster on B200) or 4 (512-thread CTAs, 16 columns each).  Environment
- * variable P4C_BWD_TPR.  Both shapes compute the same sums; the association order of the
- * LayerNorm-backward row sums and of the bias-gradient column sums differs (fp32 round-off). */
-void p4c_set_bwd_tpr(int threads_per_row);
-int p4c_get_bwd_tpr(void);
 /* developer aid: when set (16 x int64 device buffer), CTA 0 of the tensor-core forward kernel stores
  * the SM clock at the phases of its first tile (set-up, gather, GEMM 1, epilogue 1, ...). NULL = off. */
 void p4c_set_trace_buffer(void* device_buffer);

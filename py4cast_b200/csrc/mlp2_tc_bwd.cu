@@ -808,19 +808,6 @@ int tc_backward_grid(const p4c_mlp_t* m) {
   return static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
 }
 
-// threads per tile row of the backward kernel: 2 (default) or 4 (P4C_BWD_TPR / p4c_set_bwd_tpr).
-// Measured on B200 (profiles/r01h_bwd_shapes.txt): the 4-threads-per-row shape (32 warps per SM at 64
-// registers) is ~8 % SLOWER on the large calls -- the kernel is bound by its per-tile chain of
-// proxy fences (fence.proxy.async = MEMBAR.ALL.CTA in SASS) and LDGSTS issue, not by warp count.
-static int g_bwd_tpr = 0;
-static int bwd_threads_per_row() {
-  if (g_bwd_tpr == 0) {
-    const char* e = getenv("P4C_BWD_TPR");
-    g_bwd_tpr = (e && atoi(e) == 4) ? 4 : 2;
-  }
-  return g_bwd_tpr;
-}
-
 int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStream_t st) {
   using namespace tc;
   BwdArgs a;
@@ -860,16 +847,18 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
     }
   }
   const size_t smem = bwd_smem_bytes(a.kb.nblk, a.ndx) + 1024;
-  const int tpr = bwd_threads_per_row();
-  auto kernel = tpr == 4 ? mlp2_tc_bwd_kernel<4> : mlp2_tc_bwd_kernel<2>;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[tpr == 4]) {
+  // two threads per tile row (a 4-threads-per-row shape, 32 warps per SM at 64 registers, measured 8 % slower in
+  // round 1 and was removed)
+  constexpr int tpr = 2;
+  auto kernel = mlp2_tc_bwd_kernel<2>;
+  static size_t configured[1] = {0};
+  if (smem > configured[0]) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mlp_backward(tc): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return P4C_ECUDA;
     }
-    configured[tpr == 4] = smem;
+    configured[0] = smem;
   }
   launch_pdl(kernel, dim3(tc_backward_grid(m)), dim3(TM * tpr), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_backward(tc)");
@@ -877,6 +866,3 @@ int launch_mlp2_tc_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, cudaStre
 }
 
 }  // namespace p4c
-
-extern "C" void p4c_set_bwd_tpr(int tpr) { p4c::g_bwd_tpr = tpr == 4 ? 4 : 2; }
-extern "C" int p4c_get_bwd_tpr(void) { return p4c::bwd_threads_per_row(); }

@@ -259,51 +259,3 @@ def test_forward_aggregate_rejects_bad_groups(ops, cuda):
     assert rc == 0
     torch.cuda.synchronize()
 
-
-@pytest.mark.parametrize("update_edges", [False, True])
-def test_backward_thread_shapes_agree(ops, cuda, update_edges):
-    """The backward kernel's two thread shapes (2 / 4 threads per tile row, p4c_set_bwd_tpr) produce
-    the same gradients up to fp32 summation order, and both match the fp32 oracle."""
-    from oracle import graph_ref
-    from py4cast_b200 import _lib
-    from py4cast_b200.graph_build import EdgeSet
-    from py4cast_b200.nlam import InteractionNet
-
-    lib = _lib.load()
-    nr, ns, B, deg = 700, 90, 2, 4
-    ei = _uniform_graph(nr, ns, deg, seed=11)
-    E = ei.shape[1]
-    torch.manual_seed(7)
-    ref = graph_ref.InteractionNet(ei, 64, update_edges=update_edges)
-    net = InteractionNet(EdgeSet(ei, torch.zeros(E, 3), ns, nr), 64, update_edges=update_edges)
-    net.load_state_dict(ref.state_dict())
-    net = net.to(cuda)
-    g = torch.Generator().manual_seed(8)
-    send, rec, edge = (torch.randn(B, n, 64, generator=g).bfloat16().float() for n in (ns, nr, E))
-    g_rec, g_edge = torch.randn(B, nr, 64, generator=g), torch.randn(B, E, 64, generator=g)
-
-    def run(module, ins, dev):
-        out = module(*ins)
-        if update_edges:
-            (out[0].float() * g_rec.to(dev)).sum().add((out[1].float() * g_edge.to(dev)).sum()).backward()
-        else:
-            (out.float() * g_rec.to(dev)).sum().backward()
-        return [t.grad.float().cpu() for t in ins] + [p.grad.float().cpu() for p in module.parameters()]
-
-    ins_r = [t.clone().requires_grad_(True) for t in (send, rec, edge)]
-    grads_ref = run(ref, ins_r, "cpu")
-    results = {}
-    default = lib.p4c_get_bwd_tpr()
-    try:
-        for tpr in (2, 4):
-            lib.p4c_set_bwd_tpr(tpr)
-            assert lib.p4c_get_bwd_tpr() == tpr
-            net.zero_grad(set_to_none=True)
-            ins_g = [t.to(cuda).bfloat16().requires_grad_(True) for t in (send, rec, edge)]
-            results[tpr] = run(net, ins_g, cuda)
-            for i, (a, b) in enumerate(zip(results[tpr], grads_ref)):
-                assert_close(a, b, BF16_TOL, f"tpr={tpr} gradient {i}")
-    finally:
-        lib.p4c_set_bwd_tpr(default)
-    for i, (a, b) in enumerate(zip(results[2], results[4])):
-        assert_close(a, b, 2e-3, f"thread shapes differ on gradient {i}")
