@@ -280,6 +280,30 @@ int p4c_seg_linear(const void* src, int64_t src_batch_stride, const int32_t* row
                    void* out, int64_t out_batch_stride, int accumulate, int32_t tile_rows /* as in
                    p4c_mlp_t */, int dtype, void* stream);
 
+/* One or TWO segment sets over the same rows `src` in ONE launch (the InteractionNet backward needs the
+ * gradient by receiver and by sender of the same dh1: reference autograd of `index_select` x 2,
+ * SURVEY.md 3.2 K1 / K3 transposed).  part1 may be NULL (= p4c_seg_linear).  When both parts name the same
+ * `out` (senders are receivers: same-level mesh InteractionNets) the two summed tiles are the two K-blocks
+ * of one product and `out` is read-modify-written once (part1->accumulate must be 1; part0->accumulate says
+ * whether the previous content of `out` is added); otherwise the parts are independent problems that share
+ * the launch (CTAs split in proportion to their tiles).                                           */
+typedef struct {
+  const int32_t* rowptr;
+  const int32_t* perm;
+  const float* scale;
+  int32_t num_seg;
+  int32_t batch;
+  int64_t src_batch_stride;
+  int32_t col0;
+  int32_t kblock;
+  void* out;
+  int64_t out_batch_stride;
+  int32_t accumulate;
+  int32_t tile_rows;
+} p4c_seg_part_t;
+int p4c_seg_linear_pair(const void* src, const float* w1, int32_t k1, const void* packed,
+                        const p4c_seg_part_t* part0, const p4c_seg_part_t* part1, int dtype, void* stream);
+
 int64_t p4c_mlp_wgrad_partial_floats(const p4c_mlp_t* m);
 int p4c_mlp_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, void* stream);
 

@@ -109,6 +109,16 @@ class WGrad(C.Structure):
     ]
 
 
+class SegPart(C.Structure):
+    _fields_ = [
+        ("rowptr", C.c_void_p), ("perm", C.c_void_p), ("scale", C.c_void_p),
+        ("num_seg", C.c_int32), ("batch", C.c_int32), ("src_batch_stride", C.c_int64),
+        ("col0", C.c_int32), ("kblock", C.c_int32),
+        ("out", C.c_void_p), ("out_batch_stride", C.c_int64),
+        ("accumulate", C.c_int32), ("tile_rows", C.c_int32),
+    ]
+
+
 class ArX(C.Structure):
     _fields_ = [
         ("batch", C.c_int32),
@@ -169,6 +179,7 @@ SYMBOLS = {
     "p4c_seg_linear": (
         _int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _int, _i32, _int, _vp]
     ),
+    "p4c_seg_linear_pair": (_int, [_vp, _vp, _i32, _vp, C.POINTER(SegPart), C.POINTER(SegPart), _int, _vp]),
     "p4c_mlp_backward": (_int, [C.POINTER(Mlp), C.POINTER(MlpBwd), _vp]),
     "p4c_rows_matmul": (_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _int, _int, _vp]),
     "p4c_batch_sum": (_int, [_vp, _i64, _i32, _i64, _vp, _int, _int, _vp]),

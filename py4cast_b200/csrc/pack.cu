@@ -112,7 +112,10 @@ int launch_wgrad_reduce_single(const p4c_wgrad_t* e, cudaStream_t st) {
 // ------------------------------------------------------------------ segment sum + 64x64 GEMM (TC)
 namespace tc {
 
-struct SegLinSmem {
+// Set 0 first: launches that sum one set per tile (classic and split calls) allocate only SegLinSmem0.  The
+// large gathers are bound by the requests the L1 can keep in flight, and every KB of shared memory is taken from
+// it (measured: m2g by-sender pass 0.62 -> 0.84 ms with the two-set layout).
+struct SegLinSmem0 {
   uint8_t A[128 * 128];  // summed rows, bf16, swizzled
   uint8_t W[64 * 128];   // [n = input column][k = hidden unit] = W1T block
   uint32_t lo[128], hi[128], sbase[128];
@@ -120,41 +123,81 @@ struct SegLinSmem {
   int32_t orow[128];
   uint64_t mbar;
   uint32_t tmem_base;
+  uint32_t pad[125];  // to a multiple of 1 KB (swizzled tiles follow)
 };
+struct SegLinSmem1 {  // the second set of a fused call
+  uint8_t A[128 * 128];
+  uint8_t W[64 * 128];
+  uint32_t lo[128], hi[128], sbase[128];
+  float sc[128];
+};
+static_assert(sizeof(SegLinSmem0) % 1024 == 0, "the second set's tiles must stay 1 KB aligned");
 
-struct SegLinArgs {
-  const __nv_bfloat16* src;
-  long long src_bs;
+// One segment set of a launch: out[b, r, :] (+)= (scale[r] * sum over segment r of src rows) x W1 block
+struct SegPart {
   const int32_t* rowptr;
   const int32_t* perm;
   const float* scale;
-  int num_seg, batch;
-  const float* w1;
-  int k1, col0;
   const uint8_t* packed_block;  // PK_W1T block of the image, or NULL
+  int col0;
+  int num_seg, batch;
+  long long src_bs;
   __nv_bfloat16* out;
   long long out_bs;
   int accumulate;
   int tile_rows;  // valid rows per tile (16..128)
 };
 
+// One or two segment sets over the SAME rows `src` (dh1 of an edge MLP):
+//   nparts == 1                    the classic call;
+//   nparts == 2, fused             both sets end in the same output rows (sender and receiver gradient of an
+//                                  InteractionNet whose senders are its receivers): the two summed tiles are
+//                                  the two K-blocks of ONE product, one read-modify-write of the output;
+//   nparts == 2, not fused         independent problems, CTAs [0, grid0) run set 0 and the others set 1
+//                                  (one launch instead of two on the launch-bound mesh levels).
+struct SegLinArgs {
+  const __nv_bfloat16* src;
+  const float* w1;
+  int k1;
+  int nparts, fused, grid0;
+  SegPart p[2];
+};
+
+// PAIR = false: one set per launch (everything about the second set folds away at compile time; the large
+// gathers of the m2g / g2m backward run through this instantiation).
+template <bool PAIR>
 __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_constant__ SegLinArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  SegLinSmem& S = *reinterpret_cast<SegLinSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  SegLinSmem0& S = *reinterpret_cast<SegLinSmem0*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  SegLinSmem1& S1 = *reinterpret_cast<SegLinSmem1*>(reinterpret_cast<unsigned char*>(&S) + sizeof(SegLinSmem0));
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // uniform for the compiler
   const int quad = warp & 3, hsel = warp >> 2;
   const int row = quad * 32 + lane, col0 = hsel * 32;
-  const long long total = static_cast<long long>(a.num_seg) * a.batch;
-  const int TR = a.tile_rows;
+  const bool split = PAIR && a.nparts == 2 && !a.fused;
+  const int first = (split && static_cast<int>(blockIdx.x) >= a.grid0) ? 1 : 0;  // this CTA's (first) set
+  const int nsum = (PAIR && a.fused) ? 2 : 1;
+  const int bid = static_cast<int>(blockIdx.x) - (first ? a.grid0 : 0);
+  const int nct = split ? (first ? static_cast<int>(gridDim.x) - a.grid0 : a.grid0) : static_cast<int>(gridDim.x);
+  const SegPart& P0 = PAIR ? a.p[first] : a.p[0];
+  const long long total = static_cast<long long>(P0.num_seg) * P0.batch;
+  const int TR = P0.tile_rows;
+  const int32_t* const perm0 = P0.perm;
+  const int32_t* const perm1 = a.p[1].perm;
+  __nv_bfloat16* const outp = P0.out;
+  const bool accum = P0.accumulate != 0;
   const long long ntiles = (total + TR - 1) / TR;
 
-  if (a.packed_block) {
-    for (int i = tid; i < 512; i += 256) cp_async16(smem_u32(S.W) + i * 16, a.packed_block + i * 16, 16u);
-  } else {
-    for (int i = tid; i < 64 * 64; i += 256) {
-      const int c = i >> 6, k = i & 63;  // W[n=k][K=c] = w1[c][col0 + k]
-      *reinterpret_cast<__nv_bfloat16*>(S.W + sw128_offset(k, c >> 3) + (c & 7) * 2) =
-          __float2bfloat16_rn(a.w1[static_cast<long long>(c) * a.k1 + a.col0 + k]);
+  for (int s = 0; s < nsum; ++s) {
+    const SegPart& P = a.p[first + s];
+    uint8_t* const Ws = s ? S1.W : S.W;
+    if (P.packed_block) {
+      for (int i = tid; i < 512; i += 256) cp_async16(smem_u32(Ws) + i * 16, P.packed_block + i * 16, 16u);
+    } else {
+      for (int i = tid; i < 64 * 64; i += 256) {
+        const int c = i >> 6, k = i & 63;  // W[n=k][K=c] = w1[c][col0 + k]
+        *reinterpret_cast<__nv_bfloat16*>(Ws + sw128_offset(k, c >> 3) + (c & 7) * 2) =
+            __float2bfloat16_rn(a.w1[static_cast<long long>(c) * a.k1 + P.col0 + k]);
+      }
     }
   }
   cp_async_commit();
@@ -174,36 +217,54 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
   pdl_launch_dependents();
   pdl_wait();  // the previous kernel's outputs are complete and visible
   uint32_t it = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    if (tid < 128) {
-      const long long g = tile * TR + tid;
-      uint32_t lo = 0xFFFFFFFFu, hi = 0, sb = 0;
-      float sc = 1.f;
-      int32_t o = -1;
-      if (tid < TR && g < total) {
-        const long long b = g / a.num_seg;
-        const int rr = static_cast<int>(g - b * a.num_seg);
-        lo = static_cast<uint32_t>(a.rowptr[rr]);
-        hi = static_cast<uint32_t>(a.rowptr[rr + 1]);
-        sb = static_cast<uint32_t>((b * a.src_bs) >> 3);
-        if (a.scale) sc = a.scale[rr];
-        o = static_cast<int32_t>((b * a.out_bs) / 64 + rr);
+  for (long long tile = bid; tile < ntiles; tile += nct, ++it) {
+    {  // row tables: threads 0..127 fill set 0, threads 128..255 set 1 (fused calls)
+      const int s = tid >> 7, t = tid & 127;
+      if (s < nsum) {
+        const SegPart& P = a.p[first + s];
+        const long long g = tile * TR + t;
+        uint32_t lo = 0xFFFFFFFFu, hi = 0, sb = 0;
+        float sc = 1.f;
+        int32_t o = -1;
+        if (t < TR && g < total) {
+          const long long b = g / P.num_seg;
+          const int rr = static_cast<int>(g - b * P.num_seg);
+          lo = static_cast<uint32_t>(P.rowptr[rr]);
+          hi = static_cast<uint32_t>(P.rowptr[rr + 1]);
+          sb = static_cast<uint32_t>((b * P.src_bs) >> 3);
+          if (P.scale) sc = P.scale[rr];
+          o = static_cast<int32_t>((b * P.out_bs) / 64 + rr);
+        }
+        if (s == 0) {
+          S.lo[t] = lo; S.hi[t] = hi; S.sbase[t] = sb; S.sc[t] = sc; S.orow[t] = o;
+        } else {
+          S1.lo[t] = lo; S1.hi[t] = hi; S1.sbase[t] = sb; S1.sc[t] = sc;
+        }
       }
-      S.lo[tid] = lo; S.hi[tid] = hi; S.sbase[tid] = sb; S.sc[tid] = sc; S.orow[tid] = o;
     }
     __syncthreads();
-    seg_sum_tile<256>(a.src, a.perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
-    cp_async_wait<0>();  // the weight block (first tile)
+    // (the branches on the null-ness of perm are taken here, outside the gather loops: inside them the compiler
+    // would serialise the index loads)
+    if (!PAIR) seg_sum_tile<256>(a.src, a.p[0].perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+    else if (perm0) seg_sum_tile<256>(a.src, perm0, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+    else seg_sum_tile<256>(a.src, nullptr, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+    if (PAIR && nsum == 2) {
+      if (perm1) seg_sum_tile<256>(a.src, perm1, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
+      else seg_sum_tile<256>(a.src, nullptr, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
+    }
+    cp_async_wait<0>();  // the weight blocks (first tile)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t aa = smem_u32(S.A), wa = smem_u32(S.W);
+      for (int s = 0; s < nsum; ++s) {
+        const uint32_t aa = smem_u32(s ? S1.A : S.A), wa = smem_u32(s ? S1.W : S.W);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        mma_bf16_ss_elect(tmem, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024), IDESC,
-                    j ? 1u : 0u);
+        for (int j = 0; j < 4; ++j)
+          mma_bf16_ss_elect(tmem, make_desc_sw128(aa + j * 32, 16, 1024), make_desc_sw128(wa + j * 32, 16, 1024), IDESC,
+                      (s | j) ? 1u : 0u);
+      }
       mma_commit_elect(&S.mbar);
     }
     mbar_wait(&S.mbar, it & 1u);
@@ -213,18 +274,24 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
     tmem_ld_wait();
     const long long orow = S.orow[row];
     if (orow >= 0) {
-      __nv_bfloat16* dst = a.out + orow * 64 + col0;
+      __nv_bfloat16* dst = outp + orow * 64 + col0;
+      if (accum) {  // the four loads in flight together
+        uint4 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = *reinterpret_cast<const uint4*>(dst + j * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float* o = v + j * 8;
+          float2 t;
+          t = unpack_bf16x2(e[j].x); o[0] += t.x; o[1] += t.y;
+          t = unpack_bf16x2(e[j].y); o[2] += t.x; o[3] += t.y;
+          t = unpack_bf16x2(e[j].z); o[4] += t.x; o[5] += t.y;
+          t = unpack_bf16x2(e[j].w); o[6] += t.x; o[7] += t.y;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float* o = v + j * 8;
-        if (a.accumulate) {
-          const uint4 e = *reinterpret_cast<const uint4*>(dst + j * 8);
-          float2 t;
-          t = unpack_bf16x2(e.x); o[0] += t.x; o[1] += t.y;
-          t = unpack_bf16x2(e.y); o[2] += t.x; o[3] += t.y;
-          t = unpack_bf16x2(e.z); o[4] += t.x; o[5] += t.y;
-          t = unpack_bf16x2(e.w); o[6] += t.x; o[7] += t.y;
-        }
+        const float* o = v + j * 8;
         uint4 u;
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
@@ -260,42 +327,110 @@ extern "C" int p4c_wgrad_reduce_batched(const p4c_wgrad_t* table_dev, int32_t n,
   return P4C_OK;
 }
 
+static int seg_check_part(const p4c_seg_part_t* q, int32_t k1, const void* packed, const char* what) {
+  P4C_REQUIRE(q->rowptr && q->out, "%s: null pointer", what);
+  P4C_REQUIRE(q->num_seg > 0 && q->batch > 0, "%s: empty problem", what);
+  P4C_REQUIRE(q->col0 >= 0 && q->col0 + HIDP <= k1, "%s: column window [%d,%d) outside k1=%d", what, q->col0,
+              q->col0 + HIDP, k1);
+  P4C_REQUIRE(q->src_batch_stride % 8 == 0 && q->out_batch_stride % 64 == 0,
+              "%s: batch strides must be multiples of 8 / 64 elements", what);
+  P4C_REQUIRE(reinterpret_cast<uintptr_t>(q->out) % 16 == 0, "%s: out must be 16-byte aligned", what);
+  P4C_REQUIRE(!packed || (q->kblock >= 0 && q->kblock < P4C_MAX_SRC), "%s: bad kblock %d", what, q->kblock);
+  const int tr = q->tile_rows == 0 ? 128 : q->tile_rows;
+  P4C_REQUIRE(tr == 16 || tr == 32 || tr == 64 || tr == 128, "%s: tile_rows=%d not in {16,32,64,128}", what, tr);
+  return P4C_OK;
+}
+
+static void seg_fill_part(tc::SegPart* d, const p4c_seg_part_t* q, const void* packed) {
+  d->rowptr = q->rowptr;
+  d->perm = q->perm;
+  d->scale = q->scale;
+  d->packed_block = packed ? static_cast<const uint8_t*>(packed) + tc::PK_W1T + q->kblock * 8192 : nullptr;
+  d->col0 = q->col0;
+  d->num_seg = q->num_seg;
+  d->batch = q->batch;
+  d->src_bs = q->src_batch_stride;
+  d->out = static_cast<__nv_bfloat16*>(q->out);
+  d->out_bs = q->out_batch_stride;
+  d->accumulate = q->accumulate;
+  d->tile_rows = q->tile_rows == 0 ? 128 : q->tile_rows;
+}
+
+static long long seg_part_tiles(const tc::SegPart& d) {
+  return (static_cast<long long>(d.num_seg) * d.batch + d.tile_rows - 1) / d.tile_rows;
+}
+
+extern "C" int p4c_seg_linear_pair(const void* src, const float* w1, int32_t k1, const void* packed,
+                                   const p4c_seg_part_t* part0, const p4c_seg_part_t* part1, int dtype, void* stream) {
+  P4C_REQUIRE(src && w1 && part0, "seg_linear_pair: null pointer");
+  P4C_REQUIRE(dtype == P4C_BF16, "seg_linear_pair: tensor-core engine, bf16 storage only (dtype=%d)", dtype);
+  P4C_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0, "seg_linear_pair: src must be 16-byte aligned");
+  int rc = seg_check_part(part0, k1, packed, "seg_linear_pair(part 0)");
+  if (rc) return rc;
+  if (part1 && (rc = seg_check_part(part1, k1, packed, "seg_linear_pair(part 1)"))) return rc;
+  using namespace tc;
+  SegLinArgs a{};
+  a.src = static_cast<const __nv_bfloat16*>(src);
+  a.w1 = w1;
+  a.k1 = k1;
+  a.nparts = part1 ? 2 : 1;
+  seg_fill_part(&a.p[0], part0, packed);
+  if (part1) seg_fill_part(&a.p[1], part1, packed);
+  else a.p[1] = a.p[0];
+  // both sets end in the same output rows: one product over two K-blocks (the second set's accumulate flag is
+  // implied; the first set's decides whether the previous content of `out` is added)
+  a.fused = part1 && part0->out == part1->out;
+  if (a.fused) {
+    P4C_REQUIRE(a.p[0].num_seg == a.p[1].num_seg && a.p[0].batch == a.p[1].batch && a.p[0].out_bs == a.p[1].out_bs &&
+                    a.p[0].tile_rows == a.p[1].tile_rows,
+                "seg_linear_pair: sets that share an output must have the same segments x batch shape and tile_rows");
+    P4C_REQUIRE(part1->accumulate, "seg_linear_pair: the second set of a shared output accumulates by definition");
+  }
+  const long long t0 = seg_part_tiles(a.p[0]), t1 = part1 ? seg_part_tiles(a.p[1]) : 0;
+  const long long cap = tc_max_ctas();
+  if (part1 && !a.fused && t0 + t1 > cap) {
+    // Independent sets that do not fit one wave of CTAs together gain nothing from sharing a launch (they are
+    // bandwidth-bound, and a set of few long segments costs more per source row than one of many short ones:
+    // measured, g2m by receiver + by sender, 0.93 ms as two launches, 1.7 ms as one with equal shares)
+    int rc2 = p4c_seg_linear_pair(src, w1, k1, packed, part0, nullptr, dtype, stream);
+    if (rc2) return rc2;
+    return p4c_seg_linear_pair(src, w1, k1, packed, part1, nullptr, dtype, stream);
+  }
+  int grid;
+  a.grid0 = 0;
+  if (part1 && !a.fused) {  // every tile of both sets has its own CTA
+    a.grid0 = static_cast<int>(t0);
+    grid = static_cast<int>(t0 + t1);
+  } else {
+    grid = static_cast<int>(t0 < cap ? t0 : cap);
+  }
+  const size_t smem_max = sizeof(SegLinSmem0) + sizeof(SegLinSmem1) + 1024;
+  const size_t smem = (a.fused ? sizeof(SegLinSmem0) + sizeof(SegLinSmem1) : sizeof(SegLinSmem0)) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(seg_linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) {
+      set_error("seg_linear: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return P4C_ECUDA;
+    }
+    configured = true;
+  }
+  if (part1) launch_pdl(seg_linear_tc_kernel<true>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a);
+  else launch_pdl(seg_linear_tc_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a);
+  P4C_CHECK_LAUNCH("seg_linear");
+  return P4C_OK;
+}
+
 extern "C" int p4c_seg_linear(const void* src, int64_t src_bs, const int32_t* rowptr, const int32_t* perm,
                               const float* scale, int32_t num_seg, int32_t batch, const float* w1, int32_t k1,
                               int32_t col0, const void* packed, int32_t kblock, void* out, int64_t out_bs,
                               int accumulate, int32_t tile_rows, int dtype, void* stream) {
   P4C_REQUIRE(src && rowptr && out && w1, "seg_linear: null pointer");
-  P4C_REQUIRE(num_seg > 0 && batch > 0, "seg_linear: empty problem");
-  P4C_REQUIRE(dtype == P4C_BF16, "seg_linear: tensor-core engine, bf16 storage only (dtype=%d)", dtype);
-  P4C_REQUIRE(col0 >= 0 && col0 + HIDP <= k1, "seg_linear: column window [%d,%d) outside k1=%d", col0, col0 + HIDP, k1);
-  P4C_REQUIRE(src_bs % 8 == 0 && out_bs % 64 == 0, "seg_linear: batch strides must be multiples of 8 / 64 elements");
-  P4C_REQUIRE(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
-              "seg_linear: src / out must be 16-byte aligned");
-  P4C_REQUIRE(!packed || (kblock >= 0 && kblock < P4C_MAX_SRC), "seg_linear: bad kblock %d", kblock);
-  if (tile_rows == 0) tile_rows = 128;
-  P4C_REQUIRE(tile_rows == 16 || tile_rows == 32 || tile_rows == 64 || tile_rows == 128,
-              "seg_linear: tile_rows=%d not in {16,32,64,128}", tile_rows);
-  using namespace tc;
-  SegLinArgs a;
-  a.src = static_cast<const __nv_bfloat16*>(src);
-  a.src_bs = src_bs;
-  a.rowptr = rowptr;
-  a.perm = perm;
-  a.scale = scale;
-  a.num_seg = num_seg;
-  a.batch = batch;
-  a.w1 = w1;
-  a.k1 = k1;
-  a.col0 = col0;
-  a.packed_block = packed ? static_cast<const uint8_t*>(packed) + PK_W1T + kblock * 8192 : nullptr;
-  a.out = static_cast<__nv_bfloat16*>(out);
-  a.out_bs = out_bs;
-  a.accumulate = accumulate;
-  a.tile_rows = tile_rows;
-  const long long ntiles = (static_cast<long long>(num_seg) * batch + tile_rows - 1) / tile_rows;
-  const int grid = static_cast<int>(ntiles < tc_max_ctas() ? ntiles : tc_max_ctas());
-  const size_t smem = sizeof(SegLinSmem) + 1024;
-  launch_pdl(seg_linear_tc_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a);
-  P4C_CHECK_LAUNCH("seg_linear");
-  return P4C_OK;
+  p4c_seg_part_t q;
+  q.rowptr = rowptr; q.perm = perm; q.scale = scale;
+  q.num_seg = num_seg; q.batch = batch; q.src_batch_stride = src_bs;
+  q.col0 = col0; q.kblock = kblock;
+  q.out = out; q.out_batch_stride = out_bs;
+  q.accumulate = accumulate; q.tile_rows = tile_rows;
+  return p4c_seg_linear_pair(src, w1, k1, packed, &q, nullptr, dtype, stream);
 }

@@ -227,6 +227,7 @@ extern "C" int p4c_sizeof(int which) {
     case 4: return (int)sizeof(p4c_adamw_state_t);
     case 5: return (int)sizeof(p4c_pack_t);
     case 6: return (int)sizeof(p4c_wgrad_t);
+    case 7: return (int)sizeof(p4c_seg_part_t);
     default: return -1;
   }
 }

@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import HIDDEN, PACK_BYTES, ArX, Mlp, MlpBwd, Pack, WGrad, check, dtype_code, ptr, stream
+from ._lib import HIDDEN, PACK_BYTES, ArX, Mlp, MlpBwd, Pack, SegPart, WGrad, check, dtype_code, ptr, stream
 
 # ------------------------------------------------------------------ workspaces
 _WGRAD_WS: dict = {}
@@ -635,6 +635,33 @@ def seg_linear(src: torch.Tensor, csr: Csr, batch: int, w1: torch.Tensor, col0: 
     )
 
 
+def _seg_part(src: torch.Tensor, csr: Csr, batch: int, col0: int, out: torch.Tensor, accumulate: bool) -> SegPart:
+    q = SegPart()
+    q.rowptr, q.perm, q.scale = ptr(csr.rowptr), ptr(csr.perm), None
+    q.num_seg, q.batch, q.src_batch_stride = csr.num_seg, batch, src.shape[1] * HIDDEN
+    q.col0, q.kblock = col0, col0 // HIDDEN
+    q.out, q.out_batch_stride = ptr(out), out.shape[1] * HIDDEN
+    q.accumulate, q.tile_rows = int(accumulate), _seg_tile_rows(src.shape[1], csr.num_seg)
+    return q
+
+
+def seg_linear_pair(src: torch.Tensor, w1: torch.Tensor, meta: Optional[MlpMeta], batch: int,
+                    a: Tuple[Csr, int, torch.Tensor, bool], b: Tuple[Csr, int, torch.Tensor, bool]) -> None:
+    """Two seg_linear problems (csr, col0, out, accumulate) over the same rows `src` in ONE launch.  When both
+    write the same `out` (sender == receiver nodes) they become the two K-blocks of one product and `out` is
+    updated once; otherwise the CTAs of the launch are split between them."""
+    packed = meta.image_ptr(src.dtype) if meta is not None else None
+    qa = _seg_part(src, a[0], batch, a[1], a[2], a[3])
+    qb = _seg_part(src, b[0], batch, b[1], b[2], b[3])
+    if a[2].data_ptr() == b[2].data_ptr():
+        qb.tile_rows = qa.tile_rows = min(qa.tile_rows, qb.tile_rows)
+    check(
+        _lib.load().p4c_seg_linear_pair(ptr(src), ptr(w1), w1.shape[1], packed, C.byref(qa), C.byref(qb),
+                                        dtype_code(src.dtype), stream()),
+        "p4c_seg_linear_pair",
+    )
+
+
 def _batch_rows_csr(gi: GraphIndex, batch: int, device) -> Csr:
     """Segments {b * E + e : b < batch} over the rows of a (B, E, 64) tensor viewed as (B * E, 64):
     the batch sum of per-edge rows expressed as a segment sum (cached per edge set and batch)."""
@@ -895,14 +922,23 @@ class _InteractionNetFn(torch.autograd.Function):
                     bc = _batch_rows_csr(gi, B, dev)
                     seg_linear(dh1.view(1, B * E, HIDDEN), Csr(bc.rowptr[grp.start: grp.stop + 1], bc.perm, n),
                                1, w[0], 0, d_edge[grp.start: grp.stop].unsqueeze(0), False, meta=metas[gidx])
-                if need_rec and not rec_in_epilogue:
-                    seg_linear(dh1, grp.by_rec, B, w[0], 2 * HIDDEN, d_rec, True, meta=metas[gidx])
-                if need_send:
-                    if same_nodes:
-                        seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_rec, True, meta=metas[gidx])
-                    else:
-                        seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_send, not first_send, meta=metas[gidx])
+                rec_pass = need_rec and not rec_in_epilogue
+                if rec_pass and need_send:
+                    # receiver and sender gradient of the same dh1 in one launch (one product over two
+                    # K-blocks and one update of d_rec when the senders are the receivers)
+                    send_part = ((grp.by_send, HIDDEN, d_rec, True) if same_nodes
+                                 else (grp.by_send, HIDDEN, d_send, not first_send))
+                    seg_linear_pair(dh1, w[0], metas[gidx], B, (grp.by_rec, 2 * HIDDEN, d_rec, True), send_part)
                     first_send = False
+                else:
+                    if rec_pass:
+                        seg_linear(dh1, grp.by_rec, B, w[0], 2 * HIDDEN, d_rec, True, meta=metas[gidx])
+                    if need_send:
+                        if same_nodes:
+                            seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_rec, True, meta=metas[gidx])
+                        else:
+                            seg_linear(dh1, grp.by_send, B, w[0], HIDDEN, d_send, not first_send, meta=metas[gidx])
+                        first_send = False
             else:
                 if need_rec:
                     s_r = segment_sum(dh1, grp.by_rec, B)

@@ -38,9 +38,11 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.AdamWState) == 24
     assert ctypes.sizeof(_lib.Pack) == 7 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.WGrad) == 7 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.SegPart) == 3 * 8 + 2 * 4 + 8 + 2 * 4 + 8 + 8 + 2 * 4
     # and against the compiled library itself
     lib = _lib.load()
-    for which, st in enumerate((_lib.Src, _lib.Mlp, _lib.MlpBwd, _lib.ArX, _lib.AdamWState, _lib.Pack, _lib.WGrad)):
+    for which, st in enumerate((_lib.Src, _lib.Mlp, _lib.MlpBwd, _lib.ArX, _lib.AdamWState, _lib.Pack, _lib.WGrad,
+                                _lib.SegPart)):
         assert lib.p4c_sizeof(which) == ctypes.sizeof(st), st.__name__
     assert lib.p4c_sizeof(99) == -1
 
