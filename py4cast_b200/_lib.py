@@ -19,6 +19,8 @@ MAX_SRC = 3
 MAX_PREV = 8
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpy4cast_b200.so")
+if os.environ.get("P4C_LIB_AB"):  # developer aid: A/B timing of another in-tree build of the same ABI (scripts/ab_build.sh)
+    _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", os.environ["P4C_LIB_AB"])
 
 
 class Src(C.Structure):

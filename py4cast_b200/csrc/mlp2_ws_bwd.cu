@@ -456,21 +456,30 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         tmem_ld32(tm_ch, v);
         tmem_ld_wait();
         tc_fence_before();
+        const f32x2 half2 = f2_dup(0.5f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
           const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           float h[8];
-          h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
-          h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 0], v[c * 8 + 1]), f2_pack(ba.x, ba.y)), h[0], h[1]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 2], v[c * 8 + 3]), f2_pack(ba.z, ba.w)), h[2], h[3]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 4], v[c * 8 + 5]), f2_pack(bb.x, bb.y)), h[4], h[5]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 6], v[c * 8 + 7]), f2_pack(bb.z, bb.w)), h[6], h[7]);
           const uint4 hb = ws_pack8(h);  // the forward kept h1 in bf16: same rounding, same a1
           ws_unpack8(hb, h);
           float sg8[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float sg = fast_sigmoid(h[q]);
-            sg8[q] = fmaf(sg, fmaf(-h[q], sg, h[q]), sg);  // s (1 + h (1 - s))
-            h[q] *= sg;
+          for (int q = 0; q < 8; q += 2) {  // two elements per instruction (fp32 pairs): the forward's operations
+            const f32x2 hp = f2_pack(h[q], h[q + 1]);
+            float t0, t1;
+            f2_unpack(f2_mul(hp, half2), t0, t1);
+            asm("tanh.approx.f32 %0, %0;" : "+f"(t0));
+            asm("tanh.approx.f32 %0, %0;" : "+f"(t1));
+            const f32x2 sg = f2_fma(half2, f2_pack(t0, t1), half2);  // sigmoid
+            const f32x2 ap = f2_mul(hp, sg);                         // a1 = SiLU(h1)
+            f2_unpack(f2_fma(sg, f2_sub(hp, ap), sg), sg8[q], sg8[q + 1]);  // s (1 + h (1 - s))
+            f2_unpack(ap, h[q], h[q + 1]);
           }
           sts128(a1s + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
           gs[c] = ws_pack8(sg8);
@@ -511,22 +520,29 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         tmem_ld32(tm_ch, xh);
         tmem_ld_wait();
         tc_fence_before();
-        float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+        // fp32 pairs: two elements per instruction; the four row sums are kept as (even, odd) column pairs
+        f32x2 X2[16];
+        f32x2 s1p = 0ull, s2p = 0ull, s3p = 0ull, s4p = 0ull;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float d[8];
           ws_unpack8(dyr[c], d);
+          const float4 ba = *reinterpret_cast<const float4*>(b2 + c * 8), bb = *reinterpret_cast<const float4*>(b2 + c * 8 + 4);
+          const float4 ga = *reinterpret_cast<const float4*>(gamma + c * 8), gb = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+          const f32x2 bp[4] = {f2_pack(ba.x, ba.y), f2_pack(ba.z, ba.w), f2_pack(bb.x, bb.y), f2_pack(bb.z, bb.w)};
+          const f32x2 gp[4] = {f2_pack(ga.x, ga.y), f2_pack(ga.z, ga.w), f2_pack(gb.x, gb.y), f2_pack(gb.z, gb.w)};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float x = xh[c * 8 + q] + b2[c * 8 + q];
-            xh[c * 8 + q] = x;
-            const float dg = d[q] * gamma[c * 8 + q];
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-            s3 += dg;
-            s4 = fmaf(dg, x, s4);
+          for (int q = 0; q < 4; ++q) {
+            const f32x2 x = f2_add(f2_pack(xh[c * 8 + 2 * q], xh[c * 8 + 2 * q + 1]), bp[q]);
+            X2[c * 4 + q] = x;
+            const f32x2 dg = f2_mul(f2_pack(d[2 * q], d[2 * q + 1]), gp[q]);
+            s1p = f2_add(s1p, x);
+            s2p = f2_fma(x, x, s2p);
+            s3p = f2_add(s3p, dg);
+            s4p = f2_fma(dg, x, s4p);
           }
         }
+        const float s1 = f2_hsum(s1p), s2 = f2_hsum(s2p), s3 = f2_hsum(s3p), s4 = f2_hsum(s4p);
         S.ln_part[grp][hsel][row] = make_float4(s1, s2, s3, s4);
         asm volatile("bar.sync %0, 64;" : : "r"(pair_bar) : "memory");
         const float4 p0 = S.ln_part[grp][0][row], p1 = S.ln_part[grp][1][row];  // same order in both threads
@@ -538,16 +554,20 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         const float nmr = -mean * rstd;
         const float k1 = -(t3 * (1.0f / WB_HID)) * rstd;
         const float k2 = -(rstd * (t4 - mean * t3) * (1.0f / WB_HID)) * rstd;
+        const f32x2 rstd2 = f2_dup(rstd), nmr2 = f2_dup(nmr), k12 = f2_dup(k1), k22 = f2_dup(k2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float d[8], o[8];
           ws_unpack8(dyr[c], d);
+          const float4 ga = *reinterpret_cast<const float4*>(gamma + c * 8), gb = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+          const f32x2 gp[4] = {f2_pack(ga.x, ga.y), f2_pack(ga.z, ga.w), f2_pack(gb.x, gb.y), f2_pack(gb.z, gb.w)};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float xhat = fmaf(xh[c * 8 + q], rstd, nmr);
-            const float dg = d[q] * gamma[c * 8 + q];
-            o[q] = fmaf(xhat, k2, fmaf(dg, rstd, k1));
-            xh[c * 8 + q] = d[q] * xhat;  // dgamma contribution
+          for (int q = 0; q < 4; ++q) {
+            const f32x2 dp = f2_pack(d[2 * q], d[2 * q + 1]);
+            const f32x2 xhat = f2_fma(X2[c * 4 + q], rstd2, nmr2);
+            const f32x2 dg = f2_mul(dp, gp[q]);
+            f2_unpack(f2_fma(xhat, k22, f2_fma(dg, rstd2, k12)), o[2 * q], o[2 * q + 1]);
+            f2_unpack(f2_mul(dp, xhat), xh[c * 8 + 2 * q], xh[c * 8 + 2 * q + 1]);  // dgamma contribution
           }
           sts128(dhs + sw128_offset(row, hsel * 4 + c), ws_pack8(o));
         }

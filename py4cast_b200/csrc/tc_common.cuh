@@ -449,6 +449,46 @@ __device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
   return v[0];
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2) ------------------------------------------------
+// Two IEEE fp32 operations (round-to-nearest, the same results as two scalar instructions) per issued
+// instruction: the element-wise phases of the pipelined kernels are bound by instruction issue, not by the
+// fp32 pipe.  A pair lives in an aligned 64-bit register pair; packing / unpacking adjacent registers is free.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_dup(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float f2_hsum(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return lo + hi;
+}
+
 // ---- packed bf16x2 arithmetic (two elements per instruction) -----------------------------------------
 __device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
   uint32_t d;
