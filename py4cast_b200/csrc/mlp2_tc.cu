@@ -68,10 +68,14 @@ struct FwdArgs {
 };
 
 static long long* g_trace = nullptr;
+#ifdef P4C_PHASE_TRACE  // make EXTRA=-DP4C_PHASE_TRACE
 #define P4C_TRACE(i)                                   \
   do {                                                 \
     if (a.trace && blockIdx.x == 0 && tid == 0 && it == 0) a.trace[i] = clock64(); \
   } while (0)
+#else
+#define P4C_TRACE(i) do { (void)it; } while (0)
+#endif
 
 __device__ __forceinline__ void row_info(const FwdArgs& a, long long tile_row0, long long total_rows,
                                          FwdSmem& S, int p, int tid) {
@@ -119,9 +123,13 @@ __device__ __forceinline__ void issue_gather(const FwdArgs& a, FwdSmem& S, int p
     const uint32_t xs = smem_u32(S.X[k]);
     if (SEG && src.seg_rowptr) {
       // InteractionNet.aggregate fused into the prologue (fixed summation order)
+#ifdef P4C_PHASE_TRACE
+      long long* const seg_trace = (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace : nullptr;
+#else
+      long long* const seg_trace = nullptr;
+#endif
       seg_sum_tile<NT>(base, src.seg_perm, S.row_off[p][k], S.seg_hi[p], S.seg_base[p], S.seg_sc[p],
-                       S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid, a.tile_rows,
-                       (a.trace && blockIdx.x == 0 && tid == 0) ? a.trace : nullptr);
+                       S.orow[p], S.X[k], reinterpret_cast<__nv_bfloat16*>(src.seg_out), tid, a.tile_rows, seg_trace);
       continue;
     }
     const int nch = a.kb.nchunks[k];

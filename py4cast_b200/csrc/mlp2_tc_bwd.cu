@@ -93,11 +93,15 @@ struct BwdArgs {
   int ablate;        // developer aid (P4C_BWD_ABLATE, timing experiments only: results are WRONG when non-zero)
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's first tile, slots 16..31
 };
+#ifdef P4C_PHASE_TRACE  // make EXTRA=-DP4C_PHASE_TRACE
 #define P4C_BWD_TRACE(i)                                                             \
   do {                                                                               \
     if (args.trace && blockIdx.x == 0 && tid == 0 && (it == 0 || it == 2))           \
       args.trace[16 + (it ? 16 : 0) + (i)] = clock64();                              \
   } while (0)
+#else
+#define P4C_BWD_TRACE(i) do { (void)it; } while (0)
+#endif
 
 // Addressing of one tile row (thread tid < TM owns row tid): output row and, per K-block, the source
 // row.  The gather-index loads are issued here (bwd_row_addr) and their values are first touched

@@ -96,10 +96,17 @@ struct WbArgs {
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's tile 2, see scripts/trace_ws_bwd.py
 };
 // slots 0.. compute group 0 (warp 0), 16.. MMA lane (context 0), 32.. producer warp 0
+// Phase traces are compiled in only with -DP4C_PHASE_TRACE (make EXTRA=-DP4C_PHASE_TRACE; the trace_* / bwd_micro
+// scripts print zeros otherwise): the ~30 predicated clock reads per tile cost 1.5 % of the m2g edge backward.
+#ifdef P4C_PHASE_TRACE
 #define P4C_WB_TRACE(cond, i)                                   \
   do {                                                          \
     if (a.trace && blockIdx.x == 0 && (cond)) a.trace[i] = clock64(); \
   } while (0)
+#else
+#define P4C_WB_TRACE(cond, i) do { } while (0)
+#endif
+#define P4C_WB_KTRACE(i) P4C_WB_TRACE(tid == 0, i)  // kernel-level timeline (slots 48..), scripts/trace_ws_bwd_small.py
 
 __device__ __forceinline__ bool wb_mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -133,8 +140,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
   const int nslot = a.nslot;
-  P4C_WB_TRACE(tid == 0, 48);  // kernel-level timeline (slots 48..): entry, set-up done, first tile, last tile, partials, exit
+  P4C_WB_KTRACE(48);  // kernel-level timeline (slots 48..): entry, set-up done, first tile, last tile, partials, exit
+#ifdef P4C_PHASE_TRACE
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[56] = static_cast<long long>(wb_globaltimer());
+#endif
   // X ring depth: three stages when a stage is at most two K-blocks (the gather of tile t + 2 then runs while
   // tiles t, t + 1 compute), two otherwise (shared memory); dX scratch: one per context when a tile has a
   // single dX product, else one pair shared by the contexts (TMEM columns)
@@ -188,8 +197,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   const uint32_t tmem = S.tmem_base;
   const uint32_t ntl = a.ntiles > blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
   pdl_launch_dependents();
-  P4C_WB_TRACE(tid == 0, 49);
+  P4C_WB_KTRACE(49);
+#ifdef P4C_PHASE_TRACE
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[55] = ntl;
+#endif
 
   float vacc0 = 0.f, vacc1 = 0.f;  // compute warps: dgamma / dbeta column sums (column col0 + lane, rows of the warp)
 
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     __nv_bfloat16* const dh1_out = reinterpret_cast<__nv_bfloat16*>(g.dh1_out);
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     pdl_wait();
-    P4C_WB_TRACE(tid == 0, 50);
+    P4C_WB_KTRACE(50);
     for (uint32_t t = grp; t < ntl; t += 2) {
       const uint32_t par = (t >> 1) & 1u;
       const uint32_t tile = blockIdx.x + t * gridDim.x;
@@ -754,16 +765,18 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         if (lane == 0) mbar_arrive(&S.dxs_empty[dx_shared ? 0 : grp]);
       }
       P4C_WB_TRACE(trc, 10);
+#ifdef P4C_PHASE_TRACE
       P4C_WB_TRACE(tid == 0 && t < 12, 58 + (t >> 1));  // end of the group's tiles 0, 2, 4, ...
+#endif
     }
   }
 
   // ---- every tile of the CTA is done (each group waited for the commit that follows its last MMAs)
-  P4C_WB_TRACE(tid == 0, 51);
+  P4C_WB_KTRACE(51);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  P4C_WB_TRACE(tid == 0, 52);
+  P4C_WB_KTRACE(52);
 
   // per-CTA partials: weight and bias gradients from TMEM (layout of the classic engine)
   const int k1pad = (m.k1 + 31) / 32 * 32;
@@ -837,12 +850,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       *d = padd ? *d + (s0 + s1) : (s0 + s1);
     }
   }
-  P4C_WB_TRACE(tid == 0, 53);
+  P4C_WB_KTRACE(53);
   tc_fence_before();
   __syncthreads();
   if (warp == WB_MMA_WARP) tmem_dealloc(tmem, WB_TMEM_COLS);
-  P4C_WB_TRACE(tid == 0, 54);
+  P4C_WB_KTRACE(54);
+#ifdef P4C_PHASE_TRACE
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[57] = static_cast<long long>(wb_globaltimer());
+#endif
 }
 
 }  // namespace tc

@@ -1,4 +1,5 @@
-"""Backward of the m2g / g2m InteractionNets of the Titan-shaped HiLAM graph in isolation, classic
+"""[phase traces need a library built with `make -C py4cast_b200/csrc EXTRA=-DP4C_PHASE_TRACE`]
+Backward of the m2g / g2m InteractionNets of the Titan-shaped HiLAM graph in isolation, classic
 tensor-core engine against the pipelined recomputing one (CUDA events around the whole backward =
 node MLP + edge MLP + segment-sum passes), and the phase trace of the pipelined edge kernel
 (SM clocks of CTA 0, tile 2: compute group 0, MMA lane, producer warp 0)."""

@@ -1,4 +1,5 @@
-"""Phase timing (SM clocks) of the tensor-core BACKWARD kernel: CTA 0, thread 0, tiles 0 and 2 of
+"""[phase traces need a library built with `make -C py4cast_b200/csrc EXTRA=-DP4C_PHASE_TRACE`]
+Phase timing (SM clocks) of the tensor-core BACKWARD kernel: CTA 0, thread 0, tiles 0 and 2 of
 the LAST backward-kernel launch (the edge MLP of an InteractionNet, or a plain MLP)."""
 import os, sys
 import torch

@@ -1,4 +1,5 @@
-"""Phase timing (SM clocks) of ONE small forward kernel launch: where do ~15 us go?"""
+"""[phase traces need a library built with `make -C py4cast_b200/csrc EXTRA=-DP4C_PHASE_TRACE`]
+Phase timing (SM clocks) of ONE small forward kernel launch: where do ~15 us go?"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

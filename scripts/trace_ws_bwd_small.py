@@ -1,4 +1,5 @@
-"""Kernel-level timeline (SM clocks of CTA 0) of the pipelined backward on the MID-SIZE calls of the mesh
+"""[phase traces need a library built with `make -C py4cast_b200/csrc EXTRA=-DP4C_PHASE_TRACE`]
+Kernel-level timeline (SM clocks of CTA 0) of the pipelined backward on the MID-SIZE calls of the mesh
 levels (level-0 InteractionNet at the bench batch): where do the ~70 us of an 820-tile node MLP go?
 P4C_WB_TRACE_NBLK=2 traces the node MLP (last launch with two K-blocks), =3 the edge MLP."""
 import os
