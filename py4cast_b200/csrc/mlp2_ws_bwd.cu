@@ -104,7 +104,7 @@ struct WbArgs {
     if (a.trace && blockIdx.x == 0 && (cond)) a.trace[i] = clock64(); \
   } while (0)
 #else
-#define P4C_WB_TRACE(cond, i) do { } while (0)
+#define P4C_WB_TRACE(cond, i) do { (void)sizeof(cond); } while (0)
 #endif
 #define P4C_WB_KTRACE(i) P4C_WB_TRACE(tid == 0, i)  // kernel-level timeline (slots 48..), scripts/trace_ws_bwd_small.py
 
