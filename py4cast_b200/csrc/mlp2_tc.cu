@@ -509,7 +509,8 @@ bool tc_forward_supported(const p4c_mlp_t* m) {
 int launch_mlp2_tc_forward(const p4c_mlp_t* m, const void* residual, void* out, void* out2, void* save_h1,
                            float* save_stats, void* aggr_out, int agg_group, float agg_scale, cudaStream_t st) {
   using namespace tc;
-  if (ws_forward_supported(m, residual, out2, aggr_out, agg_group))
+  if (ws_forward_supported(m, residual, out2, aggr_out, agg_group) &&
+      (m->out_features == P4C_HIDDEN || (out && reinterpret_cast<uintptr_t>(out) % 16 == 0)))
     return launch_mlp2_ws_forward(m, residual, out, out2, save_h1, save_stats, aggr_out, agg_group, agg_scale, st);
   FwdArgs a;
   a.m = *m;

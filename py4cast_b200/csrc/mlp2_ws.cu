@@ -72,6 +72,7 @@ struct WsArgs {
   int agg_group;
   float agg_scale;
   int residual_x0;  // out = y + (row of K-block 0)
+  int out_width;    // 64, or the width of a narrow output without LayerNorm (output map: 64 -> 64 -> 21)
   int zero_x;
   // Tile order: tile T = (row block T / batch, sample T % batch), i.e. the samples of one row block are
   // processed back to back (by neighbouring CTAs at the same time), so that a source shared by the
@@ -382,6 +383,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         if (a.save_stats && orow >= 0 && hsel == 0)
           *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
       }
+      if (a.out_width != WS_HID) {
+        // Narrow output (no LayerNorm; columns >= out_width of y are zero): rows are out_width * 2 bytes and a
+        // tile's rows are contiguous in `out`.  Compact [row][out_width] bf16 image of the row quad in the (free)
+        // A2 tile, then the 64 threads that own the quad copy its bytes with 16-byte stores.
+        const int OW = a.out_width;
+        uint8_t* const ct = S.A2[grp];
+        __nv_bfloat16* const crow = reinterpret_cast<__nv_bfloat16*>(ct) + row * OW + col0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (col0 + c < OW) crow[c] = __float2bfloat16_rn(y[c]);
+        asm volatile("bar.sync %0, 64;" : : "r"(pair_bar) : "memory");
+        const uint32_t q0 = blk * WS_TM + static_cast<uint32_t>(quad * 32);  // first row of the quad
+        const int nv = q0 < rows ? static_cast<int>(rows - q0 < 32u ? rows - q0 : 32u) : 0;
+        const int nbytes = nv * OW * 2;
+        const uint8_t* const src = ct + quad * 32 * OW * 2;
+        uint8_t* const dst = reinterpret_cast<uint8_t*>(out) +
+                             (static_cast<long long>(tile - blk * nbatch) * full + q0) * OW * 2;
+        for (int i = (hsel * 32 + lane) * 16; i < nbytes; i += 64 * 16) {
+          if (i + 16 <= nbytes) {
+            *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+          } else {
+            for (int b = i; b < nbytes; b += 2)
+              *reinterpret_cast<uint16_t*>(dst + b) = *reinterpret_cast<const uint16_t*>(src + b);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" : : "r"(pair_bar) : "memory");  // the A2 tile is rewritten by the next tile
+        continue;
+      }
       // ---- outputs staged through the A2 tile (free: G2 of this tile is complete)
       if (out2) {  // edge update: src0 row + y
 #pragma unroll
@@ -501,7 +530,13 @@ static long long ws_min_tiles() {
 // The warp-specialised kernel covers the large calls; everything else stays on mlp2_tc_fwd_kernel.
 bool ws_forward_supported(const p4c_mlp_t* m, const void* residual, const void* out2, const void* aggr_out,
                           int agg_group) {
-  if (!m->packed || m->out_features != P4C_HIDDEN) return false;
+  if (!m->packed) return false;
+  if (m->out_features != P4C_HIDDEN) {
+    // narrow output: no LayerNorm, plain store, 16-byte aligned row quads in every sample
+    const long long fr = m->full_rows > 0 ? m->full_rows : m->rows;
+    if (m->layer_norm || residual || out2 || aggr_out || m->out_features < 1 || m->out_features > P4C_HIDDEN) return false;
+    if (m->batch > 1 && (fr * m->out_features * 2) % 16 != 0) return false;
+  }
   if (m->tile_rows != 0 && m->tile_rows != 128) return false;
   for (int s = 0; s < m->nsrc; ++s)
     if (m->src[s].seg_rowptr) return false;
@@ -532,6 +567,7 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   a.agg_group = aggr_out ? agg_group : 1;
   a.agg_scale = agg_scale;
   a.residual_x0 = residual != nullptr;
+  a.out_width = m->out_features;
   a.tma_mask = 0;
   for (int k = 0; k < a.kb.nblk; ++k) {
     const p4c_src_t& src = m->src[a.kb.src[k]];

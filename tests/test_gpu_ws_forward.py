@@ -82,6 +82,36 @@ def test_dense_mlp_matches_monolithic_kernel_and_oracle(lib, cuda, k1, rows, bat
     assert_close(wsr, mono, 4e-3, "pipelined vs monolithic")
 
 
+@pytest.mark.parametrize("rows,batch,out", [(640, 2, 21), (1000, 1, 21), (333, 1, 5), (256, 3, 40)])
+def test_narrow_output_without_layernorm(lib, cuda, rows, batch, out):
+    """Output map (64 -> 64 -> out < 64, no LayerNorm) on the pipelined kernel: compact rows staged in shared
+    memory and stored with 16-byte chunks; partial last tile, several samples, odd widths."""
+    from oracle.graph_ref import make_mlp
+    from py4cast_b200 import ops
+
+    torch.manual_seed(rows + out)
+    ref = make_mlp([64, 64, out], layer_norm=False)
+    ws = _weights(ref, False, cuda)
+    meta = ops.MlpMeta(ws, (64,), out)
+    ops.WeightPacker([meta]).pack()
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(batch, rows, 64, generator=g).bfloat16().float()
+    xg = x.to(cuda).bfloat16()
+
+    def run():
+        with torch.no_grad():
+            return ops.fused_mlp(xg, ws, meta=meta).float().cpu()
+
+    if batch > 1 and (rows * out * 2) % 16 != 0:
+        pytest.skip("sample stride not 16-byte aligned: stays on the monolithic kernel")
+    mono, wsr = _both(lib, run)
+    with torch.no_grad():
+        yr = ref(x)
+    assert wsr.shape == (batch, rows, out)
+    assert_close(wsr, yr, BF16_TOL, "pipelined vs oracle")
+    assert torch.equal(wsr, mono), "same arithmetic, same rounding as the monolithic kernel"
+
+
 def _uniform_graph(nr, ns, deg, seed):
     g = torch.Generator().manual_seed(seed)
     rec = torch.arange(nr).repeat_interleave(deg)
