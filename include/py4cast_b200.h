@@ -360,14 +360,18 @@ int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev_last,
 /* Backward of p4c_ar_step_forward, for the autograd node
  *     (y, prev[0..T_in-1]) -> (new_state, x_next).
  *   g_new   : gradient w.r.t. new_state from its other consumers ([batch][nodes][F], may be NULL)
+ *   g_new2  : a second addend of the same gradient (NULL or [batch][nodes][F]): the input gradient the NEXT
+ *             step's backward produced for this state, summed here instead of by a separate element-wise
+ *             pass (torch autograd's accumulation of the two gradients of a state that feeds both the loss and
+ *             the next step, reference lightning.py:598-662)
  *   g_xnext : gradient w.r.t. x_next ([batch][nodes][f_in] of x_dtype, may be NULL)
- *   G = g_new + g_xnext[slot T_in-1];  dy = G*interior*(std);
+ *   G = (g_new + g_new2) + g_xnext[slot T_in-1];  dy = G*interior*(std);
  *   d_prev[T_in-1] = G*interior + g_xnext[slot T_in-2]   (prev_last is also copied into x_next)
  *   d_prev[t]      = g_xnext[slot t-1]   for 1 <= t <= T_in-2;   d_prev[0] unused (T_in >= 2).
  *   d_prev: HOST array of T_in device pointers (NULL entries are skipped); all outputs are
  *   written, not accumulated. */
-int p4c_ar_step_backward(const float* g_new, int64_t g_new_batch_stride, const void* g_xnext,
-                         int x_dtype, const float* border, const float* diff_std,
+int p4c_ar_step_backward(const float* g_new, int64_t g_new_batch_stride, const float* g_new2,
+                         int64_t g_new2_batch_stride, const void* g_xnext, int x_dtype, const float* border, const float* diff_std,
                          int32_t batch, int32_t nodes, int32_t f_state, int32_t num_prev,
                          int32_t f_in /* row stride of g_xnext */, void* dy, int y_dtype,
                          float* const* d_prev, void* stream);

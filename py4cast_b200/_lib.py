@@ -193,7 +193,7 @@ SYMBOLS = {
     ),
     "p4c_ar_step_backward": (
         _int,
-        [_vp, _i64, _vp, _int, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _int,
+        [_vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _int,
          C.POINTER(C.c_void_p), _vp],
     ),
     "p4c_loss_denominator": (_int, [_vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp]),

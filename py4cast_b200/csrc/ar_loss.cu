@@ -221,6 +221,8 @@ ar_tile_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x, int has_u
 struct ArBwd {
   const float* g_new;
   long long g_new_bs;
+  const float* g_new2;
+  long long g_new2_bs;
   const void* g_x;
   const float* border;
   const float* std_;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(256) ar_step_bwd_kernel(const ArBwd s) {
     const int n = (int)(rem / s.F), f = (int)(rem - (long long)n * s.F);
     const long long xrow = ((long long)b * s.nodes + n) * s.f_in;
     float G = s.g_new ? s.g_new[(long long)b * s.g_new_bs + rem] : 0.f;
+    if (s.g_new2) G += s.g_new2[(long long)b * s.g_new2_bs + rem];
     if (gx) G += to_f32<TX>(gx[xrow + (long long)(T - 1) * s.F + f]);
     const float interior = s.border ? 1.0f - s.border[n] : 1.0f;
     const float gi = G * interior;
@@ -702,18 +705,18 @@ extern "C" int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev
   return P4C_OK;
 }
 
-extern "C" int p4c_ar_step_backward(const float* g_new, int64_t g_new_bs, const void* g_xnext,
-                                    int x_dtype, const float* border, const float* diff_std,
+extern "C" int p4c_ar_step_backward(const float* g_new, int64_t g_new_bs, const float* g_new2, int64_t g_new2_bs,
+                                    const void* g_xnext, int x_dtype, const float* border, const float* diff_std,
                                     int32_t batch, int32_t nodes, int32_t f_state,
                                     int32_t num_prev, int32_t f_in, void* dy, int y_dtype,
                                     float* const* d_prev, void* stream) {
   P4C_REQUIRE(dy != nullptr, "ar_step_backward: dy is null");
-  P4C_REQUIRE(g_new || g_xnext, "ar_step_backward: no incoming gradient");
+  P4C_REQUIRE(g_new || g_new2 || g_xnext, "ar_step_backward: no incoming gradient");
   P4C_REQUIRE(batch > 0 && nodes > 0 && f_state > 0, "ar_step_backward: empty problem");
   P4C_REQUIRE(num_prev >= 1 && num_prev <= P4C_MAX_PREV, "ar_step_backward: bad num_prev %d", num_prev);
   P4C_REQUIRE(!g_xnext || f_in >= num_prev * f_state, "ar_step_backward: f_in too small");
   ArBwd s{};
-  s.g_new = g_new; s.g_new_bs = g_new_bs; s.g_x = g_xnext; s.border = border; s.std_ = diff_std;
+  s.g_new = g_new; s.g_new_bs = g_new_bs; s.g_new2 = g_new2; s.g_new2_bs = g_new2_bs; s.g_x = g_xnext; s.border = border; s.std_ = diff_std;
   s.batch = batch; s.nodes = nodes; s.F = f_state; s.num_prev = num_prev; s.f_in = f_in; s.dy = dy;
   for (int t = 0; t < P4C_MAX_PREV; ++t) s.d_prev[t] = (d_prev && t < num_prev) ? d_prev[t] : nullptr;
   const long long total = (long long)batch * nodes * f_state;

@@ -137,6 +137,8 @@ class _ARStepFn(torch.autograd.Function):
             "p4c_ar_step_forward",
         )
         ctx.border, ctx.std = border, std
+        # gradient hand-over between consecutive steps of a slab rollout (see backward)
+        ctx.holder, ctx.slot, ctx.prev_last_slot = cfg.get("holder"), cfg.get("slot"), cfg.get("prev_last_slot")
         ctx.dims = (B, N, F, len(prevs))
         ctx.y_dtype = y.dtype
         ctx.has_next = has_next
@@ -149,6 +151,15 @@ class _ARStepFn(torch.autograd.Function):
         lib = _lib.load()
         B, N, F, T = ctx.dims
         dev = ctx.border.device if ctx.border is not None else (g_new if g_new is not None else g_x).device
+        # The state this step produced feeds the loss (through the slab) AND the next step.  Instead of letting
+        # autograd add the two gradients with an element-wise pass (a strided slab view + a dense tensor), the
+        # next step's backward parks its input gradient in the rollout's holder and this kernel adds it.
+        holder = ctx.holder
+        g_new2 = None
+        if holder is not None and ctx.slot is not None:
+            g_new2 = holder["carry"].pop(ctx.slot, None)
+        if g_new is None and g_new2 is not None:
+            g_new, g_new2 = g_new2, None
         if g_new is None and g_x is None:
             return (None,) * (2 + T)
         if g_new is not None:
@@ -174,13 +185,20 @@ class _ARStepFn(torch.autograd.Function):
                 arr[t] = ptr(d_prev[t])
         check(
             lib.p4c_ar_step_backward(
-                ptr(g_new), _bstride(g_new) if g_new is not None else 0, ptr(g_x),
+                ptr(g_new), _bstride(g_new) if g_new is not None else 0,
+                ptr(g_new2), _bstride(g_new2) if g_new2 is not None else 0, ptr(g_x),
                 dtype_code(g_x.dtype) if g_x is not None else 0, ptr(ctx.border), ptr(ctx.std),
                 B, N, F, T, x_ld, ptr(dy), dtype_code(ctx.y_dtype),
                 arr, stream(),
             ),
             "p4c_ar_step_backward",
         )
+        if (holder is not None and holder["slab_seen"] and ctx.prev_last_slot is not None
+                and d_prev[T - 1] is not None):
+            # prev_last is a slab state whose own backward has not run yet (it precedes this step) and will run
+            # (the slab gradient reaches it): it picks this tensor up as g_new2
+            holder["carry"][ctx.prev_last_slot] = d_prev[T - 1]
+            d_prev[T - 1] = None
         return (None, dy, *d_prev)
 
 
@@ -189,13 +207,16 @@ class _SlabFn(torch.autograd.Function):
     (replaces torch.stack, reference lightning.py:660-662) without copying."""
 
     @staticmethod
-    def forward(ctx, slab, *states):
+    def forward(ctx, slab, holder, *states):
         ctx.T = len(states)
+        ctx.holder = holder
         return slab.view(slab.shape)
 
     @staticmethod
     def backward(ctx, g):
-        return (None, *[g[:, i] for i in range(ctx.T)])
+        if ctx.holder is not None:
+            ctx.holder["slab_seen"] = True  # every state receives a gradient: the steps may hand theirs over
+        return (None, None, *[g[:, i] for i in range(ctx.T)])
 
 
 class AutoRegressiveLightning(nn.Module):
@@ -429,6 +450,8 @@ class AutoRegressiveLightning(nn.Module):
             prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
             x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
             states = []
+            holder = {"slab_seen": False, "carry": {}}
+            prev_last_slot = None  # slab slot of prevs[-1] when it is a state of this rollout
             for i in range(T):
                 for k in range(num_inter_steps):
                     y = self._run_model(x, spatial)
@@ -442,6 +465,7 @@ class AutoRegressiveLightning(nn.Module):
                         "border": border, "std": std, "mean": mean,
                         "new_state": slab[:, i] if last_k else torch.empty(B, N, F, dtype=torch.float32, device=dev),
                         "static": self._static_flat, "forcing_next": next_forcing, "x_dtype": x_dtype,
+                        "holder": holder, "slot": i if last_k else None, "prev_last_slot": prev_last_slot,
                     }
                     res = _ARStepFn.apply(cfg, y, *prevs)
                     if more:
@@ -449,13 +473,14 @@ class AutoRegressiveLightning(nn.Module):
                         prevs = prevs[1:] + [new_state]
                     else:
                         new_state = res
+                    prev_last_slot = i if last_k else None
                 states.append(new_state)
         finally:
             # always paired: an exception inside the rollout must not leave stale embeddings /
             # weight images behind for the next one
             if hasattr(self.model, "end_rollout"):
                 self.model.end_rollout()
-        prediction = _SlabFn.apply(slab, *states).view(B, T, *spatial, F)
+        prediction = _SlabFn.apply(slab, holder, *states).view(B, T, *spatial, F)
 
         if inference:
             pred_out = NamedTensor(prediction.type(self.output_dtype), self.output_dim_names, self.output_feature_names)
