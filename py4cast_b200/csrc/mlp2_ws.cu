@@ -86,6 +86,10 @@ struct WsArgs {
   alignas(64) CUtensorMap tmap[P4C_MAX_SRC];
 };
 
+// NARROW: output narrower than 64 columns, no LayerNorm (its store path is kept out of the main instantiation:
+// the epilogue warps are sensitive to every instruction in their tile loop, executed or not)
+// AGGR_ONLY: the m2g edge call (LayerNorm, aggregation in the epilogue, nothing else stored or saved).
+template <bool NARROW, bool AGGR_ONLY = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid_constant__ WsArgs a) {
   extern __shared__ unsigned char smem_raw[];
   WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
   const int nblk = a.kb.nblk;
   const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
-  const bool need_x0 = a.residual_x0 || a.out2 != nullptr;
+  const bool need_x0 = !AGGR_ONLY && (a.residual_x0 || a.out2 != nullptr);
 
   // ---- set-up: weight image, barriers, TMEM
   if (a.zero_x) {
@@ -271,9 +275,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     const uint32_t tm_d1 = tmem + (static_cast<uint32_t>(quad * 32) << 16) + grp * WS_HID + col0;
     const uint32_t tm_d2 = tm_d1 + 2 * WS_HID;
     const int pair_bar = 1 + grp * 4 + quad;  // named barrier of the two warps that share these rows
-    __nv_bfloat16* const save_h1 = a.save_h1;
-    __nv_bfloat16* const out = a.out;
-    __nv_bfloat16* const out2 = a.out2;
+    __nv_bfloat16* const save_h1 = AGGR_ONLY ? nullptr : a.save_h1;
+    __nv_bfloat16* const out = AGGR_ONLY ? nullptr : a.out;
+    __nv_bfloat16* const out2 = AGGR_ONLY ? nullptr : a.out2;
     const float* const b1 = S.vec[0] + col0;
     const float* const b2 = S.vec[1] + col0;
     const float* const gamma = S.vec[2] + col0;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const float4 bv = *reinterpret_cast<const float4*>(b2 + c * 4);
         y[c * 4 + 0] += bv.x; y[c * 4 + 1] += bv.y; y[c * 4 + 2] += bv.z; y[c * 4 + 3] += bv.w;
       }
-      if (m.layer_norm) {
+      if (!NARROW && (AGGR_ONLY || m.layer_norm)) {
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -380,10 +384,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           y[c * 4 + 2] = fmaf(fmaf(y[c * 4 + 2], rstd, nm), gv.z, bv.z);
           y[c * 4 + 3] = fmaf(fmaf(y[c * 4 + 3], rstd, nm), gv.w, bv.w);
         }
-        if (a.save_stats && orow >= 0 && hsel == 0)
+        if (!AGGR_ONLY && a.save_stats && orow >= 0 && hsel == 0)
           *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
       }
-      if (a.out_width != WS_HID) {
+      if constexpr (NARROW) {
         // Narrow output (no LayerNorm; columns >= out_width of y are zero): rows are out_width * 2 bytes and a
         // tile's rows are contiguous in `out`.  Compact [row][out_width] bf16 image of the row quad in the (free)
         // A2 tile, then the 64 threads that own the quad copy its bytes with 16-byte stores.
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         }
         __syncwarp();
       }
-      if (a.aggr_out) {
+      if (AGGR_ONLY || a.aggr_out) {
         // sum of the messages of `agg_group` consecutive rows (= lanes): transposing butterfly, at
         // every step a lane hands one half of its columns to its partner and adds the partner's
         // other half (fp32, fixed order; invalid rows add zero)
@@ -588,16 +592,24 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   if (max_ctas < 1) max_ctas = 1;
   const int grid = static_cast<int>(a.ntiles < static_cast<uint32_t>(max_ctas) ? a.ntiles : max_ctas);
   const size_t smem = sizeof(WsSmem) + 1024;
+  const bool narrow = m->out_features != P4C_HIDDEN;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mlp_forward(ws): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return P4C_ECUDA;
     }
     configured = true;
   }
-  launch_pdl(mlp2_ws_fwd_kernel, dim3(grid), dim3(WS_THREADS), smem, st, a);
+  const bool aggr_only = !narrow && aggr_out && !out && !out2 && !save_h1 && !save_stats && !residual && m->layer_norm;
+  if (narrow) launch_pdl(mlp2_ws_fwd_kernel<true>, dim3(grid), dim3(WS_THREADS), smem, st, a);
+  else if (aggr_only) launch_pdl(mlp2_ws_fwd_kernel<false, true>, dim3(grid), dim3(WS_THREADS), smem, st, a);
+  else launch_pdl(mlp2_ws_fwd_kernel<false>, dim3(grid), dim3(WS_THREADS), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_forward(ws)");
   ++g_ws_launches;
   return P4C_OK;
