@@ -89,7 +89,8 @@ struct WsArgs {
 // NARROW: output narrower than 64 columns, no LayerNorm (its store path is kept out of the main instantiation:
 // the epilogue warps are sensitive to every instruction in their tile loop, executed or not)
 // AGGR_ONLY: the m2g edge call (LayerNorm, aggregation in the epilogue, nothing else stored or saved).
-template <bool NARROW, bool AGGR_ONLY = false>
+// NO_SAVE: h1 is not saved (calls whose backward recomputes it): epilogue 1 runs in one pass.
+template <bool NARROW, bool AGGR_ONLY = false, bool NO_SAVE = AGGR_ONLY>
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid_constant__ WsArgs a) {
   extern __shared__ unsigned char smem_raw[];
   WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -302,11 +303,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.x_empty[s]);
       }
-      // ---- epilogue 1, pass 1: h1 = D1 + b1 -> bf16 -> A2 (own row, own column half)
-      {
+      if constexpr (NO_SAVE) {
+        // ---- epilogue 1 in one pass (h1 is not saved: the backward of this call recomputes it): a1 = SiLU of the
+        //      bf16-rounded h1 (what a saving call would have stored) -> A2 operand of G2, own row / column half
         float v[32];
         tmem_ld32(tm_d1, v);
         tmem_ld_wait();
+        tc_fence_before();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
@@ -314,36 +317,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           float h[8];
           h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
           h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
+          const uint4 hb = ws_pack8(h);
+          ws_unpack8(hb, h);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
           sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      // ---- pass 2 (lane -> chunk j of row 8 i + sub of this warp): SiLU in place -> A2 operand of G2,
-      //      hand the tile to the MMA warp, THEN the coalesced store of h1 (saved activation): the
-      //      proxy fence (MEMBAR.ALL.CTA in SASS) would otherwise wait for the stores' acknowledgement
-      //      on the critical path to G2
-      uint4 hb[4];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a2_full[grp]);
+      } else {
+      // ---- epilogue 1, pass 1: h1 = D1 + b1 -> bf16 -> A2 (own row, own column half)
+        {
+          float v[32];
+          tmem_ld32(tm_d1, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = 8 * i + sub;
-        const uint32_t addr = a2 + sw128_offset(quad * 32 + r, j);
-        hb[i] = lds128(addr);
-        float h[8];
-        ws_unpack8(hb[i], h);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
-        sts128(addr, ws_pack8(h));
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.a2_full[grp]);
-      if (save_h1) {
+          for (int c = 0; c < 4; ++c) {
+            const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
+            float h[8];
+            h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
+            h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
+            sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        // ---- pass 2 (lane -> chunk j of row 8 i + sub of this warp): SiLU in place -> A2 operand of G2,
+        //      hand the tile to the MMA warp, THEN the coalesced store of h1 (saved activation): the
+        //      proxy fence (MEMBAR.ALL.CTA in SASS) would otherwise wait for the stores' acknowledgement
+        //      on the critical path to G2
+        uint4 hb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int32_t orr = __shfl_sync(0xffffffffu, orow, 8 * i + sub);
-          if (orr >= 0) *reinterpret_cast<uint4*>(save_h1 + static_cast<long long>(orr) * WS_HID + j * 8) = hb[i];
+          const int r = 8 * i + sub;
+          const uint32_t addr = a2 + sw128_offset(quad * 32 + r, j);
+          hb[i] = lds128(addr);
+          float h[8];
+          ws_unpack8(hb[i], h);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+          sts128(addr, ws_pack8(h));
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a2_full[grp]);
+        if (save_h1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int32_t orr = __shfl_sync(0xffffffffu, orow, 8 * i + sub);
+            if (orr >= 0) *reinterpret_cast<uint4*>(save_h1 + static_cast<long long>(orr) * WS_HID + j * 8) = hb[i];
+          }
+        }
+
       }
 
       // ---- epilogue 2
@@ -600,6 +627,8 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
       e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp2_ws_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mlp_forward(ws): cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return P4C_ECUDA;
@@ -609,6 +638,7 @@ int launch_mlp2_ws_forward(const p4c_mlp_t* m, const void* residual, void* out, 
   const bool aggr_only = !narrow && aggr_out && !out && !out2 && !save_h1 && !save_stats && !residual && m->layer_norm;
   if (narrow) launch_pdl(mlp2_ws_fwd_kernel<true>, dim3(grid), dim3(WS_THREADS), smem, st, a);
   else if (aggr_only) launch_pdl(mlp2_ws_fwd_kernel<false, true>, dim3(grid), dim3(WS_THREADS), smem, st, a);
+  else if (!save_h1) launch_pdl(mlp2_ws_fwd_kernel<false, false, true>, dim3(grid), dim3(WS_THREADS), smem, st, a);
   else launch_pdl(mlp2_ws_fwd_kernel<false>, dim3(grid), dim3(WS_THREADS), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_forward(ws)");
   ++g_ws_launches;
