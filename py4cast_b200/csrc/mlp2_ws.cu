@@ -315,12 +315,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
           const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           float h[8];
-          h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
-          h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 0], v[c * 8 + 1]), f2_pack(ba.x, ba.y)), h[0], h[1]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 2], v[c * 8 + 3]), f2_pack(ba.z, ba.w)), h[2], h[3]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 4], v[c * 8 + 5]), f2_pack(bb.x, bb.y)), h[4], h[5]);
+          f2_unpack(f2_add(f2_pack(v[c * 8 + 6], v[c * 8 + 7]), f2_pack(bb.z, bb.w)), h[6], h[7]);
           const uint4 hb = ws_pack8(h);
           ws_unpack8(hb, h);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+          silu8_pairs(h);
           sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
         }
         fence_proxy_async();
@@ -356,8 +357,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           hb[i] = lds128(addr);
           float h[8];
           ws_unpack8(hb[i], h);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) h[q] = fast_silu(h[q]);
+          silu8_pairs(h);
           sts128(addr, ws_pack8(h));
         }
         fence_proxy_async();
@@ -382,18 +382,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.d2_empty[grp]);  // D2 is in registers: G2 of tile t + 2 may overwrite it
+      // fp32 pairs (FADD2 / FFMA2): two columns per instruction
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 bv = *reinterpret_cast<const float4*>(b2 + c * 4);
-        y[c * 4 + 0] += bv.x; y[c * 4 + 1] += bv.y; y[c * 4 + 2] += bv.z; y[c * 4 + 3] += bv.w;
+        f2_unpack(f2_add(f2_pack(y[c * 4 + 0], y[c * 4 + 1]), f2_pack(bv.x, bv.y)), y[c * 4 + 0], y[c * 4 + 1]);
+        f2_unpack(f2_add(f2_pack(y[c * 4 + 2], y[c * 4 + 3]), f2_pack(bv.z, bv.w)), y[c * 4 + 2], y[c * 4 + 3]);
       }
       if (!NARROW && (AGGR_ONLY || m.layer_norm)) {
-        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+        f32x2 ps2[2] = {0ull, 0ull}, pq2[2] = {0ull, 0ull};  // (ps[0], ps[1]), (ps[2], ps[3]) of the scalar form
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          ps[q & 3] += y[q];
-          pq[q & 3] = fmaf(y[q], y[q], pq[q & 3]);
+        for (int q = 0; q < 32; q += 4) {
+          const f32x2 a01 = f2_pack(y[q], y[q + 1]), a23 = f2_pack(y[q + 2], y[q + 3]);
+          ps2[0] = f2_add(ps2[0], a01);
+          ps2[1] = f2_add(ps2[1], a23);
+          pq2[0] = f2_fma(a01, a01, pq2[0]);
+          pq2[1] = f2_fma(a23, a23, pq2[1]);
         }
+        float ps[4], pq[4];
+        f2_unpack(ps2[0], ps[0], ps[1]);
+        f2_unpack(ps2[1], ps[2], ps[3]);
+        f2_unpack(pq2[0], pq[0], pq[1]);
+        f2_unpack(pq2[1], pq[2], pq[3]);
         S.ln_part[grp][hsel][row] = make_float2((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]));
         asm volatile("bar.sync %0, 64;" : : "r"(pair_bar) : "memory");
         const float2 p0 = S.ln_part[grp][0][row], p1 = S.ln_part[grp][1][row];  // same order in both threads
@@ -402,14 +412,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const float var = fmaxf(sq * (1.0f / WS_HID) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + m.ln_eps);
         const float nm = -mean * rstd;
+        const f32x2 rstd2 = f2_dup(rstd), nm2 = f2_dup(nm);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 gv = *reinterpret_cast<const float4*>(gamma + c * 4);
           const float4 bv = *reinterpret_cast<const float4*>(beta + c * 4);
-          y[c * 4 + 0] = fmaf(fmaf(y[c * 4 + 0], rstd, nm), gv.x, bv.x);
-          y[c * 4 + 1] = fmaf(fmaf(y[c * 4 + 1], rstd, nm), gv.y, bv.y);
-          y[c * 4 + 2] = fmaf(fmaf(y[c * 4 + 2], rstd, nm), gv.z, bv.z);
-          y[c * 4 + 3] = fmaf(fmaf(y[c * 4 + 3], rstd, nm), gv.w, bv.w);
+          f2_unpack(f2_fma(f2_fma(f2_pack(y[c * 4 + 0], y[c * 4 + 1]), rstd2, nm2), f2_pack(gv.x, gv.y), f2_pack(bv.x, bv.y)),
+                    y[c * 4 + 0], y[c * 4 + 1]);
+          f2_unpack(f2_fma(f2_fma(f2_pack(y[c * 4 + 2], y[c * 4 + 3]), rstd2, nm2), f2_pack(gv.z, gv.w), f2_pack(bv.z, bv.w)),
+                    y[c * 4 + 2], y[c * 4 + 3]);
         }
         if (!AGGR_ONLY && a.save_stats && orow >= 0 && hsel == 0)
           *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
@@ -449,7 +460,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           float e[8];
           ws_unpack8(res[c], e);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) e[q] += y[c * 8 + q];
+          for (int q = 0; q < 8; q += 2)
+            f2_unpack(f2_add(f2_pack(e[q], e[q + 1]), f2_pack(y[c * 8 + q], y[c * 8 + q + 1])), e[q], e[q + 1]);
           sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(e));
         }
         __syncwarp();
@@ -469,7 +481,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           if (a.residual_x0) {
             ws_unpack8(res[c], e);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) e[q] += y[c * 8 + q];
+            for (int q = 0; q < 8; q += 2)
+              f2_unpack(f2_add(f2_pack(e[q], e[q + 1]), f2_pack(y[c * 8 + q], y[c * 8 + q + 1])), e[q], e[q + 1]);
           } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) e[q] = y[c * 8 + q];

@@ -489,6 +489,21 @@ __device__ __forceinline__ float f2_hsum(f32x2 v) {
   return lo + hi;
 }
 
+// SiLU of eight values in place, two per instruction: the operations of fast_silu (0.5 x, tanh, fma, x s), so
+// the results are bit-identical to the scalar form
+__device__ __forceinline__ void silu8_pairs(float* h) {
+  const f32x2 half2 = f2_dup(0.5f);
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    const f32x2 hp = f2_pack(h[q], h[q + 1]);
+    float t0, t1;
+    f2_unpack(f2_mul(half2, hp), t0, t1);
+    asm("tanh.approx.f32 %0, %0;" : "+f"(t0));
+    asm("tanh.approx.f32 %0, %0;" : "+f"(t1));
+    f2_unpack(f2_mul(hp, f2_fma(half2, f2_pack(t0, t1), half2)), h[q], h[q + 1]);
+  }
+}
+
 // ---- packed bf16x2 arithmetic (two elements per instruction) -----------------------------------------
 __device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
   uint32_t d;
