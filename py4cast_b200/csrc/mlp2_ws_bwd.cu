@@ -41,6 +41,10 @@
 #include "tc_common.cuh"
 #include "tma.cuh"
 
+#ifndef P4C_WB_ABLATE
+#define P4C_WB_ABLATE 0  // developer aid (scripts/ablate_ws_bwd.sh): 1 no column sums, 2 no dh1 store, 4 no dX epilogue
+#endif
+
 namespace p4c {
 namespace tc {
 
@@ -587,10 +591,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         if (lane == 0) mbar_arrive(&S.dh2_full[grp]);
         P4C_WB_TRACE(trc, 4);
         // column sums over the rows of the warp while the tensor core runs G2 / G3
+#if !(P4C_WB_ABLATE & 1)
         vacc0 += warp_colsum<32>(xh, lane);
 #pragma unroll
         for (int c = 0; c < 4; ++c) ws_unpack8(dyr[c], xh + c * 8);
         vacc1 += warp_colsum<32>(xh, lane);
+#else
+        vacc0 += xh[lane & 31];
+#endif
         P4C_WB_TRACE(trc, 5);
       }
 
@@ -618,7 +626,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.dh1_full[grp]);
       P4C_WB_TRACE(trc, 7);
-      if (dh1_out) {  // coalesced: lane -> 16-byte chunk j of row 8 i + sub of this warp's rows
+      if (dh1_out && !(P4C_WB_ABLATE & 2)) {  // coalesced: lane -> 16-byte chunk j of row 8 i + sub of this warp's rows
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + sub;
@@ -632,20 +640,28 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       // while G4 / G5 run (the read-modify-write below would otherwise expose the load latency)
       const int gsz = g.dx_group;
       int cbase = 0;
+      uint4 grp_old = zero4;
       if (g.dx_group_out) {
         if (gsz > 1 && (lane & 1)) cbase += 16;
         if (gsz > 2 && (lane & 2)) cbase += 8;
         if (gsz > 4 && (lane & 4)) cbase += 4;
-        if (valid)
-          asm volatile("prefetch.global.L1 [%0];" : : "l"(reinterpret_cast<__nv_bfloat16*>(g.dx_group_out) +
-                                                         static_cast<long long>(orow / gsz) * WB_HID + col0 + cbase));
+        if (valid) {
+          const __nv_bfloat16* old = reinterpret_cast<const __nv_bfloat16*>(g.dx_group_out) +
+                                     static_cast<long long>(orow / gsz) * WB_HID + col0 + cbase;
+          // groups of 4 / 8 rows: the lane's slice is one 16 / 8-byte word -- LOADED now (it is only this thread's
+          // to update), so that the read-modify-write after the MMAs does not wait for it; wider slices are
+          // pulled into L1
+          if (gsz == 4) grp_old = *reinterpret_cast<const uint4*>(old);
+          else if (gsz == 8) *reinterpret_cast<uint2*>(&grp_old) = *reinterpret_cast<const uint2*>(old);
+          else asm volatile("prefetch.global.L1 [%0];" : : "l"(old));
+        }
       }
       // ---- g. dX epilogues (G4 / G5 complete: the DH and X tiles of the context are free afterwards)
       P4C_WB_TRACE(trc, 8);
       mbar_wait_suspend(&S.dx_full[grp], par);
       P4C_WB_TRACE(trc, 9);
       tc_fence_after();
-      for (int s = 0; s < nslot; ++s) {
+      for (int s = 0; s < ((P4C_WB_ABLATE & 4) ? 0 : nslot); ++s) {
         float v[32];
         tmem_ld32(tm_dx + s * WB_HID, v);
         tmem_ld_wait();
@@ -740,14 +756,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
               for (int c = 0; c < 4; ++c) {
                 if (c < ncol / 8) {
                   float e[8];
-                  ws_unpack8(*reinterpret_cast<const uint4*>(dst + c * 8), e);
+                  ws_unpack8(gsz == 4 ? grp_old : *reinterpret_cast<const uint4*>(dst + c * 8), e);
 #pragma unroll
                   for (int q = 0; q < 8; ++q) e[q] += v[c * 8 + q];
                   *reinterpret_cast<uint4*>(dst + c * 8) = ws_pack8(e);
                 }
               }
             } else {  // group of 8: four columns per lane
-              const uint2 u = *reinterpret_cast<const uint2*>(dst);
+              const uint2 u = make_uint2(grp_old.x, grp_old.y);
               float e0, e1, e2, e3;
               ws_unpack2(u.x, e0, e1);
               ws_unpack2(u.y, e2, e3);
