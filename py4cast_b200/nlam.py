@@ -103,8 +103,8 @@ class FusedMLP(nn.Sequential):
             ln.weight if ln is not None else None, ln.bias if ln is not None else None,
         )
 
-    def forward(self, x: torch.Tensor, residual: bool = False) -> torch.Tensor:
-        return ops.fused_mlp(x, self.weights(), residual=residual, meta=self.meta)
+    def forward(self, x: torch.Tensor, residual: bool = False, share_grads: bool = False) -> torch.Tensor:
+        return ops.fused_mlp(x, self.weights(), residual=residual, meta=self.meta, share_grads=share_grads)
 
 
 def make_mlp(blueprint: Sequence[int], layer_norm: bool = True, widths: Optional[Sequence[int]] = None) -> FusedMLP:
@@ -192,10 +192,10 @@ class InteractionNet(nn.Module):
                 ms.append(mlp.meta)
         return ms
 
-    def forward(self, send_rep, rec_rep, edge_rep):
+    def forward(self, send_rep, rec_rep, edge_rep, share_grads: bool = False):
         return ops.interaction_net(
             self.graph_index(), send_rep, rec_rep, edge_rep, self._weights(),
-            self.update_edges, self.aggr == "mean", self._metas(),
+            self.update_edges, self.aggr == "mean", self._metas(), share_grads,
         )
 
 
@@ -407,8 +407,10 @@ class BaseGraphModel(ModelABC, nn.Module):
         g2m_emb = self._static_embedding("g2m", self.g2m_embedder, "g2m_features", dt)
         m2g_emb = self._static_embedding("m2g", self.m2g_embedder, "m2g_features", dt)
         mesh_emb = self.embedd_mesh_nodes(dt)
-        mesh_rep = self.g2m_gnn(grid_emb, mesh_emb, g2m_emb)
-        grid_rep = self.encoding_grid_mlp(grid_emb, residual=True)
+        # grid_emb has exactly two consumers, the g2m InteractionNet (senders) and the grid encoder: their input
+        # gradients are summed by g2m's by-sender kernel (ops: gradient hand-over), not by an element-wise pass
+        mesh_rep = self.g2m_gnn(grid_emb, mesh_emb, g2m_emb, share_grads=True)
+        grid_rep = self.encoding_grid_mlp(grid_emb, residual=True, share_grads=True)
         mesh_rep = self.process_step(mesh_rep, dt)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, m2g_emb)
         return self.output_map(grid_rep)
@@ -490,11 +492,11 @@ class BaseHiGraphModel(BaseGraphModel):
         higher, same, up, down = self._static_mesh_embeddings(dt)
         rep = [mesh_rep] + higher
         for l in range(1, L):  # init sweep, upward
-            rep[l], up[l - 1] = self.mesh_init_gnns[l - 1](rep[l - 1], rep[l], up[l - 1])
+            rep[l], up[l - 1] = self.mesh_init_gnns[l - 1](rep[l - 1], rep[l], up[l - 1], share_grads=True)
         rep, same, up, down = self.hi_processor_step(rep, same, up, down)
         cur = rep[-1]  # read-out sweep, downward
         for l in range(L - 2, -1, -1):
-            cur = self.mesh_read_gnns[l](cur, rep[l], down[l])
+            cur = self.mesh_read_gnns[l](cur, rep[l], down[l], share_grads=True)
         return cur
 
 
@@ -521,11 +523,11 @@ class HiLAM(BaseHiGraphModel):
         ):
             rep[L - 1], same[L - 1] = dsg[L - 1](rep[L - 1], rep[L - 1], same[L - 1])
             for l in range(L - 2, -1, -1):
-                new, down[l] = dg[l](rep[l + 1], rep[l], down[l])
+                new, down[l] = dg[l](rep[l + 1], rep[l], down[l], share_grads=True)
                 rep[l], same[l] = dsg[l](new, new, same[l])
             rep[0], same[0] = usg[0](rep[0], rep[0], same[0])
             for l in range(1, L):
-                new, up[l - 1] = ug[l - 1](rep[l - 1], rep[l], up[l - 1])
+                new, up[l - 1] = ug[l - 1](rep[l - 1], rep[l], up[l - 1], share_grads=True)
                 rep[l], same[l] = usg[l](new, new, same[l])
         return rep, same, up, down
 

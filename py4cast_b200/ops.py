@@ -542,12 +542,53 @@ def _bwd_recomputes(lib, desc: Mlp) -> bool:
 
 
 # -------------------------------------------------------------------- fused MLP
+# ---- gradient hand-over between the consumers of one tensor ------------------------------------------------
+# A representation that feeds two nodes of ours (grid embedding -> g2m senders + grid encoder; a mesh level ->
+# senders of one InteractionNet + receivers of another) receives two input gradients that torch autograd sums
+# with an element-wise pass.  The first backward to run registers the dense gradient tensor it returns, keyed by
+# the forward tensor's storage; a later backward of the SAME autograd pass whose share comes out of an
+# accumulating kernel (the by-sender segment-sum + GEMM) adds into that tensor and returns None instead.  Legal
+# because the producer's backward cannot start before every consumer's has finished; entries die with the pass
+# (torch's graph-task id), so repeated backward passes over recycled addresses never meet a stale tensor.
+# OPT-IN per call site (`share_grads`): it is only correct when the tensor has exactly these two consumers -- with
+# a third one autograd may already have summed the registered tensor into a fresh buffer before the hand-over.
+_GRAD_REG: dict = {}
+_GRAD_REG_TASK = [-1]
+GRAD_HANDOVERS = [0]  # hand-overs performed (tests / diagnostics)
+
+
+def _grad_key(t: torch.Tensor):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype)
+
+
+def _grad_task() -> int:
+    task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else -1
+    if task != _GRAD_REG_TASK[0]:
+        _GRAD_REG.clear()
+        _GRAD_REG_TASK[0] = task
+    return task
+
+
+def _grad_register(fwd_tensor: torch.Tensor, grad: Optional[torch.Tensor]) -> None:
+    if grad is None or _grad_task() < 0:
+        return
+    if fwd_tensor.dim() == 3 and grad.is_contiguous() and tuple(grad.shape) == tuple(fwd_tensor.shape):
+        _GRAD_REG[_grad_key(fwd_tensor)] = grad
+
+
+def _grad_lookup(fwd_tensor: torch.Tensor) -> Optional[torch.Tensor]:
+    if _grad_task() < 0:
+        return None
+    return _GRAD_REG.get(_grad_key(fwd_tensor))
+
+
 class _MLPFn(torch.autograd.Function):
     """y = [LN](W2 silu(W1 x + b1) + b2) [+ x]   for one dense, identity-indexed source."""
 
     @staticmethod
-    def forward(ctx, meta: Optional[MlpMeta], x, w1, b1, w2, b2, gamma, beta, residual: bool):
+    def forward(ctx, meta: Optional[MlpMeta], x, w1, b1, w2, b2, gamma, beta, residual: bool, share_grads: bool = False):
         lib = _lib.load()
+        ctx.share_grads = share_grads
         shared = x.dim() == 2
         x = _as_rows(x)
         B = 1 if shared else x.shape[0]
@@ -606,13 +647,17 @@ class _MLPFn(torch.autograd.Function):
             raise RuntimeError("residual MLP with a non-differentiable input is not supported")
         rets = _bind_wgrads(lib, desc, g, ws, ctx.needs_input_grad[2:8], ctx.meta, x.device, ctx.branch)
         check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward")
-        return (None, dx, *rets, None)
+        if ctx.share_grads and dx is not None and not shared and _row_layout(dx)[0] == K:
+            _grad_register(x, dx)
+        return (None, dx, *rets, None, None)
 
 
 def fused_mlp(x: torch.Tensor, weights: Sequence[Optional[torch.Tensor]], residual: bool = False,
-              meta: Optional[MlpMeta] = None) -> torch.Tensor:
+              meta: Optional[MlpMeta] = None, share_grads: bool = False) -> torch.Tensor:
+    """share_grads: x has exactly one other consumer, an interaction_net(..., share_grads=True) that gathers it as
+    its senders -- the two input gradients are summed by that call's by-sender kernel, not by autograd."""
     w1, b1, w2, b2, gamma, beta = weights
-    return _MLPFn.apply(meta, x, w1, b1, w2, b2, gamma, beta, residual)
+    return _MLPFn.apply(meta, x, w1, b1, w2, b2, gamma, beta, residual, share_grads)
 
 
 # --------------------------------------------------------------- InteractionNet
@@ -696,8 +741,9 @@ class _InteractionNetFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, gi: GraphIndex, update_edges: bool, mean: bool, metas, send, rec, edge, *weights):
+    def forward(ctx, gi: GraphIndex, update_edges: bool, mean: bool, metas, share_grads, send, rec, edge, *weights):
         lib = _lib.load()
+        ctx.share_grads = bool(share_grads)
         for t, n in ((send, "send"), (rec, "rec"), (edge, "edge")):
             _check_hidden(t, f"InteractionNet {n} representation")
         same_nodes = (send.data_ptr() == rec.data_ptr() and send.shape == rec.shape
@@ -828,8 +874,8 @@ class _InteractionNetFn(torch.autograd.Function):
         ew = [weights[6 * i: 6 * i + 6] for i in range(n_eg)]
         nw = [weights[6 * (n_eg + i): 6 * (n_eg + i) + 6] for i in range(len(node_chunks))]
         metas, tc = ctx.metas, ctx.tc
-        need_send, need_rec, need_edge = ctx.needs_input_grad[4:7]
-        wneed = ctx.needs_input_grad[7:]
+        need_send, need_rec, need_edge = ctx.needs_input_grad[5:8]
+        wneed = ctx.needs_input_grad[8:]
         same_nodes = ctx.same_nodes and need_send and need_rec
 
         if d_rec_out is None:
@@ -877,9 +923,17 @@ class _InteractionNetFn(torch.autograd.Function):
             d_edge = (torch.empty(E, HIDDEN, dtype=dt, device=dev) if edge_by_linearity
                       else torch.empty(B, E, HIDDEN, dtype=dt, device=dev))
         d_send = None
+        send_handed_over = False
         if need_send and not same_nodes:
-            d_send = torch.empty(B, Ns, HIDDEN, dtype=dt, device=dev)
-        first_send = True
+            # another consumer of `send` already returned its share of the gradient in this pass: the by-sender
+            # pass adds into it (see the hand-over notes above _MLPFn)
+            held = _grad_lookup(send) if (ctx.share_grads and tc and send.dim() == 3) else None
+            if held is not None and held.dtype == dt and tuple(held.shape) == (B, Ns, HIDDEN):
+                d_send, send_handed_over = held, True
+                GRAD_HANDOVERS[0] += 1
+            else:
+                d_send = torch.empty(B, Ns, HIDDEN, dtype=dt, device=dev)
+        first_send = not send_handed_over
         for gidx, (grp, w) in enumerate(zip(gi.groups, ew)):
             n = grp.stop - grp.start
             if n == 0:
@@ -954,16 +1008,24 @@ class _InteractionNetFn(torch.autograd.Function):
             d_send.zero_()
 
         g_send = None
-        if need_send and not same_nodes:
+        if need_send and not same_nodes and not send_handed_over:
             g_send = batch_sum(d_send) if send.dim() == 2 else d_send
+            if ctx.share_grads and tc and send.dim() == 3:
+                _grad_register(send, g_send)
         g_rec = (batch_sum(d_rec) if ctx.rec_shared else d_rec) if need_rec else None
+        if ctx.share_grads and tc and g_rec is not None and not ctx.rec_shared:
+            _grad_register(rec_b, g_rec)
         if edge_by_linearity:
             g_edge = d_edge
         else:
             g_edge = (batch_sum(d_edge) if edge.dim() == 2 else d_edge) if need_edge else None
-        return (None, None, None, None, g_send, g_rec, g_edge, *wgrads)
+        return (None, None, None, None, None, g_send, g_rec, g_edge, *wgrads)
 
 
 def interaction_net(gi: GraphIndex, send, rec, edge, weights: Sequence[torch.Tensor],
-                    update_edges: bool, mean: bool, metas: Optional[Sequence[Optional[MlpMeta]]] = None):
-    return _InteractionNetFn.apply(gi, update_edges, mean, metas, send, rec, edge, *weights)
+                    update_edges: bool, mean: bool, metas: Optional[Sequence[Optional[MlpMeta]]] = None,
+                    share_grads: bool = False):
+    """share_grads: the caller guarantees that `send` and `rec` (when they need gradients) have at most ONE other
+    consumer each, which is also called with share_grads: the second of the two backward passes adds its share
+    into the first one's tensor (by-sender kernel) instead of leaving the sum to autograd."""
+    return _InteractionNetFn.apply(gi, update_edges, mean, metas, share_grads, send, rec, edge, *weights)

@@ -235,6 +235,39 @@ def test_seg_linear_pair_matches_two_calls(ops, cuda):
         assert torch.equal(o1, o2)
 
 
+def test_gradient_hand_over_between_two_consumers(ops, cuda):
+    """share_grads: a representation that feeds an MLP and, as its senders, an InteractionNet gets ONE gradient
+    tensor (the by-sender kernel adds into the MLP's input gradient) -- same numbers as autograd's own sum, also
+    on repeated backward passes over the same storage (entries of the registry die with the autograd pass)."""
+    from py4cast_b200.graph_build import EdgeSet
+    from py4cast_b200.nlam import InteractionNet, make_mlp
+
+    g = torch.Generator().manual_seed(11)
+    E, ns, nr, B = 6000, 400, 250, 2
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=g), torch.randint(0, nr, (E,), generator=g)])
+    torch.manual_seed(3)
+    net = InteractionNet(EdgeSet(ei, torch.zeros(E, 3), ns, nr), 64, update_edges=False).to(cuda)
+    mlp = make_mlp([64, 64, 64]).to(cuda)
+    x = torch.randn(B, ns, 64, generator=g).to(cuda).bfloat16()
+    rec = torch.randn(B, nr, 64, generator=g).to(cuda).bfloat16()
+    edge = torch.randn(B, E, 64, generator=g).to(cuda).bfloat16()
+    gy = torch.randn(B, nr, 64, generator=g).to(cuda).bfloat16()
+    gm = torch.randn(B, ns, 64, generator=g).to(cuda).bfloat16()
+
+    def run(share):
+        xs = x.clone().requires_grad_(True)
+        h = xs * 1.0  # a produced tensor: two consumers below
+        out = net(h, rec, edge, share_grads=share)
+        y = mlp(h, residual=True, share_grads=share)
+        torch.autograd.backward([out, y], [gy, gm])
+        return xs.grad.float()
+
+    want = run(False)
+    for _ in range(3):  # recycled addresses across passes
+        got = run(True)
+        assert_close(got, want, 8e-3, "handed-over gradient vs autograd's sum")
+
+
 def test_deferred_weight_gradient_reduction_matches_immediate(ops, cuda):
     """Trainer mode: parameters with gradient sinks keep per-CTA partials across calls and are
     reduced by ONE batched launch (flush_wgrads); same numbers as the in-call reduction."""
