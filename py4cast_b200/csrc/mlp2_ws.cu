@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       const uint32_t rr = blk * WS_TM + row;
       int32_t orow = -1;  // row in the output-like arrays
       if (rr < rows) orow = static_cast<int32_t>((tile - blk * nbatch) * full + rr);
-      mbar_wait_backoff<160, true>(&S.d1_full[grp], nn & 1u);
+      mbar_wait_suspend(&S.d1_full[grp], nn & 1u);
       tc_fence_after();
       // the residual / edge row = this tile's K-block 0 (complete: G1 has consumed it)
       uint4 res[4];
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       }
 
       // ---- epilogue 2
-      mbar_wait_backoff<160, true>(&S.d2_full[grp], nn & 1u);
+      mbar_wait_suspend(&S.d2_full[grp], nn & 1u);
       tc_fence_after();
       float y[32];
       tmem_ld32(tm_d2, y);
