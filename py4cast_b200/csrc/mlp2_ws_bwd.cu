@@ -97,6 +97,10 @@ struct WbArgs {
   int tma_mask;
   int tma_b[P4C_MAX_SRC];
   alignas(64) CUtensorMap tmap[P4C_MAX_SRC];
+  // dh1 rows of a tile leave by ONE TMA store of the DH tile, issued by the context's MMA warp once the tile is
+  // complete (instead of 4 x (shuffle, 16-byte shared-memory read, global store) per compute thread)
+  alignas(64) CUtensorMap tmap_dh1;
+  int dh1_tma;
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's tile 2, see scripts/trace_ws_bwd.py
 };
 // slots 0.. compute group 0 (warp 0), 16.. MMA lane (context 0), 32.. producer warp 0
@@ -377,6 +381,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         // ---- G4: dW1 (K-blocks 0, 1) += [X0 | X1]^T dh1; dW1 (K-block 2), db1: [X2 | 1]^T dh1 or [1 | 1]^T dh1
         mbar_wait_backoff<20>(&S.dh1_full[c], par);
         P4C_WB_TRACE(trc && lane == 0, 24);
+        if (a.dh1_tma && lane == 0) {  // the DH tile holds dh1 (fenced for the async proxy by its writers)
+          const uint32_t tile = blockIdx.x + t * gridDim.x;
+          const uint32_t blk = nbatch == 1 ? tile
+                                           : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
+          tma_store_3d(&a.tmap_dh1, da, 0, static_cast<int>(blk * WB_TM), static_cast<int>(tile - blk * nbatch));
+          tma_store_commit();
+        }
+        __syncwarp();
         if (t > 0) mbar_wait_backoff<20>(&S.g4_turn[c ^ 1u], tpar);
         tc_fence_after();
         {
@@ -411,9 +423,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
               mma_bf16_ss_elect(dxc + s * WB_HID, dh_k + q * KSTEP, wd + q * MNSTEP, IDESC_KM, q ? 1u : 0u);
           }
         }
+        // the compute group overwrites the DH tile after dx_full (dX staging) or after a later commit of this warp
+        // (next tile's dh2): the TMA store must have read it by then
+        if (a.dh1_tma && lane == 0) tma_store_wait_read();
+        __syncwarp();
         mma_commit_elect(&S.dx_full[c]);
         P4C_WB_TRACE(trc && lane == 0, 20);
       }
+      if (a.dh1_tma && lane == 0) tma_store_wait_all();
     }
   } else {
     // ================================ compute ===============================
@@ -626,7 +643,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.dh1_full[grp]);
       P4C_WB_TRACE(trc, 7);
-      if (dh1_out && !(P4C_WB_ABLATE & 2)) {  // coalesced: lane -> 16-byte chunk j of row 8 i + sub of this warp's rows
+      if (dh1_out && !a.dh1_tma && !(P4C_WB_ABLATE & 2)) {  // coalesced: lane -> 16-byte chunk j of row 8 i + sub of this warp's rows
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + sub;
@@ -982,6 +999,11 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   }
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8 && !(a.tma_mask >> k & 1);
+  a.dh1_tma = 0;
+  if (g->dh1_out && tma_enabled()) {
+    const long long fr = m->full_rows > 0 ? m->full_rows : m->rows;
+    if (tma_rows_map(&a.tmap_dh1, g->dh1_out, P4C_HIDDEN, m->rows, P4C_HIDDEN, m->batch, fr * P4C_HIDDEN)) a.dh1_tma = 1;
+  }
   const unsigned long long rows = static_cast<unsigned long long>(m->rows);
   const unsigned long long nb = static_cast<unsigned long long>(m->batch);
   a.div_magic = nb == 1 ? 0ull : (~0ull / nb) + 1ull;

@@ -33,5 +33,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
         "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 128-byte-swizzled shared-memory tile -> box at (column c0, row c1, sample c2) of the tensor (rows / columns beyond
+// the tensor are clipped by the hardware).  Bulk async-group of the ISSUING thread: commit, then wait for the source
+// reads (the tile may be overwritten) or for full completion (before the CTA exits).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 }  // namespace tc
 }  // namespace p4c
