@@ -229,7 +229,9 @@ typedef struct {
   /* ---- outputs only the pipelined recomputing backward engine produces (see p4c_mlp_bwd_caps) ----
    * dx0_batch_sum: optional [rows][64]: sum over the samples of dh1[b] x W1[:, K-block of src[0]] — the
    *   gradient of a 64-wide identity-indexed src[0] that is SHARED by the batch (batch_stride 0: static
-   *   edge embeddings), written (not accumulated).  Replaces a (B, E, 64) input gradient + batch sum.
+   *   edge embeddings), written (not accumulated).  Replaces a (B, E, 64) input gradient + batch sum, or a
+ *   second pass over dh1: every CTA runs the samples of its row blocks back to back and accumulates the
+ *   product in 64 TMEM columns (caps bit 2: src[0] as above and at least 148 row blocks of 128 rows).
    * dx_group_out: optional [batch][full_rows / dx_group][64], ACCUMULATED in place: the input gradient
    *   of gathered source `dx_group_src` when row r gathers source row r / dx_group (receiver-sorted
    *   edges of uniform in-degree dx_group = 1, 2, 4 or 8): out[b][r / group] += sum over the group's
@@ -252,6 +254,7 @@ int32_t p4c_mlp_bwd_caps(const p4c_mlp_t* m);
 void p4c_set_ws_bwd_min_tiles(int64_t n); /* n <= 0: default (2 * 148; env P4C_WS_BWD_MIN_TILES) */
 int64_t p4c_get_ws_bwd_min_tiles(void);
 int64_t p4c_ws_bwd_launch_count(void);
+int64_t p4c_ws_bwd_bsum_launch_count(void); /* launches that produced dx0_batch_sum */
 
 /* number of per-CTA partial blocks p4c_mlp_backward writes for this problem (its grid) */
 int32_t p4c_mlp_wgrad_blocks(const p4c_mlp_t* m);

@@ -171,6 +171,7 @@ SYMBOLS = {
     "p4c_set_ws_bwd_min_tiles": (None, [_i64]),
     "p4c_get_ws_bwd_min_tiles": (_i64, []),
     "p4c_ws_bwd_launch_count": (_i64, []),
+    "p4c_ws_bwd_bsum_launch_count": (_i64, []),
     "p4c_get_engine": (_int, []),
     "p4c_mlp_forward": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "p4c_mlp_forward_aggregate": (_int, [C.POINTER(Mlp), _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),

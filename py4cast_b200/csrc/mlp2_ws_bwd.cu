@@ -60,7 +60,7 @@ constexpr int WB_THREADS = (WB_CWARPS + WB_PWARPS + 4) * 32;  // warps 21-23 onl
 // the pool setmaxnreg redistributes is what the CTA was launched with, not the whole register file
 constexpr int WB_REGS_COMPUTE = 96, WB_REGS_PRODUCER = 40, WB_REGS_MMA = 56;
 constexpr uint32_t WB_TMEM_COLS = 512;
-constexpr uint32_t WB_COL_DW1A = 0, WB_COL_DW1B = 64, WB_COL_DW2 = 128, WB_COL_CH = 192, WB_COL_DX = 320;
+constexpr uint32_t WB_COL_DW1A = 0, WB_COL_DW1B = 64, WB_COL_DW2 = 128, WB_COL_CH = 192, WB_COL_DX = 320, WB_COL_BS = 448;
 constexpr uint32_t kWbNoRow = 0xFFFFFFFFu;
 constexpr int WB_ONES_BYTES = 2048;
 
@@ -79,6 +79,7 @@ struct WbSmem {
       dx_full[2];
   uint64_t dxs_empty[2];
   uint64_t g3_turn[2], g4_turn[2];  // weight-gradient products of a context's tile issued (MMA warp -> MMA warp)
+  uint64_t bs_empty;                // the batch-summed dX of a row block was read (compute group -> MMA warps)
   uint32_t tmem_base;
 };
 
@@ -101,6 +102,11 @@ struct WbArgs {
   // complete (instead of 4 x (shuffle, 16-byte shared-memory read, global store) per compute thread)
   alignas(64) CUtensorMap tmap_dh1;
   int dh1_tma;
+  // dx0_batch_sum: every CTA owns a contiguous range of row blocks and runs the samples of a block back to back
+  // (tile t of the CTA = sample t % batch of block blk_lo + t / batch): dh1 W1[:, block 0] of the samples is
+  // accumulated in TMEM (64 columns) and stored once per block
+  int bsum;
+  uint32_t nblocks;  // row blocks of the problem
   long long* trace;  // developer aid (p4c_set_trace_buffer): SM clock at the phases of CTA 0's tile 2, see scripts/trace_ws_bwd.py
 };
 // slots 0.. compute group 0 (warp 0), 16.. MMA lane (context 0), 32.. producer warp 0
@@ -148,6 +154,19 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   const uint32_t nbatch = a.batch;
   const uint32_t rows = static_cast<uint32_t>(m.rows);
   const int nslot = a.nslot;
+  const bool bsum = a.bsum != 0;
+  // tile t of this CTA -> (row block, sample): round-robin over the CTAs, row-block-major / sample-minor (the
+  // samples of a block run back to back on neighbouring CTAs: a K-block shared by the batch comes from HBM once),
+  // or, for dx0_batch_sum, a contiguous range of row blocks per CTA with the samples of a block back to back
+  const uint32_t blk_lo =
+      bsum ? static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x) * a.nblocks / gridDim.x) : 0u;
+  auto tile_coords = [&](uint32_t t, uint32_t& blk, uint32_t& b) {
+    const uint32_t tile = bsum ? t : blockIdx.x + t * gridDim.x;
+    const uint32_t q = nbatch == 1 ? tile
+                                   : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
+    b = tile - q * nbatch;
+    blk = blk_lo + q;
+  };
   P4C_WB_KTRACE(48);  // kernel-level timeline (slots 48..): entry, set-up done, first tile, last tile, partials, exit
 #ifdef P4C_PHASE_TRACE
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[56] = static_cast<long long>(wb_globaltimer());
@@ -189,6 +208,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     }
     mbar_init(&S.dxs_empty[0], 8);
     mbar_init(&S.dxs_empty[1], 8);
+    mbar_init(&S.bs_empty, 8);
     for (int c = 0; c < 2; ++c) {
       mbar_init(&S.g3_turn[c], 1);
       mbar_init(&S.g4_turn[c], 1);
@@ -203,7 +223,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  const uint32_t ntl = a.ntiles > blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  const uint32_t ntl =
+      bsum ? (static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x + 1) * a.nblocks / gridDim.x) - blk_lo) * nbatch
+           : (a.ntiles > blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u);
   pdl_launch_dependents();
   P4C_WB_KTRACE(49);
 #ifdef P4C_PHASE_TRACE
@@ -221,10 +243,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     uint32_t b_next = 0, blk_next = 0;
     bool valid_next = false;
     auto load_indices = [&](uint32_t t) {  // gather indices of tile t (graph constants)
-      const uint32_t tile = blockIdx.x + t * gridDim.x;
-      const uint32_t blk = nbatch == 1 ? tile
-                                       : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
-      b_next = tile - blk * nbatch;
+      uint32_t blk;
+      tile_coords(t, blk, b_next);
       blk_next = blk;
       const uint32_t rr = blk * WB_TM + pw * 32 + lane;
       valid_next = t < ntl && rr < rows;
@@ -382,10 +402,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         mbar_wait_backoff<20>(&S.dh1_full[c], par);
         P4C_WB_TRACE(trc && lane == 0, 24);
         if (a.dh1_tma && lane == 0) {  // the DH tile holds dh1 (fenced for the async proxy by its writers)
-          const uint32_t tile = blockIdx.x + t * gridDim.x;
-          const uint32_t blk = nbatch == 1 ? tile
-                                           : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
-          tma_store_3d(&a.tmap_dh1, da, 0, static_cast<int>(blk * WB_TM), static_cast<int>(tile - blk * nbatch));
+          uint32_t blk, bs;
+          tile_coords(t, blk, bs);
+          tma_store_3d(&a.tmap_dh1, da, 0, static_cast<int>(blk * WB_TM), static_cast<int>(bs));
           tma_store_commit();
         }
         __syncwarp();
@@ -403,7 +422,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
           for (int q = 0; q < 8; ++q)
             mma_bf16_ss_elect(tmem + WB_COL_DW1B, x2o + q * x2step, dh_mn + q * MNSTEP, IDESC_MM, (t | q) ? 1u : 0u);
         }
-        mma_commit_elect(&S.g4_turn[c]);
+        if (!bsum) mma_commit_elect(&S.g4_turn[c]);
         mma_commit_elect(&S.x_empty[xst]);
         P4C_WB_TRACE(trc && lane == 0, 19);
 
@@ -422,6 +441,20 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
             for (int q = 0; q < 4; ++q)  // W1 tile [n][c]: K = n along the rows, N = c contiguous
               mma_bf16_ss_elect(dxc + s * WB_HID, dh_k + q * KSTEP, wd + q * MNSTEP, IDESC_KM, q ? 1u : 0u);
           }
+        }
+        // ---- batch sum: BS (+)= dh1 W1[:, block 0], accumulated over the samples of the row block (tiles of both
+        //      contexts: the turn barrier, committed after this product, keeps them in tile order; the first sample
+        //      overwrites once the previous block's sum was read)
+        if (bsum) {
+          const uint32_t run = nbatch == 1 ? t : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(t), a.div_magic));
+          const uint32_t bs = t - run * nbatch;
+          if (bs == 0 && run > 0) mbar_wait_backoff<20>(&S.bs_empty, (run - 1) & 1u);
+          tc_fence_after();
+          const uint64_t wd = make_desc_sw128(smem_u32(S.W1[0]), WB_WBLK, 1024);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            mma_bf16_ss_elect(tmem + WB_COL_BS, dh_k + q * KSTEP, wd + q * MNSTEP, IDESC_KM, (bs | q) ? 1u : 0u);
+          mma_commit_elect(&S.g4_turn[c]);
         }
         // the compute group overwrites the DH tile after dx_full (dX staging) or after a later commit of this warp
         // (next tile's dh2): the TMA store must have read it by then
@@ -455,10 +488,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     P4C_WB_KTRACE(50);
     for (uint32_t t = grp; t < ntl; t += 2) {
       const uint32_t par = (t >> 1) & 1u;
-      const uint32_t tile = blockIdx.x + t * gridDim.x;
-      const uint32_t blk = nbatch == 1 ? tile
-                                       : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(tile), a.div_magic));
-      const uint32_t bsamp = tile - blk * nbatch;
+      uint32_t blk, bsamp;
+      tile_coords(t, blk, bsamp);
       const uint32_t rr = blk * WB_TM + row;
       const bool valid = rr < rows;
       const int32_t orow = valid ? static_cast<int32_t>(bsamp * full + rr) : -1;  // row in the output-like arrays
@@ -678,6 +709,28 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       mbar_wait_suspend(&S.dx_full[grp], par);
       P4C_WB_TRACE(trc, 9);
       tc_fence_after();
+      if (bsum && bsamp == nbatch - 1) {
+        // last sample of the row block: the batch-summed gradient of the shared src[0] rows (every product into BS
+        // completed before this tile's dx_full); released first, then staged like a stored dX slot
+        float v[32];
+        tmem_ld32(tm_lane + WB_COL_BS + col0, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.bs_empty);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(dhs + sw128_offset(row, hsel * 4 + c), ws_pack8(v + c * 8));
+        __syncwarp();
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dx0_batch_sum);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = quad * 32 + 8 * i + sub;
+          const uint32_t grow = blk * WB_TM + r;
+          const uint4 u = lds128(dhs + sw128_offset(r, j));
+          if (grow < rows) *reinterpret_cast<uint4*>(base + static_cast<long long>(grow) * WB_HID + j * 8) = u;
+        }
+        __syncwarp();
+      }
       for (int s = 0; s < ((P4C_WB_ABLATE & 4) ? 0 : nslot); ++s) {
         float v[32];
         tmem_ld32(tm_dx + s * WB_HID, v);
@@ -899,6 +952,7 @@ bool tc_kblocks(const p4c_mlp_t* m, tc::KBlocks* kb);
 
 static long long g_wb_min_tiles = -1;
 static long long g_wb_launches = 0;
+static long long g_wb_bsum_launches = 0;
 static long long wb_min_tiles() {
   if (g_wb_min_tiles < 0) {
     const char* e = getenv("P4C_WS_BWD_MIN_TILES");
@@ -933,6 +987,15 @@ bool ws_backward_shape_ok(const p4c_mlp_t* m) {
   return true;
 }
 
+// dx0_batch_sum (a function of the shape): src[0] is a plain 64-wide row source shared by the batch, and every CTA
+// gets at least one whole row block (the samples of a block run back to back on one CTA)
+bool ws_backward_bsum_ok(const p4c_mlp_t* m) {
+  if (!ws_backward_shape_ok(m)) return false;
+  const p4c_src_t& s0 = m->src[0];
+  if (s0.index || s0.seg_rowptr || s0.width != P4C_HIDDEN || s0.batch_stride != 0) return false;
+  return (m->rows + 127) / 128 >= kNumSMs;
+}
+
 static int wb_slots(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, const tc::KBlocks& kb, int* blk, int* kind) {
   int n = 0;
   for (int k = 0; k < kb.nblk; ++k)
@@ -965,7 +1028,9 @@ bool ws_backward_supported(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g) {
     if (g->dx_group_src < 0 || g->dx_group_src >= m->nsrc || m->src[g->dx_group_src].width != P4C_HIDDEN) return false;
     if (g->dx[g->dx_group_src] || (reinterpret_cast<uintptr_t>(g->dx_group_out) % 16) != 0) return false;
   }
-  if (g->dx0_batch_sum) return false;
+  if (g->dx0_batch_sum) {  // 64-wide identity-indexed src[0] shared by the batch, its own gradient not requested
+    if (!ws_backward_bsum_ok(m) || g->dx[0] || (reinterpret_cast<uintptr_t>(g->dx0_batch_sum) % 16) != 0) return false;
+  }
   int blk[2], kind[2];
   if (wb_slots(m, g, kb, blk, kind) > 2) return false;
   if (g->dy_a_batch_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(g->dy_a) % 16) != 0) return false;
@@ -999,6 +1064,8 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   }
   a.zero_x = 0;
   for (int k = 0; k < a.kb.nblk; ++k) a.zero_x |= a.kb.nchunks[k] < 8 && !(a.tma_mask >> k & 1);
+  a.bsum = g->dx0_batch_sum ? 1 : 0;
+  a.nblocks = static_cast<uint32_t>((m->rows + WB_TM - 1) / WB_TM);
   a.dh1_tma = 0;
   if (g->dh1_out && tma_enabled()) {
     const long long fr = m->full_rows > 0 ? m->full_rows : m->rows;
@@ -1020,7 +1087,7 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
     }
     if (want > 0 && a.kb.nblk != want) a.trace = nullptr;
   }
-  const int grid = ws_backward_grid(m);
+  const int grid = ws_backward_grid(m);  // bsum: nblocks >= kNumSMs, i.e. kNumSMs CTAs
   const size_t smem = sizeof(WbSmem) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -1034,6 +1101,7 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
   launch_pdl(mlp2_ws_bwd_kernel, dim3(grid), dim3(WB_THREADS), smem, st, a);
   P4C_CHECK_LAUNCH("mlp_backward(ws)");
   ++g_wb_launches;
+  if (a.bsum) ++g_wb_bsum_launches;
   return P4C_OK;
 }
 
@@ -1041,8 +1109,9 @@ int launch_mlp2_ws_backward(const p4c_mlp_t* m, const p4c_mlp_bwd_t* g, int tota
 
 extern "C" int32_t p4c_mlp_bwd_caps(const p4c_mlp_t* m) {
   if (!m || m->rows <= 0 || m->batch <= 0) return 0;
-  return p4c::ws_backward_shape_ok(m) ? (1 | 4) : 0;
+  return p4c::ws_backward_shape_ok(m) ? (1 | 4 | (p4c::ws_backward_bsum_ok(m) ? 2 : 0)) : 0;
 }
 extern "C" void p4c_set_ws_bwd_min_tiles(int64_t n) { p4c::g_wb_min_tiles = n > 0 ? n : -1; }
 extern "C" int64_t p4c_get_ws_bwd_min_tiles(void) { return p4c::wb_min_tiles(); }
 extern "C" int64_t p4c_ws_bwd_launch_count(void) { return p4c::g_wb_launches; }
+extern "C" int64_t p4c_ws_bwd_bsum_launch_count(void) { return p4c::g_wb_bsum_launches; }

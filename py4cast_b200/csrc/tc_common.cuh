@@ -340,13 +340,17 @@ __device__ __forceinline__ void seg_add8(float* s, const uint4& u) {
   t = unpack_bf16x2(u.w); s[6] += t.x; s[7] += t.y;
 }
 
-template <int NTHREADS>
+// PV: items of a thread that can be valid (rows r = item >> (3 + lg) of the items p >= PV must lie beyond `nrows`:
+// tiles of at most 16 rows with 256 threads use PV = 2); U: source rows per item and iteration.  The gather
+// indices of iteration i + 1 are loaded while the rows of iteration i are in flight (one dependent latency per
+// iteration instead of two); the rows of a segment are added in the same order whatever PV / U.
+template <int NTHREADS, int PV = 1024 / NTHREADS, int U = 2>
 __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ perm,
                                              const uint32_t* lo, const uint32_t* hi, const uint32_t* sbase,
                                              const float* sc, const int32_t* orow, uint8_t* X,
                                              __nv_bfloat16* __restrict__ out_rows, int tid, int nrows = 128,
                                              long long* trace = nullptr) {
-  constexpr int P = 1024 / NTHREADS;  // items (passes) per thread
+  constexpr int P = PV;  // items (passes) per thread
   if (trace) trace[10] = clock64();
   const int lg = nrows >= 128 ? 0 : (nrows >= 64 ? 1 : 2);  // log2(G); nrows < 32 still uses G = 4
   const uint32_t G = 1u << lg;
@@ -367,32 +371,39 @@ __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ s
     for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
   }
   if (trace) trace[11] = clock64();
+  uint32_t ix[P][U];
+  bool act[P][U];
+  auto fetch_indices = [&]() {
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ee = e[p] + u * G;
+        act[p][u] = ee < h[p];
+        ix[p][u] = act[p][u] ? (perm ? static_cast<uint32_t>(perm[ee]) : ee) : 0u;
+      }
+  };
+  fetch_indices();
   int iters = 0;
   while (true) {
     ++iters;
-    long long i0[P], i1[P];
-    bool a0[P], a1[P];
+    uint4 v[P][U];
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      a0[p] = e[p] < h[p];
-      a1[p] = e[p] + G < h[p];
-      i0[p] = a0[p] ? (perm ? static_cast<long long>(perm[e[p]]) : static_cast<long long>(e[p])) : 0ll;
-      i1[p] = a1[p] ? (perm ? static_cast<long long>(perm[e[p] + G]) : static_cast<long long>(e[p] + G)) : 0ll;
-    }
-    uint4 u0[P], u1[P];
+    for (int p = 0; p < P; ++p)
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      u0[p] = a0[p] ? *reinterpret_cast<const uint4*>(sb[p] + i0[p] * 64) : zero4;
-      u1[p] = a1[p] ? *reinterpret_cast<const uint4*>(sb[p] + i1[p] * 64) : zero4;
-    }
+      for (int u = 0; u < U; ++u)
+        v[p][u] = act[p][u] ? *reinterpret_cast<const uint4*>(sb[p] + static_cast<long long>(ix[p][u]) * 64) : zero4;
     bool more = false;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      seg_add8(acc[p], u0[p]);
-      seg_add8(acc[p], u1[p]);
-      e[p] += 2 * G;
+      e[p] += U * G;
       more |= e[p] < h[p];
     }
+    if (more) fetch_indices();  // next iteration's indices, in flight together with this iteration's rows
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int u = 0; u < U; ++u) seg_add8(acc[p], v[p][u]);
     if (!more) break;
   }
   if (trace) { trace[12] = clock64(); trace[15] = iters; }

@@ -960,8 +960,13 @@ class _InteractionNetFn(torch.autograd.Function):
             g.dh1_out = _off(dh1, o)
             # receiver-sorted edges of uniform in-degree: the pipelined engine sums the receiver gradient
             # over each group of rows in its epilogue and accumulates it into d_rec (no pass over dh1)
-            rec_in_epilogue = (tc and need_rec and gi.uniform_deg > 0 and n_eg == 1 and not ctx.mean
-                               and bool(lib.p4c_mlp_bwd_caps(C.byref(desc)) & 4))
+            caps = lib.p4c_mlp_bwd_caps(C.byref(desc)) if (tc and not ctx.mean) else 0
+            rec_in_epilogue = tc and need_rec and gi.uniform_deg > 0 and n_eg == 1 and bool(caps & 4)
+            # static edge embedding shared by the batch: the pipelined engine accumulates dh1 x W1[:, edge block] over
+            # the samples of a row block in TMEM and stores the (E, 64) gradient itself (no pass over dh1)
+            edge_in_kernel = edge_by_linearity and bool(caps & 2)
+            if edge_in_kernel:
+                g.dx0_batch_sum = _off(d_edge, o)
             if rec_in_epilogue:
                 g.dx_group_out, g.dx_group, g.dx_group_src = ptr(d_rec), gi.uniform_deg, 2
             if need_edge and not edge_by_linearity:
@@ -972,7 +977,7 @@ class _InteractionNetFn(torch.autograd.Function):
             check(lib.p4c_mlp_backward(C.byref(desc), C.byref(g), stream()), "p4c_mlp_backward(edge)")
             # sender / receiver gradients by linearity: (segment-sum of dh1) x W1 slice
             if tc:
-                if edge_by_linearity:
+                if edge_by_linearity and not edge_in_kernel:
                     bc = _batch_rows_csr(gi, B, dev)
                     seg_linear(dh1.view(1, B * E, HIDDEN), Csr(bc.rowptr[grp.start: grp.stop + 1], bc.perm, n),
                                1, w[0], 0, d_edge[grp.start: grp.stop].unsqueeze(0), False, meta=metas[gidx])

@@ -80,23 +80,28 @@ def test_dense_mlp_backward_matches_classic_engine_and_oracle(lib, cuda, k1, row
         assert_close(a, b, 8e-3, f"{n}: pipelined vs classic")
 
 
-@pytest.mark.parametrize("kind,deg,update_edges,batch,shared_edge", [
-    ("uniform", 4, False, 2, False),   # m2g: receiver gradient summed over groups of 4 rows in the epilogue
-    ("uniform", 4, False, 3, True),    # ... with the static edge embedding shared by the batch
-    ("uniform", 1, True, 1, False),    # up / down edges with edge update: dy_b, d_edge pass-through, group of 1
-    ("uniform", 8, False, 1, False),
-    ("uniform", 2, True, 2, False),
-    ("random", 0, True, 2, False),     # g2m-like: both node gradients through the segment-sum pass
-    ("random", 0, False, 1, True),
+@pytest.mark.parametrize("kind,deg,update_edges,batch,shared_edge,nr", [
+    ("uniform", 4, False, 2, False, 1500),   # m2g: receiver gradient summed over groups of 4 rows in the epilogue
+    ("uniform", 4, False, 3, True, 1500),    # ... with the static edge embedding shared by the batch
+    ("uniform", 1, True, 1, False, 1500),    # up / down edges with edge update: dy_b, d_edge pass-through, group of 1
+    ("uniform", 8, False, 1, False, 1500),
+    ("uniform", 2, True, 2, False, 1500),
+    ("random", 0, True, 2, False, 1500),     # g2m-like: both node gradients through the segment-sum pass
+    ("random", 0, False, 1, True, 1500),
+    # at least 148 row blocks: the shared edge embedding's gradient is accumulated over the samples in TMEM
+    # (dx0_batch_sum; the last row block is partial, CTAs own 1 or 2 blocks)
+    ("uniform", 4, False, 3, True, 5990),
+    ("uniform", 4, False, 1, True, 4800),
+    ("random", 0, False, 4, True, 6000),
 ])
-def test_interaction_net_backward(lib, cuda, kind, deg, update_edges, batch, shared_edge):
+def test_interaction_net_backward(lib, cuda, kind, deg, update_edges, batch, shared_edge, nr):
     from oracle import graph_ref
     from py4cast_b200 import ops
     from py4cast_b200.graph_build import EdgeSet
     from py4cast_b200.nlam import InteractionNet
 
-    nr, ns = 1500, 300
-    ei = _uniform_graph(nr, ns, deg, 3) if kind == "uniform" else _random_graph(nr, ns, 5000, 3)
+    ns = 300
+    ei = _uniform_graph(nr, ns, deg, 3) if kind == "uniform" else _random_graph(nr, ns, 5000 if nr < 4000 else 30001, 3)
     E = ei.shape[1]
     es = EdgeSet(ei, torch.zeros(E, 3), ns, nr)
     torch.manual_seed(7)
@@ -135,7 +140,10 @@ def test_interaction_net_backward(lib, cuda, kind, deg, update_edges, batch, sha
         res += [torch.cat([p.grad.flatten() for p in net.parameters()])]
         return [t.detach().float().cpu() for t in res]
 
+    nb0 = lib.p4c_ws_bwd_bsum_launch_count()
     classic, wsr = _both(lib, run_gpu)
+    assert (lib.p4c_ws_bwd_bsum_launch_count() - nb0 == 1) == (shared_edge and nr >= 4000), \
+        "dx0_batch_sum must serve exactly the shared edge embeddings of at least 148 row blocks"
     refs = run_ref() + [torch.cat([p.grad.flatten() for p in ref.parameters()])]
     names = (["rec_out", "edge_out"] if update_edges else ["rec_out"]) + ["d_send", "d_rec", "d_edge", "d_params"]
     for n, a, b, r in zip(names, wsr, classic, refs):
