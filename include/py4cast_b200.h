@@ -344,6 +344,10 @@ typedef struct {
 /* x[b,n,:] = cat(prev[0..T_in-1], static, forcing)      (lightning.py:711-767 `_next_x`)
  * x: [batch][nodes][T_in*F + F_s + F_f] of `x_dtype`. */
 int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream);
+/* 0: p4c_ar_concat / p4c_ar_step_forward / p4c_ar_step_backward use their scalar kernels only (the staged /
+ * vectorised ones need nodes % 64 == 0 resp. nodes * F % 4 == 0 and 16-byte aligned arrays; same results bit for
+ * bit: tests compare the two); default 1. */
+void p4c_set_ar_vector_paths(int enabled);
 
 /* new_state = border*truth + interior*(prev_last + y*std + mean)   (lightning.py:598-633)
  *   scale_y == 0      => predicted = prev_last + y                  (diff_ar, :623)

@@ -186,6 +186,7 @@ SYMBOLS = {
     "p4c_mlp_backward": (_int, [C.POINTER(Mlp), C.POINTER(MlpBwd), _vp]),
     "p4c_rows_matmul": (_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _int, _int, _vp]),
     "p4c_batch_sum": (_int, [_vp, _i64, _i32, _i64, _vp, _int, _int, _vp]),
+    "p4c_set_ar_vector_paths": (None, [_int]),
     "p4c_ar_concat": (_int, [C.POINTER(ArX), _vp, _int, _vp]),
     "p4c_ar_step_forward": (
         _int,

@@ -218,6 +218,162 @@ ar_tile_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x, int has_u
   }
 }
 
+// Staged variant of the tile kernel (nodes a multiple of AR_TN, 16-byte aligned arrays, even row stride of x):
+// every input array of the CTA's AR_TN nodes is one contiguous span, copied global -> shared with 16-byte
+// cp.async (no registers, every copy of the CTA in flight together: the scalar-load tile kernel above keeps one
+// 4-byte load per thread in flight and reaches 0.47 of the HBM peak); the new state is then computed from the
+// staged spans four elements at a time (same expressions as ar_new_state) and the x rows are assembled from the
+// spans through a per-column (offset, stride) table and streamed out as pairs.
+__device__ __forceinline__ void ar_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" : : "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float ar_blend(float pl, float yv, const float* std_, const float* mean_, int f,
+                                          const float* border, int n, float truth) {
+  float pred = std_ ? pl + yv * std_[f] + mean_[f] : pl + yv;
+  if (border) {
+    const float bm = border[n];
+    pred = bm * truth + (1.0f - bm) * pred;  // same expression as the reference (see ar_new_state)
+  }
+  return pred;
+}
+
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256)
+ar_stage_kernel(const ArStep s, const p4c_ar_x_t a, TX* __restrict__ x, int has_update) {
+  extern __shared__ __align__(16) float R[];
+  const int F = a.f_state, T = a.num_prev, Fs = a.f_static, Ff = a.f_forcing;
+  const int f_in = T * F + Fs + Ff;
+  const int ld = a.x_ld > 0 ? a.x_ld : f_in;
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * AR_TN;
+  const int tid = threadIdx.x;
+  const int span = AR_TN * F;  // floats of one state span
+  // layout (floats; every offset a multiple of 4): T state spans | statics | forcing | zeros(4) | prev_last |
+  // truth | y | column table
+  const int offS = T * span, offF = offS + AR_TN * Fs, offZ = offF + AR_TN * Ff;
+  const int offPL = offZ + 4, offTR = offPL + span, offY = offTR + span;
+  const int ybytes = span * (int)sizeof(TY);
+  const int offTab = offY + (ybytes + 15) / 16 * 4;
+  const uint32_t r0 = (uint32_t)__cvta_generic_to_shared(R);
+  int2* tab = reinterpret_cast<int2*>(R + offTab);
+
+  const int ncopy = has_update ? T - 1 : T;
+  for (int t = 0; t < ncopy; ++t) {
+    const float* src = a.prev[t] + (long long)b * a.prev_batch_stride[t] + (long long)n0 * F;
+    for (int i = tid; i < span / 4; i += 256) ar_cp16(r0 + (t * span + 4 * i) * 4, src + 4 * i);
+  }
+  if (Fs > 0) {
+    const float* src = a.stat + (long long)b * a.stat_batch_stride + (long long)n0 * Fs;
+    for (int i = tid; i < AR_TN * Fs / 4; i += 256) ar_cp16(r0 + (offS + 4 * i) * 4, src + 4 * i);
+  }
+  if (Ff > 0) {
+    const float* src = a.forcing + (long long)b * a.forcing_batch_stride + (long long)n0 * Ff;
+    for (int i = tid; i < AR_TN * Ff / 4; i += 256) ar_cp16(r0 + (offF + 4 * i) * 4, src + 4 * i);
+  }
+  if (has_update) {
+    const float* pl = s.prev_last + (long long)b * s.prev_last_bs + (long long)n0 * F;
+    for (int i = tid; i < span / 4; i += 256) ar_cp16(r0 + (offPL + 4 * i) * 4, pl + 4 * i);
+    if (s.border) {
+      const float* tr = s.truth + (long long)b * s.truth_bs + (long long)n0 * F;
+      for (int i = tid; i < span / 4; i += 256) ar_cp16(r0 + (offTR + 4 * i) * 4, tr + 4 * i);
+    }
+    const char* yb = reinterpret_cast<const char*>(s.y) + ((long long)b * s.nodes * F + (long long)n0 * F) * (long long)sizeof(TY);
+    for (int i = tid; i < ybytes / 16; i += 256) ar_cp16(r0 + offY * 4 + 16 * i, yb + 16 * i);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < 4) R[offZ + tid] = 0.f;
+  for (int k = tid; k < ld; k += 256) {  // column k of an x row -> (offset of node 0's value, stride per node)
+    int2 e;
+    if (k < T * F) {
+      const int t = k / F;
+      e = make_int2(t * span + (k - t * F), F);
+    } else if (k < T * F + Fs) {
+      e = make_int2(offS + (k - T * F), Fs);
+    } else if (k < f_in) {
+      e = make_int2(offF + (k - T * F - Fs), Ff);
+    } else {
+      e = make_int2(offZ, 0);
+    }
+    tab[k] = e;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  if (has_update) {
+    const float invF = 1.0f / (float)F;
+    float* ns = s.new_state + (long long)b * s.new_state_bs + (long long)n0 * F;
+    const TY* ys = reinterpret_cast<const TY*>(R + offY);
+    for (int i = tid; i < span / 4; i += 256) {
+      const int e0 = 4 * i;
+      int n = (int)(((float)e0 + 0.5f) * invF), f = e0 - n * F;
+      const float4 pl = *reinterpret_cast<const float4*>(R + offPL + e0);
+      float4 tr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s.border) tr = *reinterpret_cast<const float4*>(R + offTR + e0);
+      const float plv[4] = {pl.x, pl.y, pl.z, pl.w}, trv[4] = {tr.x, tr.y, tr.z, tr.w};
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = ar_blend(plv[q], to_f32<TY>(ys[e0 + q]), s.std_, s.mean_, f, s.border, n0 + n, trv[q]);
+        if (++f == F) {
+          f = 0;
+          ++n;
+        }
+      }
+      const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(R + (T - 1) * span + e0) = o;
+      *reinterpret_cast<float4*>(ns + e0) = o;
+    }
+    __syncthreads();
+  }
+
+  TX* dst = x + ((long long)b * a.nodes + n0) * ld;
+  const int half = ld >> 1;
+  const float inv_half = 1.0f / (float)half;
+  for (int p = tid; p < AR_TN * half; p += 256) {
+    const int n = (int)(((float)p + 0.5f) * inv_half), k = 2 * (p - n * half);
+    const int2 t0 = tab[k], t1 = tab[k + 1];
+    ar_store_pair<TX>(dst + 2 * p, R[t0.x + n * t0.y], R[t1.x + n * t1.y]);
+  }
+}
+
+static size_t ar_stage_smem(const p4c_ar_x_t* a, int y_bytes_per_elem) {
+  const int F = a->f_state, T = a->num_prev;
+  const int f_in = T * F + a->f_static + a->f_forcing;
+  const int ld = a->x_ld > 0 ? a->x_ld : f_in;
+  const size_t span = (size_t)AR_TN * F;
+  size_t fl = T * span + (size_t)AR_TN * a->f_static + (size_t)AR_TN * a->f_forcing + 4 + 2 * span;
+  fl += (span * y_bytes_per_elem + 15) / 16 * 4;
+  return fl * 4 + (size_t)ld * 8;
+}
+
+static bool ar_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int g_ar_vector_paths = 1;  // p4c_set_ar_vector_paths (tests compare the staged / vectorised kernels with the scalar ones)
+
+// the staged kernel's requirements (else the scalar tile kernel / flat kernels serve the call)
+static bool ar_stage_ok(const p4c_ar_x_t* a, const void* x, int x_dtype, const ArStep* s, int y_dtype, size_t* smem) {
+  const int F = a->f_state, T = a->num_prev;
+  const int f_in = T * F + a->f_static + a->f_forcing;
+  const int ld = a->x_ld > 0 ? a->x_ld : f_in;
+  if (!g_ar_vector_paths || a->nodes % AR_TN != 0 || (ld & 1) || a->batch > 65535 || F > 512) return false;
+  if (!ar_al16(x) && x_dtype == P4C_F32) return false;
+  if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return false;
+  const int ncopy = s ? T - 1 : T;
+  for (int t = 0; t < ncopy; ++t)
+    if (!ar_al16(a->prev[t]) || a->prev_batch_stride[t] % 4 != 0) return false;
+  if (a->f_static > 0 && (!ar_al16(a->stat) || a->stat_batch_stride % 4 != 0)) return false;
+  if (a->f_forcing > 0 && (!ar_al16(a->forcing) || a->forcing_batch_stride % 4 != 0)) return false;
+  int ybytes = 4;
+  if (s) {
+    ybytes = y_dtype == P4C_BF16 ? 2 : 4;
+    if (!ar_al16(s->prev_last) || s->prev_last_bs % 4 != 0) return false;
+    if (s->border && (!ar_al16(s->truth) || s->truth_bs % 4 != 0)) return false;
+    if (!ar_al16(s->y) || ((long long)a->nodes * F * ybytes) % 16 != 0) return false;
+    if (!ar_al16(s->new_state) || s->new_state_bs % 4 != 0) return false;
+  }
+  *smem = ar_stage_smem(a, ybytes);
+  return *smem <= 48 * 1024;
+}
+
 struct ArBwd {
   const float* g_new;
   long long g_new_bs;
@@ -259,6 +415,61 @@ __global__ void __launch_bounds__(256) ar_step_bwd_kernel(const ArBwd s) {
         if (s.d_prev[t]) s.d_prev[t][i] = to_f32<TX>(gx[xrow + (long long)(t - 1) * s.F + f]);
     }
   }
+}
+
+// Vectorised form of ar_step_bwd_kernel: blockIdx.y = sample, a thread handles four consecutive elements of the
+// (nodes x F) plane with 16-byte loads / stores of the state-shaped arrays and ONE exact 32-bit division (the scalar
+// kernel pays two 64-bit divisions per element).  Same arithmetic per element: bit-identical results.  Needs
+// nodes * F a multiple of 4 and 16-byte aligned arrays (p4c_ar_step_backward checks).
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256) ar_step_bwd_vec_kernel(const ArBwd s, unsigned long long magic_f) {
+  const uint32_t per_b = (uint32_t)s.nodes * (uint32_t)s.F;
+  const uint32_t e0 = 4u * (blockIdx.x * 256u + threadIdx.x);
+  if (e0 >= per_b) return;
+  const int b = blockIdx.y;
+  const int T = s.num_prev, F = s.F;
+  const TX* gx = reinterpret_cast<const TX*>(s.g_x);
+  int n = (int)__umul64hi((unsigned long long)e0, magic_f);
+  int f = (int)e0 - n * F;
+  const long long i0 = (long long)b * per_b + e0;
+  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.g_new) g4 = *reinterpret_cast<const float4*>(s.g_new + (long long)b * s.g_new_bs + e0);
+  float G[4] = {g4.x, g4.y, g4.z, g4.w};
+  if (s.g_new2) {
+    const float4 h = *reinterpret_cast<const float4*>(s.g_new2 + (long long)b * s.g_new2_bs + e0);
+    G[0] += h.x; G[1] += h.y; G[2] += h.z; G[3] += h.w;
+  }
+  float dyv[4], dl[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long xrow = ((long long)b * s.nodes + n) * s.f_in;
+    float Gq = G[q];
+    if (gx) Gq += to_f32<TX>(gx[xrow + (long long)(T - 1) * F + f]);
+    const float interior = s.border ? 1.0f - s.border[n] : 1.0f;
+    const float gi = Gq * interior;
+    dyv[q] = s.std_ ? gi * s.std_[f] : gi;
+    float dlast = gi;
+    if (gx && T >= 2) dlast += to_f32<TX>(gx[xrow + (long long)(T - 2) * F + f]);
+    dl[q] = dlast;
+    if (gx) {
+      for (int t = 1; t < T - 1; ++t)
+        if (s.d_prev[t]) s.d_prev[t][i0 + q] = to_f32<TX>(gx[xrow + (long long)(t - 1) * F + f]);  // T_in >= 3 only
+    }
+    if (++f == F) {
+      f = 0;
+      ++n;
+    }
+  }
+  if (sizeof(TY) == 2) {
+    uint2 o;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(dyv[0], dyv[1]), hi = __floats2bfloat162_rn(dyv[2], dyv[3]);
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(s.dy) + i0) = o;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(s.dy) + i0) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+  }
+  if (s.d_prev[T - 1]) *reinterpret_cast<float4*>(s.d_prev[T - 1] + i0) = make_float4(dl[0], dl[1], dl[2], dl[3]);
 }
 
 // ------------------------------------------------------------------------------ losses
@@ -621,6 +832,8 @@ static int check_ar_x(const p4c_ar_x_t* a, bool last_may_be_null) {
 
 using namespace p4c;
 
+extern "C" void p4c_set_ar_vector_paths(int enabled) { p4c::g_ar_vector_paths = enabled ? 1 : 0; }
+
 extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream) {
   int rc = check_ar_x(a, false);
   if (rc) return rc;
@@ -631,6 +844,15 @@ extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* st
   P4C_REQUIRE(x_dtype == P4C_F32 || x_dtype == P4C_BF16, "ar_concat: bad dtype %d", x_dtype);
   const int ld = a->x_ld > 0 ? a->x_ld : f_in;
   const size_t tile_smem = (size_t)AR_TN * ld * sizeof(float);
+  size_t stage_smem = 0;
+  if (ar_stage_ok(a, x, x_dtype, nullptr, 0, &stage_smem)) {
+    const dim3 grid(a->nodes / AR_TN, a->batch);
+    ArStep none{};
+    if (x_dtype == P4C_F32) ar_stage_kernel<float, float><<<grid, 256, stage_smem, st>>>(none, *a, (float*)x, 0);
+    else ar_stage_kernel<float, __nv_bfloat16><<<grid, 256, stage_smem, st>>>(none, *a, (__nv_bfloat16*)x, 0);
+    P4C_CHECK_LAUNCH("ar_concat(staged)");
+    return P4C_OK;
+  }
   if (tile_smem <= 48 * 1024 && a->batch <= 65535) {
     const dim3 grid((a->nodes + AR_TN - 1) / AR_TN, a->batch);
     ArStep none{};
@@ -680,6 +902,20 @@ extern "C" int p4c_ar_step_forward(const void* y, int y_dtype, const float* prev
   const int grid = grid_for(total, 256);
   const int ld = next->x_ld > 0 ? next->x_ld : f_in;
   const size_t tile_smem = (size_t)AR_TN * ld * sizeof(float);
+  size_t stage_smem = 0;
+  if (ar_stage_ok(next, x_next, x_dtype, &s, y_dtype, &stage_smem)) {
+    const dim3 tg(nodes / AR_TN, batch);
+    if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
+      ar_stage_kernel<float, float><<<tg, 256, stage_smem, st>>>(s, *next, (float*)x_next, 1);
+    else if (y_dtype == P4C_F32 && x_dtype == P4C_BF16)
+      ar_stage_kernel<float, __nv_bfloat16><<<tg, 256, stage_smem, st>>>(s, *next, (__nv_bfloat16*)x_next, 1);
+    else if (y_dtype == P4C_BF16 && x_dtype == P4C_F32)
+      ar_stage_kernel<__nv_bfloat16, float><<<tg, 256, stage_smem, st>>>(s, *next, (float*)x_next, 1);
+    else
+      ar_stage_kernel<__nv_bfloat16, __nv_bfloat16><<<tg, 256, stage_smem, st>>>(s, *next, (__nv_bfloat16*)x_next, 1);
+    P4C_CHECK_LAUNCH("ar_step(staged)");
+    return P4C_OK;
+  }
   if (tile_smem <= 48 * 1024 && batch <= 65535) {
     const dim3 tg((nodes + AR_TN - 1) / AR_TN, batch);
     if (y_dtype == P4C_F32 && x_dtype == P4C_F32)
@@ -723,6 +959,22 @@ extern "C" int p4c_ar_step_backward(const float* g_new, int64_t g_new_bs, const 
   const int grid = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   const bool xb = g_xnext && x_dtype == P4C_BF16;
+  {
+    const long long per_b = (long long)nodes * f_state;
+    bool vec = g_ar_vector_paths && per_b % 4 == 0 && per_b < (1ll << 31) && batch <= 65535 && ar_al16(dy) && (!g_new || (ar_al16(g_new) && g_new_bs % 4 == 0)) &&
+               (!g_new2 || (ar_al16(g_new2) && g_new2_bs % 4 == 0)) && (y_dtype == P4C_F32 || y_dtype == P4C_BF16);
+    for (int t = 0; t < num_prev; ++t) vec = vec && (!s.d_prev[t] || ar_al16(s.d_prev[t]));
+    if (vec) {
+      const unsigned long long magic = (~0ull / (unsigned long long)f_state) + 1ull;  // ceil(2^64 / F): exact for 32-bit dividends
+      const dim3 vg((unsigned)((per_b / 4 + 255) / 256), (unsigned)batch);
+      if (y_dtype == P4C_F32 && !xb) ar_step_bwd_vec_kernel<float, float><<<vg, 256, 0, st>>>(s, magic);
+      else if (y_dtype == P4C_F32 && xb) ar_step_bwd_vec_kernel<float, __nv_bfloat16><<<vg, 256, 0, st>>>(s, magic);
+      else if (y_dtype == P4C_BF16 && !xb) ar_step_bwd_vec_kernel<__nv_bfloat16, float><<<vg, 256, 0, st>>>(s, magic);
+      else ar_step_bwd_vec_kernel<__nv_bfloat16, __nv_bfloat16><<<vg, 256, 0, st>>>(s, magic);
+      P4C_CHECK_LAUNCH("ar_step_bwd(vec)");
+      return P4C_OK;
+    }
+  }
   if (y_dtype == P4C_F32 && !xb) ar_step_bwd_kernel<float, float><<<grid, 256, 0, st>>>(s);
   else if (y_dtype == P4C_F32 && xb) ar_step_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(s);
   else if (y_dtype == P4C_BF16 && !xb) ar_step_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(s);

@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         float v[32];
         tmem_ld32(tm_ch, v);
         tmem_ld_wait();
+        P4C_WB_TRACE(trc, 13);
         tc_fence_before();
         const f32x2 half2 = f2_dup(0.5f);
 #pragma unroll
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         float xh[32];
         tmem_ld32(tm_ch, xh);
         tmem_ld_wait();
+        P4C_WB_TRACE(trc, 14);
         tc_fence_before();
         // fp32 pairs: two elements per instruction; the four row sums are kept as (even, odd) column pairs
         f32x2 X2[16];
@@ -735,6 +737,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         float v[32];
         tmem_ld32(tm_dx + s * WB_HID, v);
         tmem_ld_wait();
+        P4C_WB_TRACE(trc && s == 0, 11);
         const int kblk = a.slot_blk[s];
         if (a.slot_kind[s] == 0) {
           const int src = a.kb.src[kblk];
@@ -845,6 +848,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
           }
         }
       }
+      P4C_WB_TRACE(trc, 12);
       if (nslot > 0) {
         tc_fence_before();
         __syncwarp();

@@ -293,3 +293,68 @@ def test_validation_and_test_steps_vs_reference_golden(cuda, name):
     smap = ar_ref.weighted_loss(pred, tgt, ones, w, interior, interior.sum().item(), reduce_spatial_dim=False)
     assert tst["spatial_loss"].shape == (s["B"], s["T"], s["H"], s["W"])
     assert_close(tst["spatial_loss"].cpu().flatten(2, 3), smap, FP32_TOL, f"{name} spatial loss map")
+
+
+@pytest.mark.parametrize("T_in,x_dtype,y_dtype,scaled,border", [
+    (2, torch.bfloat16, torch.bfloat16, False, False),   # the benchmarked configuration (diff_ar, bf16-true)
+    (2, torch.bfloat16, torch.bfloat16, True, True),     # scaled_ar with the border blend
+    (3, torch.float32, torch.float32, True, True),       # three input steps: the middle d_prev comes from g_xnext
+    (1, torch.bfloat16, torch.float32, False, True),
+])
+def test_staged_ar_kernels_equal_the_scalar_ones_bit_for_bit(cuda, T_in, x_dtype, y_dtype, scaled, border):
+    """The cp.async-staged concat / step kernel and the vectorised step backward (nodes % 64 == 0, aligned arrays)
+    against the scalar kernels they replace (p4c_set_ar_vector_paths(0)): every output bit-identical; and against
+    plain torch (reference lightning.py:598-633, 711-767) within fp32 rounding."""
+    from py4cast_b200 import _lib
+    from py4cast_b200 import lightning as L
+
+    lib = _lib.load()
+    B, N, F, Fs, Ff = 3, 64 * 7, 21, 4, 21
+    g = torch.Generator().manual_seed(T_in * 7 + int(scaled))
+    prevs = [torch.randn(B, N, F, generator=g).to(cuda) for _ in range(T_in)]
+    static = torch.randn(N, Fs, generator=g).to(cuda)
+    forcing0 = torch.randn(B, N, Ff, generator=g).to(cuda)
+    forcing1 = torch.randn(B, N, Ff, generator=g).to(cuda)
+    truth = torch.randn(B, N, F, generator=g).to(cuda)
+    bmask = (torch.rand(N, generator=g) < 0.3).float().to(cuda)
+    std = (torch.rand(F, generator=g) + 0.5).to(cuda)
+    mean = torch.randn(F, generator=g).to(cuda)
+    yv = torch.randn(B, N, F, generator=g).to(cuda).to(y_dtype)
+    g_state = torch.randn(B, N, F, generator=g).to(cuda)
+
+    def run():
+        x0 = L.ar_concat(prevs, static, forcing0, x_dtype)
+        ps = [p.clone().requires_grad_(True) for p in prevs]
+        y = yv.clone().requires_grad_(True)
+        cfg = {"truth": truth if border else None, "border": bmask if border else None,
+               "std": std if scaled else None, "mean": mean if scaled else None,
+               "new_state": torch.empty(B, N, F, device=cuda), "forcing_next": forcing1, "static": static,
+               "x_dtype": x_dtype}
+        new_state, x1 = L._ARStepFn.apply(cfg, y, *ps)
+        g_x = torch.randn(x1.shape, generator=torch.Generator().manual_seed(1)).to(cuda).to(x1.dtype)
+        torch.autograd.backward([new_state, x1], [g_state, g_x])
+        outs = [x0, new_state, x1, y.grad] + [p.grad for p in ps if p.grad is not None]
+        return [o.detach().clone() for o in outs]
+
+    try:
+        lib.p4c_set_ar_vector_paths(0)
+        scalar = run()
+        lib.p4c_set_ar_vector_paths(1)
+        staged = run()
+    finally:
+        lib.p4c_set_ar_vector_paths(1)
+    assert len(scalar) == len(staged)
+    for i, (a, b) in enumerate(zip(scalar, staged)):
+        assert a.shape == b.shape and a.stride() == b.stride()
+        assert torch.equal(a, b), f"output {i}: staged / vectorised kernel differs from the scalar kernel"
+    # plain-torch reference of the forward
+    pred = prevs[-1] + (yv.float() * std + mean if scaled else yv.float())
+    if border:
+        pred = bmask[None, :, None] * truth + (1 - bmask[None, :, None]) * pred
+    assert_close(staged[1], pred, FP32_TOL, "new state vs torch")
+    x1_ref = torch.cat(prevs[1:] + [pred, static.expand(B, -1, -1), forcing1], dim=-1)
+    f_in = x1_ref.shape[-1]
+    assert_close(staged[2][..., :f_in].float(), x1_ref.to(x_dtype).float(), 1e-2 if x_dtype == torch.bfloat16 else FP32_TOL,
+                 "x_next vs torch")
+    assert torch.equal(staged[0][..., :f_in],
+                       torch.cat(prevs + [static.expand(B, -1, -1), forcing0], dim=-1).to(x_dtype)), "concat is a pure copy"
