@@ -139,7 +139,7 @@ typedef struct {
  * a source of width w contributes ceil(w/64) blocks (columns beyond w are zero).
  * p4c_pack_weights converts `n` MLPs in ONE launch from a DEVICE table of descriptors.
  * ---------------------------------------------------------------------- */
-#define P4C_PACK_BYTES (8 * 8192 + 4 * 64 * 4)
+#define P4C_PACK_BYTES (9 * 8192 + 4 * 64 * 4)
 typedef struct {
   const float* w1; const float* b1; const float* w2; const float* b2;
   const float* gamma; const float* beta; /* NULL -> 1 / 0 */

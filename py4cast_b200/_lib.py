@@ -90,7 +90,7 @@ class MlpBwd(C.Structure):
     ]
 
 
-PACK_BYTES = 8 * 8192 + 4 * 64 * 4
+PACK_BYTES = 9 * 8192 + 4 * 64 * 4
 
 
 class Pack(C.Structure):

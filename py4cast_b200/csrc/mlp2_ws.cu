@@ -54,12 +54,16 @@ struct WsSmem {
   uint8_t A2[2][WS_XBLK];
   uint8_t W1[P4C_MAX_SRC][WS_WBLK];
   uint8_t W2[WS_WBLK];
+  uint8_t WBIAS[WS_WBLK];  // bias tile of the weight image (PK_BIAS): b1 in K-slice 0, b2 in K-slice 1
+  uint8_t ONES[2048];      // 16 K-rows x 64 M of bf16 ones: the all-ones A operand of the bias products
   float vec[4][WS_HID];  // b1, b2, gamma, beta
   float2 ln_part[2][2][WS_TM];  // [group][column half][row]: LayerNorm partial (sum, sum of squares)
   uint64_t x_full[WS_NS], x_empty[WS_NS];
   uint64_t d1_full[2], a2_full[2], d2_full[2], d2_empty[2];
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(WsSmem) + 1024 <= 232448, "pipelined forward: shared memory beyond the 227 KB a CTA can opt into");
 
 struct WsArgs {
   p4c_mlp_t m;
@@ -112,9 +116,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     for (int i = tid; i < nblk * (WS_WBLK / 16); i += WS_THREADS)
       cp_async16(smem_u32(S.W1) + i * 16, img + PK_W1 + i * 16, 16u);
     for (int i = tid; i < WS_WBLK / 16; i += WS_THREADS) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
+    for (int i = tid; i < WS_WBLK / 16; i += WS_THREADS) cp_async16(smem_u32(S.WBIAS) + i * 16, img + PK_BIAS + i * 16, 16u);
     if (tid < 64) cp_async16(smem_u32(S.vec) + tid * 16, img + PK_VEC + tid * 16, 16u);
     cp_async_commit();
   }
+  if (tid < 2048 / 16)
+    reinterpret_cast<uint4*>(S.ONES)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (tid == 0) {
     for (int i = 0; i < WS_NS; ++i) {
       mbar_init(&S.x_full[i], WS_PROD_WARPS);
@@ -236,6 +243,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       constexpr uint32_t IDESC = make_idesc_bf16(WS_TM, WS_HID, 0, 0);
       constexpr long long KSTEP = 2;  // 32 bytes = K 16 bf16 columns, in descriptor address units
       const uint64_t w2d = make_desc_sw128(smem_u32(S.W2), 16, 1024);
+      // biases inside the products (see PK_BIAS): all-ones A (MN-major, both 64-wide M blocks at the ONES rows)
+      // times K-slice 0 (b1 hi, lo) / 1 (b2 hi, lo) of the bias tile -- the epilogues neither load nor add them
+      constexpr uint32_t IDESC_MK = make_idesc_bf16(WS_TM, WS_HID, 1, 0);
+      const uint64_t ones_mn = make_desc_sw128(smem_u32(S.ONES), 0, 1024), wb_k = make_desc_sw128(smem_u32(S.WBIAS), 16, 1024);
       for (uint32_t t = 0; t <= ntl; ++t) {
         if (t < ntl) {
           const uint32_t s = t % WS_NS, n = t / WS_NS, buf = t & 1u;
@@ -249,6 +260,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
               mma_bf16_ss_elect(tmem + buf * WS_HID, xd, wd, IDESC, acc);
           }
           mma_commit_elect(&S.x_empty[s]);
+          mma_bf16_ss_elect(tmem + buf * WS_HID, ones_mn, wb_k, IDESC_MK, acc);  // + b1
           mma_commit_elect(&S.d1_full[buf]);
         }
         if (t >= 1) {
@@ -260,6 +272,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             mma_bf16_ss_elect(tmem + 2 * WS_HID + buf * WS_HID, ad + q * KSTEP, w2d + q * KSTEP, IDESC, q ? 1u : 0u);
+          mma_bf16_ss_elect(tmem + 2 * WS_HID + buf * WS_HID, ones_mn, wb_k + KSTEP, IDESC_MK, 1u);  // + b2
           mma_commit_elect(&S.d2_full[buf]);
         }
       }
@@ -279,8 +292,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
     __nv_bfloat16* const save_h1 = AGGR_ONLY ? nullptr : a.save_h1;
     __nv_bfloat16* const out = AGGR_ONLY ? nullptr : a.out;
     __nv_bfloat16* const out2 = AGGR_ONLY ? nullptr : a.out2;
-    const float* const b1 = S.vec[0] + col0;
-    const float* const b2 = S.vec[1] + col0;
     const float* const gamma = S.vec[2] + col0;
     const float* const beta = S.vec[3] + col0;
     pdl_wait();
@@ -312,14 +323,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         tc_fence_before();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           float h[8];
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 0], v[c * 8 + 1]), f2_pack(ba.x, ba.y)), h[0], h[1]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 2], v[c * 8 + 3]), f2_pack(ba.z, ba.w)), h[2], h[3]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 4], v[c * 8 + 5]), f2_pack(bb.x, bb.y)), h[4], h[5]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 6], v[c * 8 + 7]), f2_pack(bb.z, bb.w)), h[6], h[7]);
-          const uint4 hb = ws_pack8(h);
+          const uint4 hb = ws_pack8(v + c * 8);  // D1 holds X W1^T + b1
           ws_unpack8(hb, h);
           silu8_pairs(h);
           sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
@@ -335,12 +340,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
-            const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
-            float h[8];
-            h[0] = v[c * 8 + 0] + ba.x; h[1] = v[c * 8 + 1] + ba.y; h[2] = v[c * 8 + 2] + ba.z; h[3] = v[c * 8 + 3] + ba.w;
-            h[4] = v[c * 8 + 4] + bb.x; h[5] = v[c * 8 + 5] + bb.y; h[6] = v[c * 8 + 6] + bb.z; h[7] = v[c * 8 + 7] + bb.w;
-            sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(h));
+            sts128(a2 + sw128_offset(row, hsel * 4 + c), ws_pack8(v + c * 8));  // D1 holds X W1^T + b1
           }
         }
         tc_fence_before();
@@ -382,13 +382,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.d2_empty[grp]);  // D2 is in registers: G2 of tile t + 2 may overwrite it
-      // fp32 pairs (FADD2 / FFMA2): two columns per instruction
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 bv = *reinterpret_cast<const float4*>(b2 + c * 4);
-        f2_unpack(f2_add(f2_pack(y[c * 4 + 0], y[c * 4 + 1]), f2_pack(bv.x, bv.y)), y[c * 4 + 0], y[c * 4 + 1]);
-        f2_unpack(f2_add(f2_pack(y[c * 4 + 2], y[c * 4 + 3]), f2_pack(bv.z, bv.w)), y[c * 4 + 2], y[c * 4 + 3]);
-      }
+      // (D2 holds a1 W2^T + b2)  fp32 pairs (FADD2 / FFMA2): two columns per instruction
       if (!NARROW && (AGGR_ONLY || m.layer_norm)) {
         f32x2 ps2[2] = {0ull, 0ull}, pq2[2] = {0ull, 0ull};  // (ps[0], ps[1]), (ps[2], ps[3]) of the scalar form
 #pragma unroll
@@ -413,6 +407,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const float rstd = rsqrtf(var + m.ln_eps);
         const float nm = -mean * rstd;
         const f32x2 rstd2 = f2_dup(rstd), nm2 = f2_dup(nm);
+        if constexpr (AGGR_ONLY) {
+          // only the sum over the rows of a group leaves this kernel: sum_rows (xhat gamma + beta) =
+          // gamma sum_rows xhat + group beta -- the affine part is applied to the few columns a lane keeps after
+          // the group sums (2 + 2 vector loads per thread instead of 8 + 8 broadcast ones, 8 instead of 32 FMAs)
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            f2_unpack(f2_fma(f2_pack(y[2 * c], y[2 * c + 1]), rstd2, nm2), y[2 * c], y[2 * c + 1]);
+        } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 gv = *reinterpret_cast<const float4*>(gamma + c * 4);
@@ -422,16 +424,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           f2_unpack(f2_fma(f2_fma(f2_pack(y[c * 4 + 2], y[c * 4 + 3]), rstd2, nm2), f2_pack(gv.z, gv.w), f2_pack(bv.z, bv.w)),
                     y[c * 4 + 2], y[c * 4 + 3]);
         }
+        }
         if (!AGGR_ONLY && a.save_stats && orow >= 0 && hsel == 0)
           *reinterpret_cast<float2*>(a.save_stats + 2ll * orow) = make_float2(mean, rstd);
       }
       if constexpr (NARROW) {
         // Narrow output (no LayerNorm; columns >= out_width of y are zero): rows are out_width * 2 bytes and a
         // tile's rows are contiguous in `out`.  Compact [row][out_width] bf16 image of the row quad in the (free)
-        // A2 tile, then the 64 threads that own the quad copy its bytes with 16-byte stores.
+        // A2 tile, then the 64 threads that own the quad copy its bytes with 16-byte stores.  The image lives in
+        // the 4 KB of the tile that hold the quad's OWN rows: the only other writers of those bytes are the same
+        // two warps (epilogue 1 of their next tile), which the pair barriers order.  (Packed back to back, the
+        // images of quads 1-3 sat in the rows of quads 0 / 1, whose warps may already be writing a1 of the next
+        // tile: a race that corrupted the last chunks of a quad once epilogue 1 got faster.)
         const int OW = a.out_width;
-        uint8_t* const ct = S.A2[grp];
-        __nv_bfloat16* const crow = reinterpret_cast<__nv_bfloat16*>(ct) + row * OW + col0;
+        uint8_t* const ct = S.A2[grp] + quad * 4096;
+        __nv_bfloat16* const crow = reinterpret_cast<__nv_bfloat16*>(ct) + lane * OW + col0;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
           if (col0 + c < OW) crow[c] = __float2bfloat16_rn(y[c]);
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
         const uint32_t q0 = blk * WS_TM + static_cast<uint32_t>(quad * 32);  // first row of the quad
         const int nv = q0 < rows ? static_cast<int>(rows - q0 < 32u ? rows - q0 : 32u) : 0;
         const int nbytes = nv * OW * 2;
-        const uint8_t* const src = ct + quad * 32 * OW * 2;
+        const uint8_t* const src = ct;
         uint8_t* const dst = reinterpret_cast<uint8_t*>(out) +
                              (static_cast<long long>(tile - blk * nbatch) * full + q0) * OW * 2;
         for (int i = (hsel * 32 + lane) * 16; i < nbytes; i += 64 * 16) {
@@ -528,10 +535,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
           const int ncol = 32 / gsz;
           __nv_bfloat16* dst = a.aggr_out + static_cast<long long>(orow / gsz) * WS_HID + col0 + cbase;
           const float sc = a.agg_scale;
+          const float gb = static_cast<float>(gsz);
           if (ncol >= 8) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (c < ncol / 8) {
+                if constexpr (AGGR_ONLY) {  // affine part of the LayerNorm on the group sums (see above)
+                  const float4 g0 = *reinterpret_cast<const float4*>(gamma + cbase + c * 8);
+                  const float4 g1 = *reinterpret_cast<const float4*>(gamma + cbase + c * 8 + 4);
+                  const float4 b0 = *reinterpret_cast<const float4*>(beta + cbase + c * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(beta + cbase + c * 8 + 4);
+                  float* yy = y + c * 8;
+                  yy[0] = fmaf(yy[0], g0.x, gb * b0.x); yy[1] = fmaf(yy[1], g0.y, gb * b0.y);
+                  yy[2] = fmaf(yy[2], g0.z, gb * b0.z); yy[3] = fmaf(yy[3], g0.w, gb * b0.w);
+                  yy[4] = fmaf(yy[4], g1.x, gb * b1.x); yy[5] = fmaf(yy[5], g1.y, gb * b1.y);
+                  yy[6] = fmaf(yy[6], g1.z, gb * b1.z); yy[7] = fmaf(yy[7], g1.w, gb * b1.w);
+                }
                 float e[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) e[q] = y[c * 8 + q] * sc;
@@ -539,11 +558,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp2_ws_fwd_kernel(const __grid
               }
             }
           } else if (ncol == 4) {
+            if constexpr (AGGR_ONLY) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) y[q] = fmaf(y[q], gamma[cbase + q], gb * beta[cbase + q]);
+            }
             uint2 o;
             o.x = pack_bf16x2(y[0] * sc, y[1] * sc);
             o.y = pack_bf16x2(y[2] * sc, y[3] * sc);
             *reinterpret_cast<uint2*>(dst) = o;
           } else {
+            if constexpr (AGGR_ONLY) {
+              y[0] = fmaf(y[0], gamma[cbase], gb * beta[cbase]);
+              y[1] = fmaf(y[1], gamma[cbase + 1], gb * beta[cbase + 1]);
+            }
             *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(y[0] * sc, y[1] * sc);
           }
         }

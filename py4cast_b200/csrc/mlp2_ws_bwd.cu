@@ -72,6 +72,7 @@ struct WbSmem {
   uint8_t DH[2][WB_BLK];
   uint8_t W1[P4C_MAX_SRC][WB_WBLK];
   uint8_t W2[WB_WBLK];
+  uint8_t WBIAS[WB_WBLK];  // bias tile of the weight image (PK_BIAS): b1 in K-slice 0, b2 in K-slice 1
   uint8_t ONES[WB_ONES_BYTES];
   float vec[4][WB_HID];  // b1, b2, gamma, beta
   float4 ln_part[2][2][WB_TM];  // [group][column half][row]
@@ -82,6 +83,8 @@ struct WbSmem {
   uint64_t bs_empty;                // the batch-summed dX of a row block was read (compute group -> MMA warps)
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(WbSmem) + 1024 <= 232448, "pipelined backward: shared memory beyond the 227 KB a CTA can opt into");
 
 struct WbArgs {
   p4c_mlp_t m;
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     for (int i = tid; i < nblk * (WB_WBLK / 16); i += WB_THREADS)
       cp_async16(smem_u32(S.W1) + i * 16, img + PK_W1 + i * 16, 16u);
     for (int i = tid; i < WB_WBLK / 16; i += WB_THREADS) cp_async16(smem_u32(S.W2) + i * 16, img + PK_W2 + i * 16, 16u);
+    for (int i = tid; i < WB_WBLK / 16; i += WB_THREADS) cp_async16(smem_u32(S.WBIAS) + i * 16, img + PK_BIAS + i * 16, 16u);
     if (tid < 64) cp_async16(smem_u32(S.vec) + tid * 16, img + PK_VEC + tid * 16, 16u);
     cp_async_commit();
   }
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       constexpr uint32_t IDESC_KK = make_idesc_bf16(WB_TM, WB_HID, 0, 0);  // A, B K-major
       constexpr uint32_t IDESC_KM = make_idesc_bf16(WB_TM, WB_HID, 0, 1);  // A K-major, B MN-major
       constexpr uint32_t IDESC_MM = make_idesc_bf16(WB_TM, WB_HID, 1, 1);  // A, B MN-major
+      constexpr uint32_t IDESC_MK = make_idesc_bf16(WB_TM, WB_HID, 1, 0);  // A MN-major (all ones), B K-major
       constexpr long long KSTEP = 2, MNSTEP = 128;
       // [tile rows | ONES] as an MN-major M = 128 operand: the address moves on, the ONES block does not
       constexpr long long ONES_STEP = MNSTEP - (MNSTEP << 16);
@@ -348,6 +353,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
       const uint64_t w2_mn = make_desc_sw128(smem_u32(S.W2), WB_WBLK, 1024);
       const uint64_t a1_k = make_desc_sw128(a1, 16, 1024), a1_ones = make_desc_sw128(a1, ones - a1, 1024);
       const uint64_t dh_k = make_desc_sw128(da, 16, 1024), dh_mn = make_desc_sw128(da, WB_BLK, 1024);
+      // biases inside the products: [1 ... 1] (M = 128 x K = 16 of ones, both 64-wide M blocks at the ONES rows)
+      // times K-slice 0 (b1 hi, lo) / 1 (b2 hi, lo) of the bias tile
+      const uint64_t ones_mn = make_desc_sw128(ones, 0, 1024), wb_k = make_desc_sw128(smem_u32(S.WBIAS), 16, 1024);
       for (uint32_t n = 0, t = c; t < ntl; ++n, t += 2) {
         const uint32_t par = n & 1u;
         const uint32_t xst = t % xns, xpar = (t / xns) & 1u;  // X ring stage of the tile
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
             const int nk = (a.kb.kvalid[k] + 15) >> 4;
             for (int q = 0; q < nk; ++q, xd += KSTEP, wd += KSTEP, acc = 1u) mma_bf16_ss_elect(ch, xd, wd, IDESC_KK, acc);
           }
+          mma_bf16_ss_elect(ch, ones_mn, wb_k, IDESC_MK, acc);  // + b1
         }
         mma_commit_elect(&S.h1_full[c]);
         P4C_WB_TRACE(trc && lane == 0, 16);
@@ -377,6 +386,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 4; ++q) mma_bf16_ss_elect(ch, a1_k + q * KSTEP, w2_k + q * KSTEP, IDESC_KK, q ? 1u : 0u);
+        mma_bf16_ss_elect(ch, ones_mn, wb_k + KSTEP, IDESC_MK, 1u);  // + b2
         mma_commit_elect(&S.h2_full[c]);
         P4C_WB_TRACE(trc && lane == 0, 17);
 
@@ -477,8 +487,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
     const uint32_t tm_ch = tm_lane + WB_COL_CH + grp * WB_HID + col0;
     const uint32_t tm_dx = tm_lane + WB_COL_DX + (dx_shared ? 0u : grp * WB_HID) + col0;
     const int pair_bar = 1 + grp * 4 + quad;  // named barrier of the two warps that share these rows
-    const float* const b1 = S.vec[0] + col0;
-    const float* const b2 = S.vec[1] + col0;
     const float* const gamma = S.vec[2] + col0;
     const __nv_bfloat16* const dya = reinterpret_cast<const __nv_bfloat16*>(g.dy_a);
     const __nv_bfloat16* const dyb = reinterpret_cast<const __nv_bfloat16*>(g.dy_b);
@@ -523,14 +531,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         const f32x2 half2 = f2_dup(0.5f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           float h[8];
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 0], v[c * 8 + 1]), f2_pack(ba.x, ba.y)), h[0], h[1]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 2], v[c * 8 + 3]), f2_pack(ba.z, ba.w)), h[2], h[3]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 4], v[c * 8 + 5]), f2_pack(bb.x, bb.y)), h[4], h[5]);
-          f2_unpack(f2_add(f2_pack(v[c * 8 + 6], v[c * 8 + 7]), f2_pack(bb.z, bb.w)), h[6], h[7]);
-          const uint4 hb = ws_pack8(h);  // the forward kept h1 in bf16: same rounding, same a1
+          const uint4 hb = ws_pack8(v + c * 8);  // b1 came with the product; the forward kept h1 in bf16: same rounding
           ws_unpack8(hb, h);
           float sg8[8];
 #pragma unroll
@@ -592,13 +594,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) mlp2_ws_bwd_kernel(const __grid
         for (int c = 0; c < 4; ++c) {
           float d[8];
           ws_unpack8(dyr[c], d);
-          const float4 ba = *reinterpret_cast<const float4*>(b2 + c * 8), bb = *reinterpret_cast<const float4*>(b2 + c * 8 + 4);
           const float4 ga = *reinterpret_cast<const float4*>(gamma + c * 8), gb = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
-          const f32x2 bp[4] = {f2_pack(ba.x, ba.y), f2_pack(ba.z, ba.w), f2_pack(bb.x, bb.y), f2_pack(bb.z, bb.w)};
           const f32x2 gp[4] = {f2_pack(ga.x, ga.y), f2_pack(ga.z, ga.w), f2_pack(gb.x, gb.y), f2_pack(gb.z, gb.w)};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const f32x2 x = f2_add(f2_pack(xh[c * 8 + 2 * q], xh[c * 8 + 2 * q + 1]), bp[q]);
+            const f32x2 x = f2_pack(xh[c * 8 + 2 * q], xh[c * 8 + 2 * q + 1]);  // h2 (b2 came with the product)
             X2[c * 4 + q] = x;
             const f32x2 dg = f2_mul(f2_pack(d[2 * q], d[2 * q + 1]), gp[q]);
             s1p = f2_add(s1p, x);

@@ -17,7 +17,7 @@ namespace p4c {
 constexpr int HIDP = P4C_HIDDEN;
 
 // ------------------------------------------------------------------------------ weight images
-// grid (n, 8): blockIdx.y = 8 KB block of the image (0-2 W1, 3 W2, 4 W2T, 5-7 W1T); y == 0 also
+// grid (n, 9): blockIdx.y = 8 KB block of the image (0-2 W1, 3 W2, 4 W2T, 5-7 W1T, 8 bias tile); y == 0 also
 // writes the vectors.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const p4c_pack_t* __restrict__ table) {
   const p4c_pack_t e = table[blockIdx.x];
@@ -25,12 +25,19 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const p4c_pack_t* __r
   uint8_t* img = reinterpret_cast<uint8_t*>(e.dst);
   tc::KBlocks kb;
   tc::make_kblocks(e.nsrc, e.width, &kb);
-  uint8_t* dst = img + y * 8192;
+  uint8_t* dst = y < 8 ? img + y * 8192 : img + tc::PK_BIAS;
   const int OUT = e.out_features;
   for (int i = tid; i < HIDP * HIDP; i += 256) {
     const int n = i >> 6, kk = i & 63;  // image element [n][kk]
     float v = 0.f;
-    if (y < 3) {  // W1 block y: [n = hidden unit][kk = input column of the block]
+    if (y == 8) {  // bias tile: hi / lo halves of b1 (k = 0, 1) and b2 (k = 16, 17)
+      const int slice = kk >> 4, part = kk & 15;
+      if (slice < 2 && part < 2 && (slice == 0 || n < OUT)) {
+        const float b = slice == 0 ? e.b1[n] : e.b2[n];
+        const float hi = __bfloat162float(__float2bfloat16_rn(b));
+        v = part == 0 ? hi : b - hi;
+      }
+    } else if (y < 3) {  // W1 block y: [n = hidden unit][kk = input column of the block]
       if (y < kb.nblk && kk < kb.kvalid[y]) v = e.w1[static_cast<long long>(n) * e.k1 + kb.kstart[y] + kk];
     } else if (y == 3) {  // W2: [n = output unit][kk = hidden unit]
       if (n < OUT) v = e.w2[n * HIDP + kk];
@@ -317,7 +324,7 @@ using namespace p4c;
 extern "C" int p4c_pack_weights(const p4c_pack_t* table_dev, int32_t n, void* stream) {
   P4C_REQUIRE(n >= 0 && (n == 0 || table_dev), "pack_weights: bad arguments");
   if (n == 0) return P4C_OK;
-  pack_weights_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  pack_weights_kernel<<<dim3(n, 9), 256, 0, (cudaStream_t)stream>>>(table_dev);
   P4C_CHECK_LAUNCH("pack_weights");
   pdl_block_next();  // the images are read before griddepcontrol.wait
   return P4C_OK;

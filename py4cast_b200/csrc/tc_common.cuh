@@ -568,7 +568,12 @@ constexpr int PK_W2 = 3 * 8192;          // [n = output unit][k = hidden]     (f
 constexpr int PK_W2T = 4 * 8192;         // [n = hidden][k = output unit]     (bwd: da1 = dh2 W2)
 constexpr int PK_W1T = 5 * 8192;         // 3 x 8 KB  [n = input col][k = hidden unit]  (bwd: dX = dh1 W1)
 constexpr int PK_VEC = 8 * 8192;         // b1, b2, gamma, beta (4 x 64 fp32)
-static_assert(PK_VEC + 4 * 64 * 4 == P4C_PACK_BYTES, "weight image layout");
+// bias tile [n][k] (8 KB, same layout as a W1 block): b1[n] as bf16 hi + lo at k = 0, 1 (K-slice 0) and b2[n] at
+// k = 16, 17 (K-slice 1), zeros elsewhere.  One extra MMA per GEMM with an all-ones A operand adds the bias inside
+// the product (hi + lo = the fp32 bias to 2^-17 relative): the row-per-thread epilogues then neither load the bias
+// vectors from shared memory (a broadcast 16-byte load costs four wavefronts of the L1 data pipe per warp) nor add them.
+constexpr int PK_BIAS = 8 * 8192 + 4 * 64 * 4;
+static_assert(PK_BIAS + 8192 == P4C_PACK_BYTES, "weight image layout");
 
 }  // namespace tc
 }  // namespace p4c

@@ -47,5 +47,5 @@ for label, es, upd in (("same[0]", graph.m2m[0], True), ("up[1]", graph.mesh_up[
         print("   tile ends (group 0): " + ", ".join(f"+{v-t[48]}" for v in t[58:64] if v))
         if t[0]:
             print("   tile 2 : " + ", ".join(f"{n}:+{t[i]-t[48]}" for i, n in enumerate(CNAMES) if t[i]))
-            extra = {13: "a: TMEM load done", 14: "c: TMEM load done", 11: "g: first TMEM load done", 12: "g: slots done"}
+            extra = {13: "a: TMEM load done", 14: "c: TMEM load done", 11: "g: first TMEM load done", 15: "g: group sums done", 12: "g: slots done"}
             print("   tile 2 (inside the phases): " + ", ".join(f"{n}:+{t[i]-t[48]}" for i, n in extra.items() if t[i]))

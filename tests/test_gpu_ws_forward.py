@@ -109,7 +109,9 @@ def test_narrow_output_without_layernorm(lib, cuda, rows, batch, out):
         yr = ref(x)
     assert wsr.shape == (batch, rows, out)
     assert_close(wsr, yr, BF16_TOL, "pipelined vs oracle")
-    assert torch.equal(wsr, mono), "same arithmetic, same rounding as the monolithic kernel"
+    # the pipelined kernel adds the biases inside its products (bf16 hi + lo rows of the bias tile, 2^-17 relative),
+    # the monolithic one in its epilogue: equal up to the last bf16 bit of a few elements
+    assert_close(wsr, mono, 4e-3, "pipelined vs monolithic")
 
 
 def _uniform_graph(nr, ns, deg, seed):
