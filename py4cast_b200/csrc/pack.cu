@@ -255,14 +255,14 @@ __global__ void __launch_bounds__(256, 2) seg_linear_tc_kernel(const __grid_cons
     if (!PAIR) {
       // tiles of at most 16 rows (long segments: m2g by sender) leave half of a thread's four items idle: two items,
       // four rows each per iteration keep eight row loads in flight (same summation order)
-      if (TR <= 16) seg_sum_tile<256, 2, 4>(a.src, a.p[0].perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
-      else seg_sum_tile<256>(a.src, a.p[0].perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+      if (TR <= 16) seg_sum_tile<256, 2, 4, true>(a.src, a.p[0].perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+      else seg_sum_tile<256, 4, 2, true>(a.src, a.p[0].perm, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
     }
-    else if (perm0) seg_sum_tile<256>(a.src, perm0, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
-    else seg_sum_tile<256>(a.src, nullptr, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+    else if (perm0) seg_sum_tile<256, 4, 2, true>(a.src, perm0, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
+    else seg_sum_tile<256, 4, 2, true>(a.src, nullptr, S.lo, S.hi, S.sbase, S.sc, S.orow, S.A, nullptr, tid, TR);
     if (PAIR && nsum == 2) {
-      if (perm1) seg_sum_tile<256>(a.src, perm1, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
-      else seg_sum_tile<256>(a.src, nullptr, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
+      if (perm1) seg_sum_tile<256, 4, 2, true>(a.src, perm1, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
+      else seg_sum_tile<256, 4, 2, true>(a.src, nullptr, S1.lo, S1.hi, S1.sbase, S1.sc, S.orow, S1.A, nullptr, tid, TR);
     }
     cp_async_wait<0>();  // the weight blocks (first tile)
     fence_proxy_async();

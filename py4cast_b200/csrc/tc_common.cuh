@@ -344,7 +344,9 @@ __device__ __forceinline__ void seg_add8(float* s, const uint4& u) {
 // tiles of at most 16 rows with 256 threads use PV = 2); U: source rows per item and iteration.  The gather
 // indices of iteration i + 1 are loaded while the rows of iteration i are in flight (one dependent latency per
 // iteration instead of two); the rows of a segment are added in the same order whatever PV / U.
-template <int NTHREADS, int PV = 1024 / NTHREADS, int U = 2>
+// PREFETCH = false keeps the index loads at the top of the iteration (the forward's aggregation prologue: short
+// segments, 128 registers already in use -- the prefetch registers spilled there and cost 20 %).
+template <int NTHREADS, int PV = 1024 / NTHREADS, int U = 2, bool PREFETCH = false>
 __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ perm,
                                              const uint32_t* lo, const uint32_t* hi, const uint32_t* sbase,
                                              const float* sc, const int32_t* orow, uint8_t* X,
@@ -383,10 +385,11 @@ __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ s
         ix[p][u] = act[p][u] ? (perm ? static_cast<uint32_t>(perm[ee]) : ee) : 0u;
       }
   };
-  fetch_indices();
+  if (PREFETCH) fetch_indices();
   int iters = 0;
   while (true) {
     ++iters;
+    if (!PREFETCH) fetch_indices();
     uint4 v[P][U];
 #pragma unroll
     for (int p = 0; p < P; ++p)
@@ -399,7 +402,7 @@ __device__ __forceinline__ void seg_sum_tile(const __nv_bfloat16* __restrict__ s
       e[p] += U * G;
       more |= e[p] < h[p];
     }
-    if (more) fetch_indices();  // next iteration's indices, in flight together with this iteration's rows
+    if (PREFETCH && more) fetch_indices();  // next iteration's indices, in flight together with this iteration's rows
 #pragma unroll
     for (int p = 0; p < P; ++p)
 #pragma unroll
