@@ -404,7 +404,13 @@ def kernel_roofline(lm, info, cfg, dev, ms_per_step):
         key = "m2g_edge_bwd_dram_bytes_per_launch" if "bwd" in dom["kernel"] else "m2g_edge_fwd_dram_bytes_per_launch"
         if tj.get(key):
             traffic, traffic_src = tj[key], tj.get("source")
+        # what actually bounds the pipelined kernels: the SM's L1 / shared-memory data pipe, shared by
+        # the LSU (shared ld / st, shuffles, TMEM write-back) and the tensor core's operand reads -- from the same capture
+        pipe = tj.get(key.replace("dram_bytes_per_launch", "l1_data_pipe"))
+    else:
+        pipe = None
     return {
+        "l1_data_pipe": pipe,
         "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
         "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "kernel": dom["kernel"],
         "achieved_dram": (traffic / dom["seconds"] / 1e9) if traffic else None,
