@@ -260,6 +260,8 @@ def make_reference_module(
     num_inter_steps: int = 1,
     precision: str = "32-true",
     named_tensor_cls=None,
+    mask_on_nan: bool = False,
+    mask_ratio: float = 0,
 ):
     """
     Builds a reference `AutoRegressiveLightning` WITHOUT running its __init__
@@ -277,9 +279,9 @@ def make_reference_module(
     lm.model = model
     lm.training_strategy = training_strategy
     lm.num_inter_steps = num_inter_steps
-    lm.mask_on_nan = False
+    lm.mask_on_nan = mask_on_nan
     lm.channels_last = False
-    lm.mask_ratio = 0
+    lm.mask_ratio = mask_ratio
     lm.diff_stats = diff_stats
     lm.stats = stats
     lm.trainer = _Trainer(precision)

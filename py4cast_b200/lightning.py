@@ -21,8 +21,11 @@ MAE / RMSE per-feature metrics the reference computes inside `StateErrorPlot.upd
 (plots.py:510-533) and the `reduce_spatial_dim=False` loss map of `SpatialErrorPlot.update`
 (plots.py:598-614) — as device tensors kept on the module instead of figures / logger calls.
 
-Out of scope (raise NotImplementedError): `downscaling_only`, `mask_on_nan=True`,
-`mask_ratio != 0`, figures / loggers / PSD-ACC metrics / GRIB writing.
+`mask_on_nan` (:568-569, :600-601, :732-757, :787-797) and `mask_ratio` (:588-589, :769-785) are
+served on the same kernels: the NaN masks are taken once per batch, the mask channel rides with
+the forcing channels of each model call, the masked-auto-encoder blocks are drawn with the
+reference's own `torch.randperm` stream.
+Out of scope (raise NotImplementedError): `downscaling_only`; figures / loggers / GRIB writing.
 """
 
 from __future__ import annotations
@@ -278,8 +281,6 @@ class AutoRegressiveLightning(nn.Module):
             )
         if self.training_strategy == "downscaling_only":
             raise NotImplementedError("downscaling_only is experimental upstream and not on the B200 hot path")
-        if mask_on_nan or mask_ratio != 0:
-            raise NotImplementedError("mask_on_nan / mask_ratio are not implemented on the B200 hot path")
 
         statics: Statics = deepcopy(dataset_info.statics)
         self.diff_stats = dataset_info.diff_stats
@@ -290,6 +291,7 @@ class AutoRegressiveLightning(nn.Module):
         num_grid_static_features = statics.grid_statics.dim_size("features")
         num_input_features = (
             num_input_steps * dataset_info.weather_dim + num_grid_static_features + dataset_info.forcing_dim
+            + self.mask_on_nan  # the "valid pixel" channel of _next_x (reference lightning.py:256-261)
         )
         num_output_features = dataset_info.weather_dim
 
@@ -386,19 +388,58 @@ class AutoRegressiveLightning(nn.Module):
         """First-step model input: cat(prev states, statics, forcing) (reference lightning.py:711-767)."""
         T_in = batch.num_input_steps
         t = prev_states.tensor
-        flat = t.reshape(t.shape[0], t.shape[1], -1, t.shape[-1])
-        prevs = [flat[:, i] for i in range(T_in)]
+        flat = t.reshape(t.shape[0], t.shape[1], -1, t.shape[-1]).float()
         f = batch.forcing.select_tensor_dim("timestep", step_idx)
-        forcing = f.reshape(f.shape[0], -1, f.shape[-1])
-        return ar_concat(prevs, self._static_flat, forcing, self._x_dtype())
+        forcing = f.reshape(f.shape[0], -1, f.shape[-1]).float()
+        if self.mask_on_nan:
+            self._require_grid_layout(t.dim() - 1)
+            valid = ~(torch.isnan(flat[:, :T_in]).any(-1).any(1) | torch.isnan(forcing).any(-1))
+            flat = torch.nan_to_num(flat, nan=0)
+            forcing = torch.cat([torch.nan_to_num(forcing, nan=0), valid.unsqueeze(-1).float()], dim=-1)
+        prevs = [flat[:, i].contiguous() for i in range(T_in)]
+        return ar_concat(prevs, self._static_flat, forcing.contiguous(), self._x_dtype())
+
+    @staticmethod
+    def _require_grid_layout(ndim: int) -> None:
+        """The reference's NaN-mask code indexes (batch, lat, lon, features) tensors
+        (lightning.py:733-748): on flattened graph inputs it raises IndexError; so does this."""
+        if ndim != 4:
+            raise IndexError("too many indices for tensor of dimension 3 (mask_on_nan needs gridded inputs)")
+
+    @staticmethod
+    def block_mask(height: int, width: int, mask_ratio: float) -> torch.Tensor:
+        """(H, W) bool mask of the masked-auto-encoder strategy, False inside the dropped blocks:
+        the blocks `mask_tensor` of the reference clears one slice assignment at a time
+        (lightning.py:769-785), drawn from the same `torch.randperm` stream (CPU default
+        generator), painted here with two outer products instead of a Python loop."""
+        num_blocks = int((1 - mask_ratio) * height * width)
+        bh, bw = height // int(height**0.5), width // int(width**0.5)
+        idx = torch.randperm(height * width)[:num_blocks]
+        rows, cols = torch.div(idx, width, rounding_mode="floor"), idx % width
+        # block (row, col) covers [row*bh, (row+1)*bh) x [col*bw, (col+1)*bw), clipped by slicing
+        hit = torch.zeros(height // bh + 1, width // bw + 1, dtype=torch.bool)
+        inside = (rows * bh < height) & (cols * bw < width)
+        hit[rows[inside], cols[inside]] = True
+        full = hit.repeat_interleave(bh, 0)[:height].repeat_interleave(bw, 1)[:, :width]
+        return ~full
+
+    def mask_tensor(self, x: torch.Tensor) -> torch.Tensor:
+        """x * mask (reference lightning.py:769-785); x is (B, H, W, C)."""
+        _, height, width, _ = x.shape
+        mask = self.block_mask(height, width, self.mask_ratio).to(x.device)
+        return x * mask.view(1, height, width, 1)
 
     def _run_model(self, x_flat: torch.Tensor, spatial: Tuple[int, ...]) -> torch.Tensor:
         """x_flat (B,N,F_in) -> y (B,N,F), through the layout the model type expects."""
         if self.model.model_type == ModelType.GRAPH:
+            if self.mask_ratio != 0:  # the reference unpacks four dimensions (lightning.py:770)
+                raise ValueError("not enough values to unpack (expected 4, got 3): mask_ratio needs gridded inputs")
             return self.model(x_flat)
         x = x_flat.view(x_flat.shape[0], *spatial, x_flat.shape[-1])
         if self.channels_last:
             x = x.to(memory_format=torch.channels_last)
+        if self.mask_ratio != 0:  # masked-auto-encoder strategy (lightning.py:588-589)
+            x = self.mask_tensor(x)
         if self.model.features_second:
             y = features_second_to_last(self.model(features_last_to_second(x)))
         else:
@@ -441,6 +482,29 @@ class AutoRegressiveLightning(nn.Module):
         std, mean = self._step_diffs(names, dev) if scale_y else (None, None)
         border = self._border_flat if (force_border and not inference) else None
         x_dtype = self._x_dtype()
+        call_forcing = None
+        if self.mask_on_nan:
+            # NaN handling of the reference (:568-569 border state, :600-601 last state, :732-757 x):
+            # every NaN of inputs / forcing / truth reads as 0 and x gains a "valid pixel" channel =
+            # no NaN in any state of the input window nor in the step's forcing.  States produced by
+            # the rollout are NaN-free, so only the raw input states still in the window count.
+            self._require_grid_layout(len(spatial) + 2)
+            in_nan = torch.isnan(inputs).any(-1)  # (B, T_in, N)
+            f_nan = torch.isnan(forcing).any(-1)  # (B, T, N)
+            inputs, forcing = torch.nan_to_num(inputs, nan=0), torch.nan_to_num(forcing, nan=0)
+            if outputs is not None:
+                outputs = torch.nan_to_num(outputs, nan=0)
+            call_forcing = torch.empty(B, T * num_inter_steps, N, forcing.shape[-1] + 1, dtype=torch.float32, device=dev)
+            for c in range(T * num_inter_steps):
+                invalid = f_nan[:, c // num_inter_steps]
+                if c < T_in:
+                    invalid = invalid | in_nan[:, c:].any(1)
+                call_forcing[:, c, :, :-1] = forcing[:, c // num_inter_steps]
+                call_forcing[:, c, :, -1] = (~invalid).float()
+
+        def forcing_of_call(c: int) -> torch.Tensor:
+            """forcing channels (+ mask channel) of model call c = i * num_inter_steps + k"""
+            return call_forcing[:, c] if call_forcing is not None else forcing[:, c // num_inter_steps]
 
         slab = torch.empty(B, T, N, F, dtype=torch.float32, device=dev)
         if hasattr(self.model, "begin_rollout"):
@@ -448,7 +512,7 @@ class AutoRegressiveLightning(nn.Module):
             self.model.begin_rollout(x_dtype)
         try:
             prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
-            x = ar_concat(prevs, self._static_flat, forcing[:, 0], x_dtype)
+            x = ar_concat(prevs, self._static_flat, forcing_of_call(0), x_dtype)
             states = []
             holder = {"slab_seen": False, "carry": {}}
             prev_last_slot = None  # slab slot of prevs[-1] when it is a state of this rollout
@@ -457,9 +521,7 @@ class AutoRegressiveLightning(nn.Module):
                     y = self._run_model(x, spatial)
                     last_k = k == num_inter_steps - 1
                     more = i < T - 1 or not last_k
-                    next_forcing = None
-                    if more:
-                        next_forcing = forcing[:, i] if not last_k else forcing[:, i + 1]
+                    next_forcing = forcing_of_call(i * num_inter_steps + k + 1) if more else None
                     cfg = {
                         "truth": outputs[:, i] if border is not None else None,
                         "border": border, "std": std, "mean": mean,
@@ -489,8 +551,13 @@ class AutoRegressiveLightning(nn.Module):
         return pred_out, batch.outputs
 
     def get_mask_on_nan(self, target: NamedTensor):
-        """mask_on_nan is False on this path: `None` stands for the all-ones mask the reference
-        allocates (lightning.py:797), so the loss kernel never reads it."""
+        """(mask, target with NaNs as zeros) (reference lightning.py:787-797).  Without `mask_on_nan`
+        `None` stands for the all-ones mask the reference allocates, so the loss kernel never reads it."""
+        if self.mask_on_nan:
+            mask = ~torch.isnan(target.tensor)
+            target_masked = target.clone()
+            target_masked.tensor = torch.nan_to_num(target_masked.tensor, nan=0)
+            return mask, target_masked
         return None, target
 
     def training_step(self, batch: ItemBatch, batch_idx: int) -> torch.Tensor:

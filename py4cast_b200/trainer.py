@@ -173,6 +173,10 @@ class DataParallelTrainer:
         CSR construction, shared-memory opt-in, casts — must not happen under capture)."""
         if warmup < 1:
             raise ValueError("at least one warm-up step is needed before capture")
+        if getattr(self.lm, "mask_ratio", 0) != 0:
+            # the masked-auto-encoder blocks are drawn on the host for every model call
+            # (lightning.mask_tensor): a replayed graph would freeze the first draw
+            raise ValueError("mask_ratio != 0 draws a new host-side mask per call: use step(), not capture()/replay()")
         self._static_batch = _clone_batch(example)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

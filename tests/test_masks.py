@@ -1,0 +1,92 @@
+"""`mask_on_nan` / `mask_ratio` branches of the AR step (reference lightning.py:568-601, 732-797) against
+golden vectors of the verbatim reference (tests/golden/ar_masks.pt, oracle/make_golden_masks.py)."""
+import pytest
+import torch
+
+from helpers import FP32_TOL, assert_close, load_golden
+
+CASES = ["nan_scaled_ar", "nan_diff_ar", "nan_scaled_ar_tin1", "mae_scaled_ar", "mae_diff_ar_odd", "mae_and_nan"]
+
+
+@pytest.mark.parametrize("name", ["mae_scaled_ar", "mae_diff_ar_odd", "mae_and_nan"])
+def test_block_mask_matches_the_reference_loop(name):
+    """The vectorised block painter draws and paints what the reference's per-block slice loop does."""
+    from py4cast_b200.lightning import AutoRegressiveLightning
+
+    case = load_golden("ar_masks.pt")[name]
+    s, cfg = case["problem"]["shape"], case["config"]
+    torch.manual_seed(cfg["rng_seed"])
+    for want in case["expected"]["block_masks"]:
+        got = AutoRegressiveLightning.block_mask(s["H"], s["W"], cfg["mask_ratio"])
+        assert got.dtype == torch.bool and torch.equal(got, want)
+    assert 0 < float(want.float().mean()) < 1  # the case does mask something, and not everything
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_masked_rollout_and_loss_vs_reference_golden(cuda, name):
+    from py4cast_b200.lightning import AutoRegressiveLightning
+    from py4cast_b200.losses import ScaledLoss
+    from test_gpu_ar_loss import _batch, _dataset_info, _register_linear_tanh
+
+    _register_linear_tanh()
+    case = load_golden("ar_masks.pt")[name]
+    p, cfg, exp = case["problem"], case["config"], case["expected"]
+    s = p["shape"]
+    info = _dataset_info(p)
+    lm = AutoRegressiveLightning(
+        settings_init_args={}, dataset_info=info, num_input_steps=s["T_in"], num_pred_steps_train=s["T"],
+        batch_size=s["B"], model_name="GoldenConvNet",
+        losses=[{"class": "WeightedLoss", "weight": 1.0, "params": {"loss": "MSELoss", "reduction": "none"}}],
+        training_strategy=cfg["strategy"], mask_on_nan=cfg.get("mask_on_nan", False),
+        mask_ratio=cfg.get("mask_ratio", 0),
+    )
+    assert lm.model.W.shape[0] == exp["model_W"].shape[0]  # + 1 input channel with mask_on_nan
+    with torch.no_grad():
+        lm.model.W.copy_(exp["model_W"])
+    lm = lm.to(cuda)
+
+    if "rng_seed" in cfg:
+        torch.manual_seed(cfg["rng_seed"])
+    batch = _batch(p, cuda)
+    pred, target = lm.common_step(batch, 0, "train")
+    assert target is batch.outputs
+    assert not torch.isnan(pred.tensor).any()
+    assert_close(pred.tensor.cpu(), exp["pred"], FP32_TOL, f"{name} prediction")
+
+    mask, target_masked = lm.get_mask_on_nan(target)
+    if cfg.get("mask_on_nan"):
+        assert torch.equal(mask.cpu(), exp["mask"])
+        assert torch.equal(target_masked.tensor.cpu(), exp["target_masked"])
+        assert torch.isnan(target.tensor).any()  # the batch itself keeps its NaNs, as in the reference
+    else:
+        assert mask is None
+    loss_bt = lm.loss(pred, target_masked, mask=mask)
+    assert_close(loss_bt.cpu(), exp["weighted_mse_bt"], FP32_TOL, f"{name} WeightedLoss")
+    (dW,) = torch.autograd.grad(torch.mean(loss_bt), lm.model.W, retain_graph=True)
+    assert_close(dW.cpu(), exp["dW"], FP32_TOL, f"{name} d(batch_loss)/dW")
+    sl = ScaledLoss("L1Loss", reduction="none")
+    sl.prepare(lm, lm.interior_mask, info)
+    assert_close(sl(pred, target_masked, mask=mask).cpu(), exp["scaled_mae_btf"], FP32_TOL, f"{name} ScaledLoss")
+
+    if "rng_seed" in cfg:
+        torch.manual_seed(cfg["rng_seed"])
+    tl = lm.training_step(_batch(p, cuda), 1)
+    assert_close(tl.detach().cpu(), exp["batch_loss"], FP32_TOL, f"{name} training_step")
+
+
+@pytest.mark.gpu
+def test_masks_need_gridded_inputs(cuda):
+    """On a graph model the reference's mask code raises (IndexError in `_next_x`, ValueError in
+    `mask_tensor`): same error types here."""
+    from py4cast_b200.lightning import AutoRegressiveLightning
+    from test_gpu_ar_loss import _batch, _dataset_info, _register_linear_tanh
+
+    _register_linear_tanh()
+    p = load_golden("ar_rollout.pt")["graph_scaled_ar"]["problem"]
+    s = p["shape"]
+    for kw, err in ((dict(mask_on_nan=True), IndexError), (dict(mask_ratio=0.5), ValueError)):
+        lm = AutoRegressiveLightning({}, _dataset_info(p), num_input_steps=s["T_in"], batch_size=s["B"],
+                                     model_name="GoldenGraphNet", training_strategy="scaled_ar", **kw).to(cuda)
+        with pytest.raises(err):
+            lm.common_step(_batch(p, cuda), 0, "train")
