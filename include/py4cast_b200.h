@@ -342,7 +342,8 @@ typedef struct {
 } p4c_ar_x_t;
 
 /* x[b,n,:] = cat(prev[0..T_in-1], static, forcing)      (lightning.py:711-767 `_next_x`)
- * x: [batch][nodes][T_in*F + F_s + F_f] of `x_dtype`. */
+ * x: [batch][nodes][T_in*F + F_s + F_f] of `x_dtype`.  num_prev = 0 is allowed here (and only here): the
+ * `downscaling_only` strategy feeds statics and forcings alone (lightning.py:759-765). */
 int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream);
 /* 0: p4c_ar_concat / p4c_ar_step_forward / p4c_ar_step_backward use their scalar kernels only (the staged /
  * vectorised ones need nodes % 64 == 0 resp. nodes * F % 4 == 0 and 16-byte aligned arrays; same results bit for

@@ -1,8 +1,8 @@
 """
 ORACLE — TEST INFRASTRUCTURE ONLY.
 
-Golden vectors for the NaN-mask (`mask_on_nan`) and masked-auto-encoder (`mask_ratio`) branches of
-the AR step, produced by the reference's OWN code (py4cast/lightning.py:568-569, 588-589, 600-601,
+Golden vectors for the NaN-mask (`mask_on_nan`), masked-auto-encoder (`mask_ratio`) and
+`downscaling_only` branches of the AR step, produced by the reference's OWN code (py4cast/lightning.py:568-569, 588-589, 600-601,
 732-797 and py4cast/losses.py, loaded verbatim through oracle/refshim.py) on seeded inputs, CPU,
 fp32.  Run in the build container (needs /root/reference):
 
@@ -44,7 +44,8 @@ def run_case(p, strategy, mask_on_nan=False, mask_ratio=0.0, model_seed=7, rng_s
     ref_losses, _ = refshim.load_reference()
     NT = mfai_shim.NamedTensor
     s = p.shape
-    f_in = s["T_in"] * s["F"] + s["Fs"] + s["Ff"] + int(mask_on_nan)
+    ds = strategy == "downscaling_only"
+    f_in = s["T_in"] * s["F"] * (1 - ds) + s["Fs"] + s["Ff"] + int(mask_on_nan)
     model = LinearTanh(f_in, s["F"], False, True, model_seed)
     info = dataset_info_for(p)
     lm = refshim.make_reference_module(
@@ -112,6 +113,18 @@ def main():
         p = make_problem(2235, **shape)
         if kw.get("mask_on_nan"):
             sprinkle_nans(p, 78)
+        cases[name] = {"problem": pack_problem(p), "config": kw, "expected": run_case(p, **kw)}
+    # downscaling_only (lightning.py:546-558, 611-621, 759-765): outputs are matched to forcing features by name
+    for name, kw, shape in (
+        ("ds_plain", dict(strategy="downscaling_only"), dict(B=2, T_in=1, T=3, H=16, W=20, F=3, Ff=4, border=2)),
+        ("ds_nan", dict(strategy="downscaling_only", mask_on_nan=True),
+         dict(B=2, T_in=2, T=2, H=12, W=14, F=3, Ff=4, border=2)),
+    ):
+        p = make_problem(2236, **shape)
+        p.feature_names = ["aro_t2m_2m", "aro_u10_10m", "aro_r2_2m"]
+        p.forcing_names = ["arp_u10_10m", "arp_t2m_2m", "arp_r2_2m", "arp_tp_0m"]
+        if kw.get("mask_on_nan"):
+            sprinkle_nans(p, 79)
         cases[name] = {"problem": pack_problem(p), "config": kw, "expected": run_case(p, **kw)}
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, "ar_masks.pt")

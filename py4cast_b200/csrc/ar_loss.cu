@@ -813,11 +813,14 @@ static int grid_for(long long n, int block) {
   return (int)(g < cap ? g : cap);
 }
 
-static int check_ar_x(const p4c_ar_x_t* a, bool last_may_be_null) {
+// min_prev = 0 for the plain concatenation: the downscaling strategy feeds statics and forcings only
+// (reference lightning.py:759-765, `inputs * (1 - ds)`)
+static int check_ar_x(const p4c_ar_x_t* a, bool last_may_be_null, int min_prev = 1) {
   P4C_REQUIRE(a != nullptr, "ar: null descriptor");
   P4C_REQUIRE(a->batch > 0 && a->nodes > 0 && a->f_state > 0, "ar: empty problem");
-  P4C_REQUIRE(a->num_prev >= 1 && a->num_prev <= P4C_MAX_PREV, "ar: num_prev=%d not in [1,%d]",
-              a->num_prev, P4C_MAX_PREV);
+  P4C_REQUIRE(a->num_prev >= min_prev && a->num_prev <= P4C_MAX_PREV, "ar: num_prev=%d not in [%d,%d]",
+              a->num_prev, min_prev, P4C_MAX_PREV);
+  P4C_REQUIRE(a->num_prev * a->f_state + a->f_static + a->f_forcing > 0, "ar: x has no columns");
   for (int t = 0; t < a->num_prev; ++t)
     P4C_REQUIRE(a->prev[t] != nullptr || (last_may_be_null && t == a->num_prev - 1),
                 "ar: prev[%d] is null", t);
@@ -835,7 +838,7 @@ using namespace p4c;
 extern "C" void p4c_set_ar_vector_paths(int enabled) { p4c::g_ar_vector_paths = enabled ? 1 : 0; }
 
 extern "C" int p4c_ar_concat(const p4c_ar_x_t* a, void* x, int x_dtype, void* stream) {
-  int rc = check_ar_x(a, false);
+  int rc = check_ar_x(a, false, 0);
   if (rc) return rc;
   P4C_REQUIRE(x != nullptr, "ar_concat: x is null");
   const int f_in = a->num_prev * a->f_state + a->f_static + a->f_forcing;

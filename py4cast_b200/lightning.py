@@ -25,7 +25,10 @@ MAE / RMSE per-feature metrics the reference computes inside `StateErrorPlot.upd
 served on the same kernels: the NaN masks are taken once per batch, the mask channel rides with
 the forcing channels of each model call, the masked-auto-encoder blocks are drawn with the
 reference's own `torch.randperm` stream.
-Out of scope (raise NotImplementedError): `downscaling_only`; figures / loggers / GRIB writing.
+`downscaling_only` (experimental upstream; :524, :546-558, :611-621, :759-765): x = cat(statics,
+forcings) through the same concat kernel with zero previous states, state = coarse forcing features + y
+through the state-update kernel.
+Out of scope: figures / loggers / GRIB writing.
 """
 
 from __future__ import annotations
@@ -94,14 +97,16 @@ def _new_x(B: int, N: int, f_in: int, x_dtype: torch.dtype, device, a: ArX) -> t
 
 def ar_concat(prevs: List[torch.Tensor], static: torch.Tensor, forcing: torch.Tensor,
               x_dtype: torch.dtype) -> torch.Tensor:
-    """x = cat(prev[0..T_in-1], static, forcing) along features (reference `_next_x`)."""
-    B, N, F = prevs[0].shape
+    """x = cat(prev[0..T_in-1], static, forcing) along features (reference `_next_x`); `prevs` is
+    empty for the downscaling strategy (statics and forcings only)."""
+    B, N = forcing.shape[0], forcing.shape[1]
+    F = prevs[0].shape[-1] if prevs else 1
     if len(prevs) > MAX_PREV:
         raise ValueError(f"at most {MAX_PREV} input steps are supported")
     f_in = len(prevs) * F + static.shape[-1] + forcing.shape[-1]
     a = ArX()
     _fill_arx(a, prevs, static, forcing, B, N, F)
-    x = _new_x(B, N, f_in, x_dtype, prevs[0].device, a)
+    x = _new_x(B, N, f_in, x_dtype, forcing.device, a)
     check(_lib.load().p4c_ar_concat(C.byref(a), ptr(x), dtype_code(x_dtype), stream()), "p4c_ar_concat")
     return x
 
@@ -280,7 +285,7 @@ class AutoRegressiveLightning(nn.Module):
                 f"Unknown strategy {self.training_strategy}, allowed strategies are {ALLOWED_STRATEGIES}"
             )
         if self.training_strategy == "downscaling_only":
-            raise NotImplementedError("downscaling_only is experimental upstream and not on the B200 hot path")
+            print("WARNING : You are using downscaling_only mode: this is experimental.")
 
         statics: Statics = deepcopy(dataset_info.statics)
         self.diff_stats = dataset_info.diff_stats
@@ -290,7 +295,8 @@ class AutoRegressiveLightning(nn.Module):
 
         num_grid_static_features = statics.grid_statics.dim_size("features")
         num_input_features = (
-            num_input_steps * dataset_info.weather_dim + num_grid_static_features + dataset_info.forcing_dim
+            num_input_steps * dataset_info.weather_dim * (self.training_strategy != "downscaling_only")
+            + num_grid_static_features + dataset_info.forcing_dim
             + self.mask_on_nan  # the "valid pixel" channel of _next_x (reference lightning.py:256-261)
         )
         num_output_features = dataset_info.weather_dim
@@ -464,6 +470,14 @@ class AutoRegressiveLightning(nn.Module):
             self.output_feature_names = batch.outputs.feature_names
             self.output_dim_names = batch.outputs.names
             self.output_dtype = batch.outputs.tensor.dtype
+            if self.training_strategy == "downscaling_only":
+                # forcing features that are the coarse version of an output feature: same name after
+                # the first "_"-separated token (reference lightning.py:546-558)
+                self.common_features_idx = [
+                    i for out_name in self.output_feature_names
+                    for i, f_name in enumerate(batch.forcing.feature_names)
+                    if out_name.split("_")[1:] == f_name.split("_")[1:]
+                ]
 
         inp = batch.inputs.tensor
         if not inp.is_cuda:
@@ -510,13 +524,39 @@ class AutoRegressiveLightning(nn.Module):
         if hasattr(self.model, "begin_rollout"):
             # batch-independent embeddings and weight images: once per rollout, not per step
             self.model.begin_rollout(x_dtype)
+        ds = self.training_strategy == "downscaling_only"
+        if ds:
+            # residual on the coarse forcing features, no recurrence (reference lightning.py:611-621):
+            # the state-update kernel runs with "previous state" = the selected forcing channels
+            self._require_grid_layout(len(spatial) + 2)
+            idx = torch.as_tensor(self.common_features_idx, dtype=torch.long, device=dev)
+            if idx.numel() != F:
+                raise RuntimeError(
+                    f"The size of tensor a ({idx.numel()}) must match the size of tensor b ({F}) at non-singleton "
+                    "dimension 3 (downscaling_only: forcing features matching the output features by name)"
+                )
+            coarse = forcing.index_select(-1, idx)  # (B, T, N, F)
         try:
-            prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
-            x = ar_concat(prevs, self._static_flat, forcing_of_call(0), x_dtype)
             states = []
             holder = {"slab_seen": False, "carry": {}}
             prev_last_slot = None  # slab slot of prevs[-1] when it is a state of this rollout
-            for i in range(T):
+            prevs: List[torch.Tensor] = [inputs[:, t] for t in range(T_in)]
+            if not ds:
+                x = ar_concat(prevs, self._static_flat, forcing_of_call(0), x_dtype)
+            for i in range(T if ds else 0):
+                for k in range(num_inter_steps):
+                    x = ar_concat([], self._static_flat, forcing_of_call(i * num_inter_steps + k), x_dtype)
+                    y = self._run_model(x, spatial)
+                    last_k = k == num_inter_steps - 1
+                    cfg = {
+                        "truth": None, "border": None, "std": None, "mean": None,
+                        "new_state": slab[:, i] if last_k else torch.empty(B, N, F, dtype=torch.float32, device=dev),
+                        "static": self._static_flat, "forcing_next": None, "x_dtype": x_dtype,
+                        "holder": holder, "slot": i if last_k else None, "prev_last_slot": None,
+                    }
+                    new_state = _ARStepFn.apply(cfg, y, coarse[:, i])
+                states.append(new_state)
+            for i in range(0 if ds else T):
                 for k in range(num_inter_steps):
                     y = self._run_model(x, spatial)
                     last_k = k == num_inter_steps - 1

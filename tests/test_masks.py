@@ -1,11 +1,13 @@
-"""`mask_on_nan` / `mask_ratio` branches of the AR step (reference lightning.py:568-601, 732-797) against
+"""`mask_on_nan` / `mask_ratio` / `downscaling_only` branches of the AR step (reference lightning.py:546-621,
+732-797) against
 golden vectors of the verbatim reference (tests/golden/ar_masks.pt, oracle/make_golden_masks.py)."""
 import pytest
 import torch
 
 from helpers import FP32_TOL, assert_close, load_golden
 
-CASES = ["nan_scaled_ar", "nan_diff_ar", "nan_scaled_ar_tin1", "mae_scaled_ar", "mae_diff_ar_odd", "mae_and_nan"]
+CASES = ["nan_scaled_ar", "nan_diff_ar", "nan_scaled_ar_tin1", "mae_scaled_ar", "mae_diff_ar_odd", "mae_and_nan",
+         "ds_plain", "ds_nan"]
 
 
 @pytest.mark.parametrize("name", ["mae_scaled_ar", "mae_diff_ar_odd", "mae_and_nan"])
@@ -41,7 +43,7 @@ def test_masked_rollout_and_loss_vs_reference_golden(cuda, name):
         training_strategy=cfg["strategy"], mask_on_nan=cfg.get("mask_on_nan", False),
         mask_ratio=cfg.get("mask_ratio", 0),
     )
-    assert lm.model.W.shape[0] == exp["model_W"].shape[0]  # + 1 input channel with mask_on_nan
+    assert lm.model.W.shape[0] == exp["model_W"].shape[0]  # + 1 channel with mask_on_nan, no states when downscaling
     with torch.no_grad():
         lm.model.W.copy_(exp["model_W"])
     lm = lm.to(cuda)
@@ -85,8 +87,10 @@ def test_masks_need_gridded_inputs(cuda):
     _register_linear_tanh()
     p = load_golden("ar_rollout.pt")["graph_scaled_ar"]["problem"]
     s = p["shape"]
-    for kw, err in ((dict(mask_on_nan=True), IndexError), (dict(mask_ratio=0.5), ValueError)):
+    for kw, err in ((dict(mask_on_nan=True), IndexError), (dict(mask_ratio=0.5), ValueError),
+                    (dict(training_strategy="downscaling_only"), IndexError)):
+        kw.setdefault("training_strategy", "scaled_ar")
         lm = AutoRegressiveLightning({}, _dataset_info(p), num_input_steps=s["T_in"], batch_size=s["B"],
-                                     model_name="GoldenGraphNet", training_strategy="scaled_ar", **kw).to(cuda)
+                                     model_name="GoldenGraphNet", **kw).to(cuda)
         with pytest.raises(err):
             lm.common_step(_batch(p, cuda), 0, "train")
