@@ -54,8 +54,8 @@ def _oracle_step(ref, info, batch, strategy):
     std, mean = info.diff_stats.to_list("std", fn), info.diff_stats.to_list("mean", fn)
     w = torch.tensor([info.state_weights[n] for n in fn]) / std**2
     border = info.statics.border_mask.flatten(0, 1)
-    static = info.statics.grid_statics.tensor.flatten(0, 1).unsqueeze(0)
     tgt = batch.outputs.tensor.flatten(2, 3)
+    static = info.statics.grid_statics.tensor.flatten(0, 1).unsqueeze(0).expand(tgt.shape[0], -1, -1)
     pred = ar_ref.ar_rollout(
         ref, batch.inputs.tensor.flatten(2, 3), batch.forcing.tensor.flatten(2, 3), tgt, static, border,
         1 - border, std, mean, strategy,
@@ -129,3 +129,37 @@ def test_config1_graphlam_fp32_scaled_ar_T4_vs_oracle(cuda, tmp_path):
     tgt = cpu_batch.outputs.tensor.flatten(2, 3)
     assert torch.equal(pred.tensor.detach().cpu().reshape(tgt.shape)[:, :, border], tgt[:, :, border])
     _compare(lm, ref, pred.tensor.detach(), loss.detach(), pred_r, loss_r, FP32_TOL, "titan GraphLAM fp32 scaled_ar T=4")
+
+
+@pytest.mark.parametrize(
+    "model_name,strategy,batch",
+    [("HiLAM", "diff_ar", 2), ("HiLAMParallel", "scaled_ar", 1), ("GraphLAM", "diff_ar", 2)],
+)
+def test_full_size_bf16_batched_and_other_families_vs_oracle(cuda, tmp_path, model_name, strategy, batch):
+    """Full 512x640 grid, `bf16-true`, T=2: (i) batch 2 — the bench runs batch 16, where the pipelined
+    backward sums the gradient of the batch-shared edge embedding over the samples of a row block in TMEM
+    and tiles are ordered sample-minor; (ii) the other two graph families of the registry at the size where
+    the pipelined kernels engage.  Prediction, loss and every parameter gradient vs the fp32 CPU oracle."""
+    from py4cast_b200 import _lib
+    from py4cast_b200.datasets import synthetic_batch
+    from py4cast_b200.trainer import _fresh
+
+    T = 2
+    lm, ref, info = _setup(tmp_path, model_name, strategy, "bf16-true", T)
+    lm = lm.to(cuda)
+    cpu_batch = synthetic_batch(info, batch, 2, T, seed=13)
+    gpu_batch = synthetic_batch(info, batch, 2, T, seed=13, device=cuda)
+    lib = _lib.load()
+    ws0, wb0, bs0 = lib.p4c_ws_launch_count(), lib.p4c_ws_bwd_launch_count(), lib.p4c_ws_bwd_bsum_launch_count()
+    with torch.no_grad():
+        pred, _ = lm.common_step(_fresh(gpu_batch), 0, "train")
+    loss = lm.training_step(_fresh(gpu_batch), 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert lib.p4c_ws_launch_count() > ws0, "the pipelined forward kernel did not run"
+    assert lib.p4c_ws_bwd_launch_count() > wb0, "the pipelined backward kernel did not run"
+    if batch > 1:
+        assert lib.p4c_ws_bwd_bsum_launch_count() > bs0, "the batch sum in TMEM did not run"
+    pred_r, loss_r = _oracle_step(ref, info, cpu_batch, strategy)
+    _compare(lm, ref, pred.tensor.detach(), loss.detach(), pred_r, loss_r, BF16_TOL,
+             f"titan {model_name} bf16 {strategy} T={T} batch {batch}")
