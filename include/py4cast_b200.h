@@ -427,6 +427,16 @@ int p4c_forcing_fill(const float* lat, const float* lon, const float* hour, cons
                      const float* cos_dec, const float* datetime4, int32_t slots, int32_t nodes,
                      float* out, int32_t ld, int32_t ch0, void* stream);
 
+/* The whole forcing tensor of a batch in one pass (reference datasets/base.py:503-515: the NWP forcing
+ * parameters followed by the five generated channels, concatenated per item and stacked by collate_fn,
+ * base.py:173-195): out[slot][node][0..n_ship) = src[slot][node][:] converted to fp32 (src_dtype P4C_F32 or
+ * P4C_BF16: the dtype the channels crossed PCIe in), out[..][n_ship..n_ship+4] = (cos_hour, sin_hour, cos_doy,
+ * sin_doy, toa_radiation) as p4c_forcing_fill computes them (bit-identical), columns beyond n_ship+5 zero.
+ * Rows are written whole (coalesced); ld >= n_ship + 5. */
+int p4c_forcing_assemble(const void* src, int src_dtype, int32_t n_ship, const float* lat, const float* lon,
+                         const float* hour, const float* sin_dec, const float* cos_dec, const float* datetime4,
+                         int32_t slots, int32_t nodes, float* out, int32_t ld, void* stream);
+
 /* -------------------------------------------------------------------------
  * Anomaly correlation coefficient (reference py4cast/metrics.py:407-420,
  * MetricACC.update): out[bt][f] = S0 / sqrt(S1 * S2) over the spatial points of one (sample, step),

@@ -215,6 +215,7 @@ SYMBOLS = {
     "p4c_feature_stats": (_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "p4c_scale_shift": (_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "p4c_forcing_fill": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "p4c_forcing_assemble": (_int, [_vp, _int, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "p4c_adamw_advance": (_int, [_vp, _f32, _f32, _i64, _i64, _f32, _f32, _vp]),
     "p4c_adamw_step": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "p4c_cast": (_int, [_vp, _int, _vp, _int, _i64, _vp]),

@@ -742,6 +742,12 @@ __global__ void acc_finalize_kernel(const float* __restrict__ partials, int nchu
 //   cos(zenith) = sin(phi) sin(dec) + cos(phi) cos(dec) cos(omega),  omega = 15 (hour + lon/15 - 12) deg,
 // written straight into channels ch0.. of the (slots, nodes, ld) forcing tensor (no per-channel
 // tensors, no expand + cat).  fp32 throughout, like the reference.
+// one association order for both forcing kernels (the compiler is free to contract a*b + c*d*e either way)
+__device__ __forceinline__ float toa_radiation(float sin_phi, float cos_phi, float sd, float cd, float omega_rad) {
+  const float cos_sza = __fmaf_rn(sin_phi, sd, __fmul_rn(__fmul_rn(cos_phi, cd), cosf(omega_rad)));
+  return fmaxf(0.f, 1366.f * cos_sza);
+}
+
 __global__ void forcing_fill_kernel(const float* __restrict__ lat, const float* __restrict__ lon,
                                     const float* __restrict__ hour, const float* __restrict__ sin_dec,
                                     const float* __restrict__ cos_dec, const float* __restrict__ dt4,
@@ -755,10 +761,71 @@ __global__ void forcing_fill_kernel(const float* __restrict__ lat, const float* 
     const float hours_lcl = hr + lon[n] / 15.f;
     const float omega_rad = (15.f * (hours_lcl - 12.f)) * kRad;
     const float phi_rad = lat[n] * kRad;
-    const float cos_sza = sinf(phi_rad) * sd + cosf(phi_rad) * cd * cosf(omega_rad);
     float* o = out + ((long long)t * nodes + n) * ld + ch0;
     if (dt4) { o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d3; o += 4; }
-    o[0] = fmaxf(0.f, 1366.f * cos_sza);
+    o[0] = toa_radiation(sinf(phi_rad), cosf(phi_rad), sd, cd, omega_rad);
+  }
+}
+
+// The input path's forcing tensor in ONE pass (datasets/base.py:503-515: NWP forcing channels, then the five
+// generated ones): rows of the (slots, nodes, ld) fp32 tensor are written whole and in order -- channels
+// [0, n_ship) converted from the shipped array (bf16 under `bf16-true`, else fp32), then cos/sin hour, cos/sin
+// day of year, TOA radiation -- instead of a strided channel copy plus forcing_fill_kernel's 20-byte writes into
+// 84-byte rows (two partial-sector passes over the tensor).  A CTA owns FA_TN nodes: sin / cos of their
+// latitude are computed once and kept in shared memory, then for each of the CTA's time slots the radiation of
+// the nodes (same expressions as forcing_fill_kernel: bit-identical) and a linear, coalesced sweep over the
+// FA_TN * ld output floats.
+constexpr int FA_TN = 256;
+template <typename TS>
+__global__ void __launch_bounds__(256)
+forcing_assemble_kernel(const TS* __restrict__ src, int n_ship, const float* __restrict__ lat,
+                        const float* __restrict__ lon, const float* __restrict__ hour,
+                        const float* __restrict__ sin_dec, const float* __restrict__ cos_dec,
+                        const float* __restrict__ dt4, int slots, int nodes, float* __restrict__ out, int ld,
+                        int slots_per_cta) {
+  __shared__ float s_sp[FA_TN], s_cp[FA_TN], s_lon[FA_TN], s_toa[FA_TN];
+  const float kRad = 0.017453292519943295f;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * FA_TN;
+  const int nn = min(FA_TN, nodes - n0);
+  if (tid < nn) {
+    const float phi_rad = lat[n0 + tid] * kRad;
+    s_sp[tid] = sinf(phi_rad);
+    s_cp[tid] = cosf(phi_rad);
+    s_lon[tid] = lon[n0 + tid];
+  }
+  const int t_lo = blockIdx.y * slots_per_cta, t_hi = min(slots, t_lo + slots_per_cta);
+  const int total = nn * ld;
+  const int dn = 256 / ld, dc = 256 - dn * ld;  // i += 256  ->  (n += dn, c += dc) with one carry
+  for (int t = t_lo; t < t_hi; ++t) {
+    const float hr = hour[t], sd = sin_dec[t], cd = cos_dec[t];
+    const float d0 = dt4[4 * t], d1 = dt4[4 * t + 1], d2 = dt4[4 * t + 2], d3 = dt4[4 * t + 3];
+    __syncthreads();  // s_sp.. written (first slot); s_toa of the previous slot consumed
+    if (tid < nn) {
+      const float hours_lcl = hr + s_lon[tid] / 15.f;
+      const float omega_rad = (15.f * (hours_lcl - 12.f)) * kRad;
+      s_toa[tid] = toa_radiation(s_sp[tid], s_cp[tid], sd, cd, omega_rad);
+    }
+    __syncthreads();
+    const long long row0 = (long long)t * nodes + n0;
+    float* o = out + row0 * ld;
+    const TS* sr = src + row0 * n_ship;
+    int n = tid / ld, c = tid - n * ld;
+    for (int i = tid; i < total; i += 256) {
+      float v;
+      const int e = c - n_ship;
+      if (e < 0) v = to_f32<TS>(sr[n * n_ship + c]);
+      else if (e == 0) v = d0;
+      else if (e == 1) v = d1;
+      else if (e == 2) v = d2;
+      else if (e == 3) v = d3;
+      else if (e == 4) v = s_toa[n];
+      else v = 0.f;
+      o[i] = v;
+      n += dn;
+      c += dc;
+      if (c >= ld) { c -= ld; ++n; }
+    }
   }
 }
 
@@ -1091,6 +1158,36 @@ extern "C" int p4c_adamw_step(float* param, const float* grad, float* exp_avg, f
   adamw_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, weight_decay, grad_scale);
   P4C_CHECK_LAUNCH("adamw_step");
+  return P4C_OK;
+}
+
+extern "C" int p4c_forcing_assemble(const void* src, int src_dtype, int32_t n_ship, const float* lat, const float* lon,
+                                    const float* hour, const float* sin_dec, const float* cos_dec,
+                                    const float* datetime4, int32_t slots, int32_t nodes, float* out, int32_t ld,
+                                    void* stream) {
+  P4C_REQUIRE(lat && lon && hour && sin_dec && cos_dec && datetime4 && out, "forcing_assemble: null pointer");
+  P4C_REQUIRE(n_ship >= 0 && (n_ship == 0 || src), "forcing_assemble: shipped channels missing");
+  P4C_REQUIRE(slots > 0 && nodes > 0, "forcing_assemble: bad sizes (slots=%d nodes=%d)", slots, nodes);
+  P4C_REQUIRE(ld >= n_ship + 5 && ld <= 256, "forcing_assemble: ld=%d does not hold %d + 5 channels (or > 256)", ld,
+              n_ship);
+  P4C_REQUIRE(src_dtype == P4C_F32 || src_dtype == P4C_BF16, "forcing_assemble: bad dtype %d", src_dtype);
+  const int bx = (nodes + FA_TN - 1) / FA_TN;
+  // enough CTAs for a few waves; a CTA keeps its nodes' sin / cos latitude over its slots
+  int by = (8 * kNumSMs + bx - 1) / bx;
+  if (by > slots) by = slots;
+  if (by > 65535) by = 65535;
+  if (by < 1) by = 1;
+  const int per = (slots + by - 1) / by;
+  by = (slots + per - 1) / per;
+  const dim3 grid(bx, by);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == P4C_BF16)
+    forcing_assemble_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, n_ship, lat, lon, hour, sin_dec,
+                                                                cos_dec, datetime4, slots, nodes, out, ld, per);
+  else
+    forcing_assemble_kernel<float><<<grid, 256, 0, st>>>((const float*)src, n_ship, lat, lon, hour, sin_dec, cos_dec,
+                                                        datetime4, slots, nodes, out, ld, per);
+  P4C_CHECK_LAUNCH("forcing_assemble");
   return P4C_OK;
 }
 

@@ -145,6 +145,32 @@ def fill_external_forcings_from_scalars(forcing: torch.Tensor, ch0: int, lat: to
     )
 
 
+def assemble_forcings(forcing: torch.Tensor, shipped: torch.Tensor, lat: torch.Tensor, lon: torch.Tensor,
+                      scalars: torch.Tensor) -> None:
+    """The whole forcing tensor of a batch in one pass: `forcing[..., :n] = shipped` (fp32 or bf16 -> fp32),
+    `forcing[..., n:n+5]` = the five external channels (bit-identical with `fill_external_forcings_from_scalars`).
+    Rows are written whole and in order, instead of a strided channel copy followed by 20-byte writes into
+    84-byte rows.  Reference: datasets/base.py:503-515 (NWP forcings, then generate_forcings, concatenated)."""
+    if not (forcing.is_cuda and forcing.dtype == torch.float32 and forcing.is_contiguous()):
+        raise _lib.P4CError("assemble_forcings: forcing must be a contiguous fp32 CUDA tensor")
+    if not (shipped.is_cuda and shipped.is_contiguous() and shipped.dtype in (torch.float32, torch.bfloat16)):
+        raise _lib.P4CError("assemble_forcings: shipped channels must be a contiguous fp32 / bf16 CUDA tensor")
+    if not (scalars.is_cuda and scalars.dtype == torch.float32 and scalars.dim() == 2 and scalars.shape[1] == 7):
+        raise _lib.P4CError("assemble_forcings: scalars must be a (B * T, 7) fp32 CUDA tensor")
+    F, n = forcing.shape[-1], shipped.shape[-1]
+    slots = scalars.shape[0]
+    if F != n + 5 or forcing.numel() != slots * lat.numel() * F or shipped.numel() != slots * lat.numel() * n:
+        raise ValueError("assemble_forcings: forcing / shipped / scalars / grid sizes do not match")
+    cols = scalars.t().contiguous()  # (7, slots): hour, sin_dec, cos_dec, ...
+    dt4 = scalars[:, 3:7].contiguous()
+    check(
+        _lib.load().p4c_forcing_assemble(ptr(shipped), _lib.dtype_code(shipped.dtype), n, ptr(lat), ptr(lon),
+                                         ptr(cols[0]), ptr(cols[1]), ptr(cols[2]), ptr(dt4), slots, lat.numel(),
+                                         ptr(forcing), F, stream()),
+        "p4c_forcing_assemble",
+    )
+
+
 def fill_external_forcings(forcing: torch.Tensor, ch0: int, lat: torch.Tensor, lon: torch.Tensor,
                            dates: Sequence[dt.datetime], timedeltas: Sequence[dt.timedelta]) -> None:
     """Writes [cos_hour, sin_hour, cos_doy, sin_doy, toa_radiation] of every (sample, step) into

@@ -228,6 +228,12 @@ class DataParallelTrainer:
         dst = sb.forcing.tensor
         fs = src["forcing"]
         n_ship = fs.shape[-1]
+        if src["ext"] is not None and fs.is_cuda and n_ship + 5 == dst.shape[-1]:
+            # staged batch: cast + channel placement + the five generated channels in one pass over whole rows
+            from .forcingutils import assemble_forcings
+
+            assemble_forcings(dst, fs.contiguous(), self._ext_grid[0], self._ext_grid[1], src["ext"])
+            return
         dst[..., :n_ship].copy_(fs.reshape(*dst.shape[:-1], n_ship), non_blocking=True)  # cast + channel slice
         if src["ext"] is not None:
             from .forcingutils import fill_external_forcings_from_scalars

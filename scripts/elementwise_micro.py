@@ -87,6 +87,19 @@ def main():
     scal = fu.external_forcing_scalars(dates, terms).to(dev)
     t_fs = timeit(lambda: fu.fill_external_forcings_from_scalars(fbuf, info.forcing_dim - 5, lat, lon, scal))
     rows.append(("external forcings (5 channels, scalars prepared by the loader)", B * T * N * 5 * 4 + 2 * 4 * N, t_fs))
+    # the input path's one-pass assembly: shipped bf16 NWP channels -> fp32 + the five generated channels, whole rows;
+    # beside it the two passes it replaces (strided channel copy + fill)
+    n_ship = info.forcing_dim - 5
+    shipped = torch.randn(B, T, H, W, n_ship, device=dev).to(torch.bfloat16)
+    by_a = B * T * N * (2 * n_ship + 4 * info.forcing_dim) + 2 * 4 * N
+    t_as = timeit(lambda: fu.assemble_forcings(fbuf, shipped, lat, lon, scal))
+    rows.append((f"forcing tensor in one pass ({n_ship} shipped bf16 channels + 5 generated -> fp32 rows)", by_a, t_as))
+
+    def two_pass():
+        fbuf[..., :n_ship].copy_(shipped)
+        fu.fill_external_forcings_from_scalars(fbuf, n_ship, lat, lon, scal)
+
+    rows.append(("  the two passes it replaces (strided channel copy + fill), same bytes", by_a, timeit(two_pass)))
     # PSD of one prediction step, dataset statistics, un-normalisation
     from py4cast_b200 import dataset_stats as dstat
     from py4cast_b200.metrics import power_spectral_density

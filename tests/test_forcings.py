@@ -97,6 +97,40 @@ def test_gpu_fill_external_forcings_batch(cuda):
         fu.fill_external_forcings(forcing, ch0, lat.to(cuda), lon.to(cuda), dates[:2], terms)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ship_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n_ship,grid", [(16, (24, 40)), (3, (17, 23)), (0, (16, 16)), (40, (9, 31))])
+def test_gpu_assemble_forcings_one_pass(cuda, ship_dtype, n_ship, grid):
+    """The input path's one-pass assembly (shipped channels converted + five generated channels, whole rows)
+    against (i) the per-item reference tensors of oracle/forcing_ref (base.py:503-515) and (ii), bit for bit,
+    the two-pass path it replaces (strided channel copy + p4c_forcing_fill).  Odd grids (partial CTAs of 256
+    nodes), narrow and wide rows (ld 5 .. 45), more slots than one CTA column."""
+    from oracle import forcing_ref
+    from py4cast_b200 import forcingutils as fu
+
+    H, W = grid
+    g = torch.Generator().manual_seed(5)
+    lat = (torch.rand(H, W, generator=g) * 30 + 35).float()
+    lon = (torch.rand(H, W, generator=g) * 40 - 10).float()
+    dates = [dt.datetime(2022, 6, 21, 12), dt.datetime(2020, 2, 29, 23), dt.datetime(2021, 3, 9, 5, 15)]
+    terms = [dt.timedelta(hours=3 * (i + 1)) for i in range(5)]
+    B, T = len(dates), len(terms)
+    shipped = torch.randn(B, T, H, W, n_ship, generator=g).to(ship_dtype).to(cuda)
+    scalars = fu.external_forcing_scalars(dates, terms).to(cuda)
+    out = torch.full((B, T, H, W, n_ship + 5), float("nan"), device=cuda)
+    fu.assemble_forcings(out, shipped, lat.to(cuda), lon.to(cuda), scalars)
+    two = torch.full_like(out, float("nan"))
+    two[..., :n_ship].copy_(shipped)
+    fu.fill_external_forcings_from_scalars(two, n_ship, lat.to(cuda), lon.to(cuda), scalars)
+    assert torch.equal(out, two)
+    assert torch.equal(out[..., :n_ship], shipped.float())
+    for b, d in enumerate(dates):
+        blk = forcing_ref.external_forcing_block(lat, lon, d, terms)
+        assert_close(out[b, ..., n_ship:].cpu(), blk, FP32_TOL, f"assembled sample {b} external forcings")
+    with pytest.raises(ValueError):
+        fu.assemble_forcings(out[..., :-1].contiguous(), shipped, lat.to(cuda), lon.to(cuda), scalars)
+
+
 def test_forcing_oracle_matches_verbatim_reference_fresh_inputs():
     """Where the reference tree is mounted (the build container): the restatement against the
     reference's own forcingutils.py on inputs that are not in the fixtures."""
