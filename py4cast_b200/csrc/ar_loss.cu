@@ -829,6 +829,162 @@ forcing_assemble_kernel(const TS* __restrict__ src, int n_ship, const float* __r
   }
 }
 
+// Staged variant (nodes a multiple of FA_TN, 16-byte aligned shipped array, two slot buffers within 48 KB of
+// shared memory): the shipped channels of the CTA's nodes for one slot are ONE contiguous span, fetched with
+// 16-byte cp.async one slot ahead of the sweep that writes the rows (the scalar kernel above keeps a single
+// 2-byte load per thread in flight: 0.20 of the HBM peak).
+template <typename TS>
+__global__ void __launch_bounds__(256)
+forcing_assemble_staged_kernel(const TS* __restrict__ src, int n_ship, const float* __restrict__ lat,
+                               const float* __restrict__ lon, const float* __restrict__ hour,
+                               const float* __restrict__ sin_dec, const float* __restrict__ cos_dec,
+                               const float* __restrict__ dt4, int slots, int nodes, float* __restrict__ out, int ld,
+                               int slots_per_cta) {
+  extern __shared__ __align__(16) unsigned char fa_raw[];  // 2 x [FA_TN][n_ship] of TS
+  __shared__ float s_sp[FA_TN], s_cp[FA_TN], s_lon[FA_TN], s_toa[FA_TN];
+  const float kRad = 0.017453292519943295f;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * FA_TN;
+  {
+    const float phi_rad = lat[n0 + tid] * kRad;
+    s_sp[tid] = sinf(phi_rad);
+    s_cp[tid] = cosf(phi_rad);
+    s_lon[tid] = lon[n0 + tid];
+  }
+  const int t_lo = blockIdx.y * slots_per_cta, t_hi = min(slots, t_lo + slots_per_cta);
+  const int span_bytes = FA_TN * n_ship * (int)sizeof(TS);  // a multiple of 16
+  const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(fa_raw);
+  auto fetch = [&](int t, int buf) {
+    const char* g = reinterpret_cast<const char*>(src + ((long long)t * nodes + n0) * n_ship);
+    for (int i = tid; i < span_bytes / 16; i += 256) ar_cp16(b0 + buf * span_bytes + 16 * i, g + 16 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (t_lo < t_hi) fetch(t_lo, 0);
+  const int total = FA_TN * ld;
+  const int dn = 256 / ld, dc = 256 - dn * ld;
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int buf = (t - t_lo) & 1;
+    const float hr = hour[t], sd = sin_dec[t], cd = cos_dec[t];
+    const float d0 = dt4[4 * t], d1 = dt4[4 * t + 1], d2 = dt4[4 * t + 2], d3 = dt4[4 * t + 3];
+    __syncthreads();  // the sweep of slot t - 1 (buffer buf ^ 1, s_toa) is over
+    if (t + 1 < t_hi) {
+      fetch(t + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    {
+      const float hours_lcl = hr + s_lon[tid] / 15.f;
+      const float omega_rad = (15.f * (hours_lcl - 12.f)) * kRad;
+      s_toa[tid] = toa_radiation(s_sp[tid], s_cp[tid], sd, cd, omega_rad);
+    }
+    __syncthreads();
+    const TS* sr = reinterpret_cast<const TS*>(fa_raw + buf * span_bytes);
+    float* o = out + ((long long)t * nodes + n0) * ld;
+    int n = tid / ld, c = tid - n * ld;
+#pragma unroll 4
+    for (int i = tid; i < total; i += 256) {
+      float v;
+      const int e = c - n_ship;
+      if (e < 0) v = to_f32<TS>(sr[n * n_ship + c]);
+      else if (e == 4) v = s_toa[n];
+      else if (e == 0) v = d0;
+      else if (e == 1) v = d1;
+      else if (e == 2) v = d2;
+      else if (e == 3) v = d3;
+      else v = 0.f;
+      __stcs(o + i, v);
+      n += dn;
+      c += dc;
+      if (c >= ld) { c -= ld; ++n; }
+    }
+  }
+}
+
+// Row-block variant of the staged kernel (additionally: n_ship a multiple of one 16-byte vector of TS, ld a
+// multiple of 4 floats per FA_TN rows -- always -- and FA_TN * ld floats of shared memory): the fp32 rows of the
+// CTA's nodes are BUILT in shared memory (16-byte reads of the staged span, one conversion per element, the five
+// generated values per node) and leave as 16-byte vectors.  The staged kernel above decides per output element
+// which of seven sources it comes from (~30 instructions per element: issue-bound at 0.40 of the HBM peak).
+template <typename TS>
+__global__ void __launch_bounds__(256)
+forcing_assemble_rows_kernel(const TS* __restrict__ src, int n_ship, const float* __restrict__ lat,
+                             const float* __restrict__ lon, const float* __restrict__ hour,
+                             const float* __restrict__ sin_dec, const float* __restrict__ cos_dec,
+                             const float* __restrict__ dt4, int slots, int nodes, float* __restrict__ out, int ld,
+                             int slots_per_cta) {
+  constexpr int VEC = 16 / (int)sizeof(TS);
+  extern __shared__ __align__(16) unsigned char fa_raw[];  // 2 x [FA_TN][n_ship] of TS | [FA_TN][ld] fp32
+  __shared__ float s_sp[FA_TN], s_cp[FA_TN], s_lon[FA_TN];
+  const float kRad = 0.017453292519943295f;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * FA_TN;
+  {
+    const float phi_rad = lat[n0 + tid] * kRad;
+    s_sp[tid] = sinf(phi_rad);
+    s_cp[tid] = cosf(phi_rad);
+    s_lon[tid] = lon[n0 + tid];
+  }
+  const int t_lo = blockIdx.y * slots_per_cta, t_hi = min(slots, t_lo + slots_per_cta);
+  const int span_bytes = FA_TN * n_ship * (int)sizeof(TS);
+  float* rows = reinterpret_cast<float*>(fa_raw + 2 * span_bytes);
+  const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(fa_raw);
+  auto fetch = [&](int t, int buf) {
+    const char* g = reinterpret_cast<const char*>(src + ((long long)t * nodes + n0) * n_ship);
+    for (int i = tid; i < span_bytes / 16; i += 256) ar_cp16(b0 + buf * span_bytes + 16 * i, g + 16 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (t_lo < t_hi) fetch(t_lo, 0);
+  const int vpr = n_ship / VEC;  // 16-byte vectors per row of the span
+  const int nvec = FA_TN * vpr;
+  const int nout4 = FA_TN * ld / 4;
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int buf = (t - t_lo) & 1;
+    const float hr = hour[t], sd = sin_dec[t], cd = cos_dec[t];
+    const float d0 = dt4[4 * t], d1 = dt4[4 * t + 1], d2 = dt4[4 * t + 2], d3 = dt4[4 * t + 3];
+    __syncthreads();  // the rows of slot t - 1 have left; buffer buf ^ 1 was consumed
+    if (t + 1 < t_hi) {
+      fetch(t + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    {  // the five generated values of node tid
+      const float hours_lcl = hr + s_lon[tid] / 15.f;
+      const float omega_rad = (15.f * (hours_lcl - 12.f)) * kRad;
+      float* r = rows + tid * ld + n_ship;
+      r[0] = d0; r[1] = d1; r[2] = d2; r[3] = d3;
+      r[4] = toa_radiation(s_sp[tid], s_cp[tid], sd, cd, omega_rad);
+      for (int c = n_ship + 5; c < ld; ++c) rows[tid * ld + c] = 0.f;
+    }
+    __syncthreads();  // everybody's part of the span has landed
+    const uint4* sv = reinterpret_cast<const uint4*>(fa_raw + buf * span_bytes);
+    int n = tid / vpr, q = tid - n * vpr;
+    const int dn = 256 / vpr, dq = 256 - dn * vpr;
+    for (int j = tid; j < nvec; j += 256) {
+      const uint4 w = sv[j];
+      float* r = rows + n * ld + q * VEC;
+      if constexpr (sizeof(TS) == 2) {
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          r[2 * k] = __uint_as_float(ww[k] << 16);
+          r[2 * k + 1] = __uint_as_float(ww[k] & 0xFFFF0000u);
+        }
+      } else {
+        r[0] = __uint_as_float(w.x); r[1] = __uint_as_float(w.y); r[2] = __uint_as_float(w.z); r[3] = __uint_as_float(w.w);
+      }
+      n += dn;
+      q += dq;
+      if (q >= vpr) { q -= vpr; ++n; }
+    }
+    __syncthreads();
+    float4* o4 = reinterpret_cast<float4*>(out + ((long long)t * nodes + n0) * ld);
+    const float4* r4 = reinterpret_cast<const float4*>(rows);
+    for (int i = tid; i < nout4; i += 256) __stcs(o4 + i, r4[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------- AdamW
 __global__ void adamw_advance_kernel(p4c_adamw_state_t* st, float base_lr, float min_lr,
                                      long long warmup, long long total_steps, float beta1,
@@ -1172,8 +1328,9 @@ extern "C" int p4c_forcing_assemble(const void* src, int src_dtype, int32_t n_sh
               n_ship);
   P4C_REQUIRE(src_dtype == P4C_F32 || src_dtype == P4C_BF16, "forcing_assemble: bad dtype %d", src_dtype);
   const int bx = (nodes + FA_TN - 1) / FA_TN;
-  // enough CTAs for a few waves; a CTA keeps its nodes' sin / cos latitude over its slots
-  int by = (8 * kNumSMs + bx - 1) / bx;
+  // ~32 CTAs per SM over the launch (several waves of the 8 resident ones: a small tail); a CTA keeps its nodes'
+  // sin / cos latitude over its slots
+  int by = (32 * kNumSMs + bx - 1) / bx;
   if (by > slots) by = slots;
   if (by > 65535) by = 65535;
   if (by < 1) by = 1;
@@ -1181,6 +1338,31 @@ extern "C" int p4c_forcing_assemble(const void* src, int src_dtype, int32_t n_sh
   by = (slots + per - 1) / per;
   const dim3 grid(bx, by);
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t esize = src_dtype == P4C_BF16 ? 2 : 4;
+  const size_t stage = 2 * (size_t)FA_TN * n_ship * esize;
+  if (g_ar_vector_paths && n_ship > 0 && nodes % FA_TN == 0 && stage <= 44 * 1024 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int vec = (int)(16 / esize);
+    const size_t rows_smem = stage + (size_t)FA_TN * ld * sizeof(float);
+    if (n_ship % vec == 0 && rows_smem <= 44 * 1024 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      if (src_dtype == P4C_BF16)
+        forcing_assemble_rows_kernel<__nv_bfloat16><<<grid, 256, rows_smem, st>>>(
+            (const __nv_bfloat16*)src, n_ship, lat, lon, hour, sin_dec, cos_dec, datetime4, slots, nodes, out, ld, per);
+      else
+        forcing_assemble_rows_kernel<float><<<grid, 256, rows_smem, st>>>((const float*)src, n_ship, lat, lon, hour, sin_dec,
+                                                                         cos_dec, datetime4, slots, nodes, out, ld, per);
+      P4C_CHECK_LAUNCH("forcing_assemble(rows)");
+      return P4C_OK;
+    }
+    if (src_dtype == P4C_BF16)
+      forcing_assemble_staged_kernel<__nv_bfloat16><<<grid, 256, stage, st>>>(
+          (const __nv_bfloat16*)src, n_ship, lat, lon, hour, sin_dec, cos_dec, datetime4, slots, nodes, out, ld, per);
+    else
+      forcing_assemble_staged_kernel<float><<<grid, 256, stage, st>>>((const float*)src, n_ship, lat, lon, hour, sin_dec,
+                                                                     cos_dec, datetime4, slots, nodes, out, ld, per);
+    P4C_CHECK_LAUNCH("forcing_assemble(staged)");
+    return P4C_OK;
+  }
   if (src_dtype == P4C_BF16)
     forcing_assemble_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, n_ship, lat, lon, hour, sin_dec,
                                                                 cos_dec, datetime4, slots, nodes, out, ld, per);

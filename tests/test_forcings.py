@@ -99,7 +99,8 @@ def test_gpu_fill_external_forcings_batch(cuda):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ship_dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("n_ship,grid", [(16, (24, 40)), (3, (17, 23)), (0, (16, 16)), (40, (9, 31))])
+@pytest.mark.parametrize("n_ship,grid", [(16, (24, 40)), (3, (17, 23)), (0, (16, 16)), (40, (9, 31)),
+                                         (16, (32, 64)), (3, (16, 48)), (37, (16, 16))])
 def test_gpu_assemble_forcings_one_pass(cuda, ship_dtype, n_ship, grid):
     """The input path's one-pass assembly (shipped channels converted + five generated channels, whole rows)
     against (i) the per-item reference tensors of oracle/forcing_ref (base.py:503-515) and (ii), bit for bit,
@@ -124,6 +125,17 @@ def test_gpu_assemble_forcings_one_pass(cuda, ship_dtype, n_ship, grid):
     fu.fill_external_forcings_from_scalars(two, n_ship, lat.to(cuda), lon.to(cuda), scalars)
     assert torch.equal(out, two)
     assert torch.equal(out[..., :n_ship], shipped.float())
+    # grids of whole 256-node chunks take the cp.async-staged kernel: same bits as the scalar one
+    from py4cast_b200 import _lib
+
+    lib = _lib.load()
+    lib.p4c_set_ar_vector_paths(0)
+    try:
+        scalar = torch.full_like(out, float("nan"))
+        fu.assemble_forcings(scalar, shipped, lat.to(cuda), lon.to(cuda), scalars)
+    finally:
+        lib.p4c_set_ar_vector_paths(1)
+    assert torch.equal(out, scalar)
     for b, d in enumerate(dates):
         blk = forcing_ref.external_forcing_block(lat, lon, d, terms)
         assert_close(out[b, ..., n_ship:].cpu(), blk, FP32_TOL, f"assembled sample {b} external forcings")
