@@ -310,12 +310,9 @@ class DataParallelTrainer:
                 self._staged_for = None
             else:
                 self.load_inputs(batch)
-        self._graph.replay()
-        # the next batch's copies are submitted AFTER the step's graph: a caller that reads the loss every step
-        # has an idle GPU until the replay is launched, and the copy stream only needs the staging buffers,
-        # which `_staging_free` (recorded above) already guards
         if prefetch is not None:
             self.prefetch(prefetch)
+        self._graph.replay()
         self.opt.step(grad_scale=self.sync_gradients())
         return self._static_loss
 
