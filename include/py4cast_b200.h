@@ -466,6 +466,12 @@ int64_t p4c_psd_partial_floats(int64_t bt, int32_t H, int32_t W, int32_t F);
 int p4c_psd_first_row(const float* x, const float* mask, const float* wy, const float* ctab,
                       int64_t bt, int32_t H, int32_t W, int32_t F, int32_t J, float* partials,
                       float* spec, void* stream);
+/* Radial profile from the spectrum entries above (reference metrics.py:311-321 radial_bin_dct with its flat
+ * indexing, :343 batch mean): spec [B][F][2R + 1] -> prof [F][R] = mean_b spec[2r] + 0.5 mean_b spec[2r - 1 (or the
+ * last entry for r = 0)] + 0.5 mean_b spec[2r + 1]; present [R] (bytes) marks the bins that hold at least one
+ * pixel, the others are NaN (0 / 0 in the reference). */
+int p4c_psd_profile(const float* spec, const unsigned char* present, int32_t B, int32_t F, int32_t R, float* prof,
+                    void* stream);
 
 /* -------------------------------------------------------------------------
  * Dataset statistics (reference py4cast/datasets/compute_dataset_stats.py:11-127).

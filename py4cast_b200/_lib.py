@@ -211,6 +211,7 @@ SYMBOLS = {
     "p4c_acc_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "p4c_psd_partial_floats": (_i64, [_i64, _i32, _i32, _i32]),
     "p4c_psd_first_row": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "p4c_psd_profile": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "p4c_feature_stats_partial_bytes": (_i64, [_i32, _i64, _i32]),
     "p4c_feature_stats": (_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "p4c_scale_shift": (_int, [_vp, _i64, _i32, _vp, _vp, _vp]),

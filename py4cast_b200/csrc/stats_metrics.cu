@@ -109,6 +109,30 @@ __global__ void __launch_bounds__(32 * PSD_XS) psd_finalize_kernel(const float2*
   spec[(bt * F + f) * (J + 1) + j] = static_cast<float>(d * d / (static_cast<double>(W) * W));
 }
 
+// prof[f][r] = mean_b spec[b][f][2r] + 0.5 mean_b spec[b][f][left(r)] + 0.5 mean_b spec[b][f][2r + 1], left(0) = J (the
+// reference's flat index -1 wraps to the last spectrum entry), left(r) = 2r - 1; NaN where the reference's bin is
+// empty (metrics.py:311-321, 343).  Replaces a dozen latency-bound torch launches after the spectrum kernel.
+__global__ void __launch_bounds__(SM_NT) psd_profile_kernel(const float* __restrict__ spec,
+                                                            const unsigned char* __restrict__ present, int B, int F, int R,
+                                                            float* __restrict__ prof) {
+  const int i = blockIdx.x * SM_NT + threadIdx.x;
+  if (i >= F * R) return;
+  const int f = i / R, r = i - f * R;
+  const int J = 2 * R;
+  const int il = r == 0 ? J : 2 * r - 1;
+  float c = 0.f, l = 0.f, g = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* sp = spec + (static_cast<long long>(b) * F + f) * (J + 1);
+    c += sp[2 * r];
+    l += sp[il];
+    g += sp[2 * r + 1];
+  }
+  const float inv = static_cast<float>(B);
+  c = c / inv; l = l / inv; g = g / inv;
+  const float v = __fadd_rn(__fadd_rn(c, __fmul_rn(0.5f, l)), __fmul_rn(0.5f, g));
+  prof[i] = present[r] ? v : __int_as_float(0x7fc00000);
+}
+
 // ------------------------------------------------------------------------- per-feature statistics
 // x [B][X][F] (optionally minus prev, same layout): per (b, f) NaN-ignoring count, sum, sum of squares, min, max.
 // block = R rows x F features (R = SM_NT / F), grid (chunks, B); partial[(b * chunks + c) * F + f] = 5 doubles
@@ -278,6 +302,16 @@ extern "C" int p4c_psd_first_row(const float* x, const float* mask, const float*
   const dim3 fgrid(static_cast<unsigned>((J + 1 + 31) / 32), static_cast<unsigned>(F), static_cast<unsigned>(bt));
   psd_finalize_kernel<<<fgrid, 32 * PSD_XS, 0, st>>>(reinterpret_cast<const float2*>(partials), ctab, bt, H, W, F, J, spec);
   P4C_CHECK_LAUNCH("psd_finalize");
+  return P4C_OK;
+}
+
+extern "C" int p4c_psd_profile(const float* spec, const unsigned char* present, int32_t B, int32_t F, int32_t R,
+                               float* prof, void* stream) {
+  P4C_REQUIRE(spec && present && prof, "psd_profile: null pointer");
+  P4C_REQUIRE(B > 0 && F > 0 && R > 0, "psd_profile: empty problem");
+  const int n = F * R;
+  psd_profile_kernel<<<(n + SM_NT - 1) / SM_NT, SM_NT, 0, (cudaStream_t)stream>>>(spec, present, B, F, R, prof);
+  P4C_CHECK_LAUNCH("psd_profile");
   return P4C_OK;
 }
 

@@ -108,7 +108,7 @@ def power_spectral_density(x: torch.Tensor, mask: Optional[torch.Tensor] = None)
     if key not in _PSD_CONST:
         import math
 
-        present = torch.from_numpy(_psd_bins(H, W)).to(x.device)
+        present = torch.from_numpy(_psd_bins(H, W)).to(torch.uint8).to(x.device)  # one byte per bin
         wy = torch.tensor([math.cos(math.pi * (2 * y + 1) * (H - 1) / (2 * H)) for y in range(H)],
                           dtype=torch.float32, device=x.device)
         R = present.numel()
@@ -129,13 +129,11 @@ def power_spectral_density(x: torch.Tensor, mask: Optional[torch.Tensor] = None)
     spec = torch.empty(B, F, J + 1, dtype=torch.float32, device=x.device)
     check(lib.p4c_psd_first_row(ptr(xf), ptr(m), ptr(wy), ptr(ctab), B, H, W, F, J, ptr(ws), ptr(spec), stream()),
           "p4c_psd_first_row")
-    flat = spec.mean(dim=0)  # (F, J + 1): batch mean of the variance spectrum (metrics.py:343)
-    r = torch.arange(R, device=x.device)
-    center = flat[:, 2 * r]
-    right = flat[:, 2 * r + 1]
-    left = torch.cat([flat[:, J:J + 1], flat[:, 2 * r[1:] - 1]], dim=1)  # index -1 wraps to the last entry
-    prof = center + 0.5 * left + 0.5 * right
-    return torch.where(present.unsqueeze(0), prof, torch.full_like(prof, float("nan")))
+    # batch mean of the variance spectrum (metrics.py:343) and the radial bins (center + half of both neighbours,
+    # index -1 wrapping to the last entry; NaN in the bins the reference leaves empty): one small kernel
+    prof = torch.empty(F, R, dtype=torch.float32, device=x.device)
+    check(lib.p4c_psd_profile(ptr(spec), ptr(present), B, F, R, ptr(prof), stream()), "p4c_psd_profile")
+    return prof
 
 
 def _unflatten_for_psd(nt: NamedTensor, shape) -> torch.Tensor:
