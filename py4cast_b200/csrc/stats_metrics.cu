@@ -265,6 +265,45 @@ __global__ void __launch_bounds__(SM_NT) scale_shift_kernel(float* __restrict__ 
   }
 }
 
+// 16-byte variant (rows * F a multiple of 4, x 16-byte aligned): the feature of element 4 i + k repeats with period
+// P = F / gcd(F, 4) in i; blocks of a multiple of P threads striding by a multiple of P keep every thread on ONE
+// phase, so its four (scale, shift) pairs are loaded once.  Same two roundings per element: bit-identical.
+__global__ void __launch_bounds__(SM_NT) scale_shift_vec_kernel(float4* __restrict__ x4, long long n4, int F, int P,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift) {
+  const int p = threadIdx.x % P;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = (4 * p + k) % F;
+    sc[k] = scale[f];
+    sh[k] = shift[f];
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = x4[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].x = __fadd_rn(__fmul_rn(v[u].x, sc[0]), sh[0]);
+      v[u].y = __fadd_rn(__fmul_rn(v[u].y, sc[1]), sh[1]);
+      v[u].z = __fadd_rn(__fmul_rn(v[u].z, sc[2]), sh[2]);
+      v[u].w = __fadd_rn(__fmul_rn(v[u].w, sc[3]), sh[3]);
+      x4[i + u * stride] = v[u];
+    }
+  }
+  for (; i < n4; i += stride) {
+    float4 v = x4[i];
+    v.x = __fadd_rn(__fmul_rn(v.x, sc[0]), sh[0]);
+    v.y = __fadd_rn(__fmul_rn(v.y, sc[1]), sh[1]);
+    v.z = __fadd_rn(__fmul_rn(v.z, sc[2]), sh[2]);
+    v.w = __fadd_rn(__fmul_rn(v.w, sc[3]), sh[3]);
+    x4[i] = v;
+  }
+}
+
 }  // namespace p4c
 
 using namespace p4c;
@@ -347,6 +386,21 @@ extern "C" int p4c_scale_shift(float* x, int64_t rows, int32_t F, const float* s
   P4C_REQUIRE(x && scale && shift, "scale_shift: null pointer");
   P4C_REQUIRE(rows > 0 && F > 0, "scale_shift: empty problem");
   P4C_REQUIRE(F <= SM_NT, "scale_shift: F=%d > 256", F);
+  const long long total = rows * F;
+  const int g4 = (F % 4 == 0) ? 4 : (F % 2 == 0 ? 2 : 1);
+  const int P = F / g4;  // period of the feature pattern in units of 4 elements
+  if (total % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && P <= SM_NT) {
+    const int nt = (SM_NT / P) * P;
+    const long long n4 = total / 4;
+    long long blocks = (n4 + 4ll * nt - 1) / (4ll * nt);  // four vectors per thread and iteration
+    const long long cap = 32ll * kNumSMs;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    scale_shift_vec_kernel<<<static_cast<unsigned>(blocks), nt, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n4, F,
+                                                                                       P, scale, shift);
+    P4C_CHECK_LAUNCH("scale_shift(vec)");
+    return P4C_OK;
+  }
   const int R = SM_NT / F;
   const long long rpb = 64ll * R;  // 64 iterations of R rows per block
   scale_shift_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), SM_NT, 0, (cudaStream_t)stream>>>(x, rows, F, R, rpb,

@@ -130,14 +130,18 @@ def test_dataset_stats_vs_reference_formulas(cuda):
         assert int(got[nme]["mean"]) == 0 and int(got[nme]["std"]) == 1
 
 
-def test_unnormalize_is_bit_equal_to_the_reference_loop(cuda):
+@pytest.mark.parametrize("F,grid,B", [(5, (16, 20), 2), (21, (16, 20), 2), (6, (9, 10), 1), (8, (7, 9), 3),
+                                      (3, (5, 7), 1), (21, (33, 37), 5)])
+def test_unnormalize_is_bit_equal_to_the_reference_loop(cuda, F, grid, B):
+    """Feature counts with every gcd(F, 4) (vector kernel: one phase per thread), element counts that are / are not
+    multiples of 4 (the last two shapes stay on the scalar kernel), more blocks than one."""
     from py4cast_b200.dataset_stats import unnormalize_
     from py4cast_b200.datasets import synthetic_dataset_info
     from py4cast_b200.namedtensor import NamedTensor
 
-    info = synthetic_dataset_info(16, 20, num_features=5, num_forcing=2, border_size=2)
+    info = synthetic_dataset_info(grid[0], grid[1], num_features=F, num_forcing=2, border_size=2)
     fn = info.shortnames["input_output"]
-    x = torch.randn(2, 3, 16, 20, 5)
+    x = torch.randn(B, 3, grid[0], grid[1], F)
     ref = x.clone()
     for i, n in enumerate(fn):  # lightning.py:1162-1169
         ref[:, :, :, :, i] *= torch.asarray(info.stats[n]["std"])
