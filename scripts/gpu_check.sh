@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu_info.txt 2>&1
 nproc > gpurun_out/host_cores.txt
-for f in test_gpu_kernels test_gpu_tc_features test_gpu_ar_loss test_gpu_models test_gpu_trainer; do
+for f in $(cd tests && grep -l "mark.gpu" test_*.py | sed 's/\.py$//'); do
   timeout 900 python -m pytest tests/$f.py -q -m gpu -x --timeout 600 > gpurun_out/$f.log 2>&1
   echo "$f exit=$?" >> gpurun_out/summary.txt
   tail -3 gpurun_out/$f.log >> gpurun_out/summary.txt
