@@ -105,8 +105,21 @@ def test_graph_model_needs_rank_zero_setup_first(tmp_path):
 def test_unsupported_settings_fail_loudly(tmp_path):
     from helpers import pixel_meshgrid
 
-    for bad in ({"hidden_layers": 2}, {"hidden_dims": 32}, {"use_checkpointing": True}):
+    for bad in ({"hidden_layers": 2}, {"hidden_dims": 32}):
         kls, s = models.get_model_kls_and_settings("GraphLAM", {"tmp_dir": str(tmp_path), **bad})
         kls.rank_zero_setup(s, pixel_meshgrid(64, 64))
         with pytest.raises(NotImplementedError):
             kls(in_channels=2, out_channels=1, settings=s, input_shape=(64, 64))
+
+
+def test_memory_knobs_of_the_reference_are_accepted(tmp_path):
+    """`use_checkpointing` / `offload_to_cpu` (graphlam.yaml:23-24) move activations, never change a result: a
+    configuration that sets them builds (with a warning) instead of failing."""
+    from helpers import pixel_meshgrid
+
+    for knob in ({"use_checkpointing": True}, {"offload_to_cpu": True}):
+        kls, s = models.get_model_kls_and_settings("GraphLAM", {"tmp_dir": str(tmp_path), **knob})
+        kls.rank_zero_setup(s, pixel_meshgrid(64, 64))
+        with pytest.warns(UserWarning, match="no effect"):
+            m = kls(in_channels=2, out_channels=1, settings=s, input_shape=(64, 64))
+        assert m.settings is s
