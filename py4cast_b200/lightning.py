@@ -406,6 +406,14 @@ class AutoRegressiveLightning(nn.Module):
         return ar_concat(prevs, self._static_flat, forcing.contiguous(), self._x_dtype())
 
     @staticmethod
+    def match_common_features(output_names: List[str], forcing_names: List[str]) -> List[int]:
+        """Indices, in output-feature order, of the forcing features that are the coarse version of an output
+        feature: same name after the first "_"-separated token ("aro_t2m_2m" ~ "arp_t2m_2m"); every match counts,
+        as in the reference's double loop (lightning.py:546-558)."""
+        return [i for out_name in output_names for i, f_name in enumerate(forcing_names)
+                if out_name.split("_")[1:] == f_name.split("_")[1:]]
+
+    @staticmethod
     def _require_grid_layout(ndim: int) -> None:
         """The reference's NaN-mask code indexes (batch, lat, lon, features) tensors
         (lightning.py:733-748): on flattened graph inputs it raises IndexError; so does this."""
@@ -473,11 +481,8 @@ class AutoRegressiveLightning(nn.Module):
             if self.training_strategy == "downscaling_only":
                 # forcing features that are the coarse version of an output feature: same name after
                 # the first "_"-separated token (reference lightning.py:546-558)
-                self.common_features_idx = [
-                    i for out_name in self.output_feature_names
-                    for i, f_name in enumerate(batch.forcing.feature_names)
-                    if out_name.split("_")[1:] == f_name.split("_")[1:]
-                ]
+                self.common_features_idx = self.match_common_features(
+                    self.output_feature_names, batch.forcing.feature_names)
 
         inp = batch.inputs.tensor
         if not inp.is_cuda:

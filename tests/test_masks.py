@@ -24,6 +24,18 @@ def test_block_mask_matches_the_reference_loop(name):
     assert 0 < float(want.float().mean()) < 1  # the case does mask something, and not everything
 
 
+def test_downscaling_feature_matching_follows_the_reference_rule():
+    """Names match on everything after the first "_" token; names without "_" all match each other (the reference's
+    rule, lightning.py:549-557, kept as it is); the golden case resolves to the permutation the reference found."""
+    from py4cast_b200.lightning import AutoRegressiveLightning as L
+
+    p = load_golden("ar_masks.pt")["ds_plain"]["problem"]
+    assert L.match_common_features(p["feature_names"], p["forcing_names"]) == [1, 0, 2]
+    assert L.match_common_features(["aro_t2m_2m"], ["arp_tp_0m", "x_t2m_2m", "arp_t2m_10m"]) == [1]
+    assert L.match_common_features(["w0", "w1"], ["f0", "f1", "f2"]) == [0, 1, 2, 0, 1, 2]
+    assert L.match_common_features(["aro_u10_10m"], ["arp_t2m_2m"]) == []
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_masked_rollout_and_loss_vs_reference_golden(cuda, name):
